@@ -262,6 +262,15 @@ def count_windows(b: Frame, col: int, first_window_start: int, interval: int) ->
     return go_div(last - first_window_start, interval) + 1
 
 
+class NewRollingError(ValueError):
+    """Aggregate/Interpolate computed `frame` but re-wrapping it in a Rolling failed
+    (e.g. trailing null timestamps leave every window unset -> first output time is nil)."""
+
+    def __init__(self, msg, frame):
+        super().__init__(msg)
+        self.frame = frame
+
+
 class IntervalRolling:
     """rolling.intervalRolling (rolling.go:31-43) with its iterator and drivers."""
 
@@ -382,7 +391,10 @@ class IntervalRolling:
             types.append(typ)
             cols.append(buf)
         out = Frame(names, types, cols)
-        return IntervalRolling(out, new_interval_col, r.interval, r.options)
+        try:                                             # aggregation.go:139-142
+            return IntervalRolling(out, new_interval_col, r.interval, r.options)
+        except (ValueError, TypeError) as e:
+            raise NewRollingError(f"newIntervalRolling: {e.args[0]}", out)
 
     # ---- Interpolate driver: rolling/interpolation.go:30-161 ----------------
     def interpolate(self, *interps: "ColInterpolation") -> "IntervalRolling":
@@ -413,7 +425,10 @@ class IntervalRolling:
         b = append_frames(bows)
         if b is None:
             b = r.bow.new_empty_slice()
-        return IntervalRolling(b, new_interval_col, r.interval, r.options)
+        try:                                             # interpolation.go:63-66
+            return IntervalRolling(b, new_interval_col, r.interval, r.options)
+        except (ValueError, TypeError) as e:
+            raise NewRollingError(f"newIntervalRolling: {e.args[0]}", b)
 
     def _interpolate_window(self, interps, window: Window) -> Frame:   # interpolation.go:118-161
         first_col_value = -1

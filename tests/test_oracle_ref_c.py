@@ -1,0 +1,167 @@
+"""oracle/ref.c (C restatement) against (1) the reference's golden vectors and
+(2) the literal transliteration oracle/literal.py on randomised inputs that cover
+what the reference's own tests do not: null / duplicate / negative timestamps,
+Inclusive, PrevRow, int64 value columns, NaN / +-0 / Inf, sliced (offset) buffers."""
+import numpy as np
+import pytest
+
+from oracle import literal as L
+from oracle import refc as R
+from tests import helpers as H
+from tests.golden import reference_vectors as G
+
+AGG_NAMES = ["WindowStart", "Count", "Sum", "ArithmeticMean", "Min", "Max", "First", "Last",
+             "IntegralStep", "IntegralTrapezoid", "WeightedAverageStep", "WeightedAverageLinear"]
+LIT_INTERP = {"WindowStart": L.InterpWindowStart, "Linear": L.InterpLinear,
+              "StepPrevious": L.InterpStepPrevious, "None_": L.InterpNone}
+
+
+def ref_rows(frame_cols, interval, aggs, **opts):
+    fr = R.Frame(frame_cols)
+    r = R.RefRolling(fr, 0, interval, **opts)
+    out = r.aggregate(aggs)
+    return H.lists_from_np(out)
+
+
+@pytest.mark.parametrize("name,cols,interval,offset,expected", G.NUM_WINDOWS, ids=[c[0] for c in G.NUM_WINDOWS])
+def test_num_windows(name, cols, interval, offset, expected):
+    fr = R.Frame(H.np_cols_from_lists(cols, [L.INT64, L.FLOAT64]))
+    assert R.RefRolling(fr, 0, interval, offset=offset).num_windows == expected
+
+
+def test_ctor_errors():
+    fr = R.Frame(H.np_cols_from_lists([[0], [1.0]], [L.INT64, L.FLOAT64]))
+    for itv in (0, -1):
+        with pytest.raises(R.RefError, match="EINVAL"):
+            R.RefRolling(fr, 0, itv)
+    with pytest.raises(R.RefError, match="ETYPE"):
+        R.RefRolling(fr, 1, 1)
+
+
+@pytest.mark.parametrize("name,opts,expected", G.ITERATE, ids=[c[0] for c in G.ITERATE])
+def test_iterate(name, opts, expected):
+    cols = H.np_cols_from_lists(G.ITERATE_COLS, [L.INT64, L.FLOAT64])
+    w = R.RefRolling(R.Frame(cols), 0, G.ITERATE_INTERVAL, **opts).windows()
+    got = []
+    for k in range(len(w["lo"])):
+        lo, hi = int(w["lo"][k]), int(w["hi"][k])
+        got.append((k, int(w["first_value"][k]), int(w["first_value"][k]) + G.ITERATE_INTERVAL,
+                    int(w["first_index"][k]), G.ITERATE_COLS[0][lo:hi], G.ITERATE_COLS[1][lo:hi]))
+    assert got == expected
+
+
+@pytest.mark.parametrize("agg,fixture,factor,vtype,expected,cite", G.AGGREGATIONS,
+                         ids=[f"{c[0]}-{c[1]}-{c[2]}" for c in G.AGGREGATIONS])
+def test_aggregations_golden(agg, fixture, factor, vtype, expected, cite):
+    rows = G.FIXTURES[fixture]
+    cols = H.np_cols_from_lists([[r[0] for r in rows], [r[1] for r in rows]], [L.INT64, L.FLOAT64])
+    out = ref_rows(cols, 10, [("WindowStart", 0), (agg, 1, [factor] if factor is not None else [])])
+    H.assert_cols_equal(out, [[r[0] for r in expected], [r[1] for r in expected]], cite)
+
+
+@pytest.mark.parametrize("name,kind,rows,offset,expected,cite", G.INTERPOLATIONS,
+                         ids=[c[0] for c in G.INTERPOLATIONS])
+def test_interpolations_golden(name, kind, rows, offset, expected, cite):
+    cols = H.np_cols_from_lists([[r[0] for r in rows], [r[1] for r in rows]], [L.INT64, L.FLOAT64])
+    r = R.RefRolling(R.Frame(cols), 0, 2, offset=offset)
+    out = H.lists_from_np(r.interpolate(["WindowStart", "None_" if kind == "None" else kind]))
+    H.assert_cols_equal(out, [[r[0] for r in expected], [r[1] for r in expected]], cite)
+
+
+@pytest.mark.parametrize("name,times,offset,expected", G.INTERP_WINDOWSTART,
+                         ids=[c[0] for c in G.INTERP_WINDOWSTART])
+def test_interp_windowstart_golden(name, times, offset, expected):
+    r = R.RefRolling(R.Frame(H.np_cols_from_lists([times], [L.INT64])), 0, 2, offset=offset)
+    H.assert_cols_equal(H.lists_from_np(r.interpolate(["WindowStart"])), [expected])
+
+
+def test_no_interval_col_error():
+    fr = R.Frame(H.np_cols_from_lists(G.AGG_DRIVER_COLS, [L.INT64, L.FLOAT64]))
+    with pytest.raises(R.RefError, match="ENOINTERVALCOL"):
+        R.RefRolling(fr, 0, 10).aggregate([("Count", 1)])
+
+
+# ---------------------------------------------------------------- differential
+def _random_case(seed):
+    rng = np.random.default_rng(seed)
+    n = int(rng.choice([0, 1, 2, 3, 7, 20, 60, 150]))
+    kind = str(rng.choice(["dense", "sparse", "bursty", "regular"]))
+    t = H.random_times(rng, n, kind)
+    tmask = None
+    if seed % 5 == 0 and n > 1:            # null timestamps (never the first row)
+        tmask = rng.random(n) >= 0.15
+        tmask[0] = True
+    cols = [(t, tmask),
+            H.random_values(rng, n, np.float64, float(rng.choice([0.0, 0.3, 0.9])), specials=seed % 3 == 0),
+            H.random_values(rng, n, np.int64, float(rng.choice([0.0, 0.3])))]
+    interval = int(rng.choice([1, 2, 5, 10, 37]))
+    offset = int(rng.integers(-50, 50))
+    inclusive = bool(rng.integers(0, 2))
+    prev = None
+    if seed % 4 == 0:
+        pt = np.array([int(t[0]) - int(rng.integers(1, 9)) if n else 0], dtype=np.int64)
+        prev = [(pt, None if seed % 8 else np.array([False])),
+                (np.array([float(rng.normal())]), None if seed % 3 else np.array([False])),
+                (np.array([int(rng.integers(-9, 9))], dtype=np.int64), None)]
+    return cols, interval, offset, inclusive, prev
+
+
+@pytest.mark.parametrize("seed", range(160))
+def test_aggregate_vs_literal(seed):
+    cols, interval, offset, inclusive, _ = _random_case(seed)
+    buf_off = seed % 3 * 5          # sliced Arrow buffers with a non-zero element/bit offset
+    r = R.RefRolling(R.Frame(cols, offset=buf_off), 0, interval, offset=offset, inclusive=inclusive)
+    lit = L.IntervalRolling.create(H.literal_frame(cols), "c0", interval, L.Options(offset, inclusive))
+    assert r.num_windows == lit.num_windows
+    for vcol in (1, 2):
+        names = AGG_NAMES if seed % 2 else [a for a in AGG_NAMES if "Trapezoid" not in a and "Linear" not in a]
+        specs = [("WindowStart", 0)] + [(a, vcol, [0.5] if (seed + i) % 7 == 0 else []) for i, a in enumerate(names)]
+        got = H.lists_from_np(r.aggregate(specs))
+        la = [L.WindowStart("c0")]
+        for s in specs[1:]:
+            a = getattr(L, s[0])(f"c{vcol}")
+            la.append(a.set_transformations(*[L.Factor(f) for f in s[2]]).rename_output(f"o{len(la)}"))
+        try:
+            want = lit.aggregate(*la).bow.materialize()
+        except L.NewRollingError as e:      # reference quirk: result computed, re-wrapping fails
+            want = e.frame.materialize()
+        H.assert_cols_equal(got, want, f"seed {seed} col {vcol}")
+
+
+@pytest.mark.parametrize("seed", range(160))
+def test_windows_vs_literal(seed):
+    cols, interval, offset, inclusive, _ = _random_case(seed)
+    w = R.RefRolling(R.Frame(cols), 0, interval, offset=offset, inclusive=inclusive).windows()
+    lit = L.IntervalRolling.create(H.literal_frame(cols), "c0", interval, L.Options(offset, inclusive))
+    k = 0
+    while lit.has_next():
+        wi, lw = lit.next()
+        assert wi == k
+        assert (lw.first_index, lw.first_value, lw.is_inclusive) == \
+            (int(w["first_index"][k]), int(w["first_value"][k]), bool(w["is_inclusive"][k]))
+        if lw.bow.num_rows() == 0:
+            assert int(w["lo"][k]) == int(w["hi"][k])
+        else:
+            assert (lw.bow.lo, lw.bow.hi) == (int(w["lo"][k]), int(w["hi"][k]))
+        k += 1
+    assert k == len(w["lo"])
+
+
+@pytest.mark.parametrize("seed", range(160))
+def test_interpolate_vs_literal(seed):
+    cols, interval, offset, inclusive, prev = _random_case(seed)
+    if cols[0][1] is not None and not cols[0][1][-1]:
+        pytest.skip("trailing null timestamp: the reference panics in AppendBows on the nil window bows")
+    rng = np.random.default_rng(1000 + seed)
+    ops = ["WindowStart", str(rng.choice(["Linear", "StepPrevious", "None_"])),
+           str(rng.choice(["Linear", "StepPrevious", "None_"]))]
+    r = R.RefRolling(R.Frame(cols, offset=seed % 2 * 3), 0, interval, offset=offset, inclusive=inclusive,
+                     prev_row=R.Frame(prev) if prev else None)
+    got = H.lists_from_np(r.interpolate(ops))
+    lit = L.IntervalRolling.create(H.literal_frame(cols), "c0", interval,
+                                   L.Options(offset, inclusive, H.literal_frame(prev) if prev else None))
+    try:
+        want = lit.interpolate(*[LIT_INTERP[o](f"c{j}") for j, o in enumerate(ops)]).bow.materialize()
+    except L.NewRollingError as e:
+        want = e.frame.materialize()
+    H.assert_cols_equal(got, want, f"seed {seed}")
