@@ -1,0 +1,925 @@
+// C ABI of libbowgpu.so (include/bowgpu.h): contexts, device-resident frames, the rolling object and
+// the Aggregate / bounds drivers.  Host logic only — every row of data is touched by CUDA kernels.
+#include "../../include/bowgpu.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+using namespace bowgpu;
+
+// ================================================================================================
+// internal objects
+// ================================================================================================
+struct bowgpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    std::string err;
+    // error flags written by kernels (ST_*), sticky until read
+    int32_t *d_status = nullptr;
+    int64_t *d_scalars = nullptr;  // 8 device int64 for tiny results
+    // scratch arena (grow only, bump allocated per call)
+    uint8_t *arena = nullptr;
+    size_t arena_cap = 0, arena_top = 0;
+    // pinned staging for pageable host memory
+    uint8_t *pinned[2] = {nullptr, nullptr};
+    cudaEvent_t pinned_ev[2] = {nullptr, nullptr};
+    size_t pinned_bytes = 0;
+    // timing
+    int timing = 0;  // 0 off, 1 per call, 2 accumulate over calls
+    cudaEvent_t ev_total[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_main;  // pairs
+    int ev_main_used = 0;
+    int launches = 0, main_launches = 0;
+};
+
+struct DevCol {
+    uint64_t *values = nullptr;
+    uint8_t *validity = nullptr;  // bit offset 0, padded to 16 bytes, padding zero; null = all valid
+    int32_t dtype = 0;
+    int64_t null_count = 0;
+    bool own_values = false, own_validity = false;
+};
+
+struct bowgpu_frame {
+    bowgpu_ctx *ctx = nullptr;
+    int64_t n = 0;
+    std::vector<DevCol> cols;
+};
+
+struct PrevCell {
+    uint64_t bits = 0;
+    int32_t valid = 0;
+    int32_t dtype = 0;
+};
+
+struct bowgpu_rolling {
+    bowgpu_frame *frame = nullptr;
+    int32_t time_col = 0;
+    int64_t interval = 0, offset = 0;
+    int32_t inclusive = 0;
+    int64_t s0 = 0, W = 0;
+    int64_t t_first = 0, t_last = 0;
+    int64_t early_rows = 0;  // rows with t < s0
+    int64_t t_after_early = 0;
+    bool has_after_early = false;
+    bool has_prev = false;
+    std::vector<PrevCell> prev;
+};
+
+namespace {
+
+struct Guard {  // selects the ctx device for the duration of a call (cgo calls land on any OS thread)
+    int prev = -1;
+    explicit Guard(const bowgpu_ctx *c) {
+        cudaGetDevice(&prev);
+        if (prev != c->device) cudaSetDevice(c->device);
+    }
+    ~Guard() {}
+};
+
+int32_t fail(bowgpu_ctx *c, int32_t code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                                  \
+    do {                                                                                                          \
+        cudaError_t e__ = (cudaError_t)(call);                                                                    \
+        if (e__ != cudaSuccess)                                                                                   \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? BOWGPU_ENOMEM : BOWGPU_ECUDA, "%s: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e__), __FILE__, __LINE__);                                             \
+    } while (0)
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+int64_t bitmap_bytes_padded(int64_t n) { return (int64_t)align_up((size_t)((n + 7) / 8), 16) + 16; }
+
+// ---- scratch arena ---------------------------------------------------------------------------------
+int32_t arena_reserve(bowgpu_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->arena_cap) return BOWGPU_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->arena) cudaFree(ctx->arena);
+    ctx->arena = nullptr;
+    ctx->arena_cap = 0;
+    size_t cap = align_up(bytes + (bytes >> 3), (size_t)1 << 20);
+    CK(cudaMalloc(&ctx->arena, cap));
+    ctx->arena_cap = cap;
+    return BOWGPU_OK;
+}
+void arena_reset(bowgpu_ctx *ctx) { ctx->arena_top = 0; }
+void *arena_take(bowgpu_ctx *ctx, size_t bytes) {
+    size_t off = align_up(ctx->arena_top, 256);
+    if (off + bytes > ctx->arena_cap) return nullptr;
+    ctx->arena_top = off + bytes;
+    return ctx->arena + off;
+}
+
+// ---- host <-> device copies (complete before return) -------------------------------------------------
+bool is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+int32_t ensure_pinned(bowgpu_ctx *ctx) {
+    if (ctx->pinned[0]) return BOWGPU_OK;
+    ctx->pinned_bytes = (size_t)32 << 20;
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaHostAlloc((void **)&ctx->pinned[i], ctx->pinned_bytes, cudaHostAllocDefault));
+        CK(cudaEventCreateWithFlags(&ctx->pinned_ev[i], cudaEventDisableTiming));
+    }
+    return BOWGPU_OK;
+}
+
+// Pageable sources go through two pinned chunks (CPU memcpy of chunk i+1 overlaps the DMA of chunk i);
+// pinned sources are DMA'd directly.  The caller synchronizes the stream before returning to Go.
+int32_t copy_h2d(bowgpu_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (bytes == 0) return BOWGPU_OK;
+    if (is_pinned(src)) {
+        CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return BOWGPU_OK;
+    }
+    int32_t rc = ensure_pinned(ctx);
+    if (rc) return rc;
+    size_t done = 0;
+    int b = 0;
+    while (done < bytes) {
+        size_t m = std::min(ctx->pinned_bytes, bytes - done);
+        CK(cudaEventSynchronize(ctx->pinned_ev[b]));
+        memcpy(ctx->pinned[b], (const char *)src + done, m);
+        CK(cudaMemcpyAsync((char *)dst + done, ctx->pinned[b], m, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaEventRecord(ctx->pinned_ev[b], ctx->stream));
+        done += m;
+        b ^= 1;
+    }
+    return BOWGPU_OK;
+}
+
+int32_t copy_d2h(bowgpu_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (bytes == 0) return BOWGPU_OK;
+    if (is_pinned(dst)) {
+        CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        return BOWGPU_OK;
+    }
+    int32_t rc = ensure_pinned(ctx);
+    if (rc) return rc;
+    // ping-pong: DMA chunk i+1 while the CPU copies chunk i out of the pinned buffer
+    size_t off = 0, prev_off = 0, prev_len = 0;
+    int b = 0, prev_b = -1;
+    while (off < bytes) {
+        const size_t m = std::min(ctx->pinned_bytes, bytes - off);
+        CK(cudaMemcpyAsync(ctx->pinned[b], (const char *)src + off, m, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaEventRecord(ctx->pinned_ev[b], ctx->stream));
+        if (prev_b >= 0) {
+            CK(cudaEventSynchronize(ctx->pinned_ev[prev_b]));
+            memcpy((char *)dst + prev_off, ctx->pinned[prev_b], prev_len);
+        }
+        prev_b = b;
+        prev_off = off;
+        prev_len = m;
+        off += m;
+        b ^= 1;
+    }
+    if (prev_b >= 0) {
+        CK(cudaEventSynchronize(ctx->pinned_ev[prev_b]));
+        memcpy((char *)dst + prev_off, ctx->pinned[prev_b], prev_len);
+    }
+    return BOWGPU_OK;
+}
+
+void count_launch(bowgpu_ctx *ctx, int n = 1, bool main = false) {
+    ctx->launches += n;
+    if (main) ctx->main_launches += n;
+}
+
+int32_t check_status(bowgpu_ctx *ctx) {  // stream must be synchronized by the caller's copy
+    int32_t st = 0;
+    CK(cudaMemcpyAsync(&st, ctx->d_status, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (st) {
+        CK(cudaMemsetAsync(ctx->d_status, 0, 4, ctx->stream));
+        if (st & ST_UNSORTED) return fail(ctx, BOWGPU_EUNSORTED, "time column is not sorted ascending");
+    }
+    return BOWGPU_OK;
+}
+
+void timing_begin(bowgpu_ctx *ctx) {
+    if (ctx->timing != 2) {  // mode 2 accumulates over calls until bowgpu_ctx_last_timing
+        ctx->launches = 0;
+        ctx->main_launches = 0;
+        ctx->ev_main_used = 0;
+    }
+    if (ctx->timing) cudaEventRecord(ctx->ev_total[0], ctx->stream);
+}
+void timing_end(bowgpu_ctx *ctx) {
+    if (ctx->timing) cudaEventRecord(ctx->ev_total[1], ctx->stream);
+}
+// returns a pair of events for one main-kernel launch (null when timing is off)
+void timing_main_pair(bowgpu_ctx *ctx, cudaEvent_t *e0, cudaEvent_t *e1) {
+    *e0 = *e1 = nullptr;
+    if (!ctx->timing) return;
+    if ((size_t)ctx->ev_main_used + 2 > ctx->ev_main.size()) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        ctx->ev_main.push_back(a);
+        ctx->ev_main.push_back(b);
+    }
+    *e0 = ctx->ev_main[ctx->ev_main_used++];
+    *e1 = ctx->ev_main[ctx->ev_main_used++];
+}
+
+WindowGeom make_geom(const bowgpu_rolling *r, bool inclusive_eff) {
+    WindowGeom g;
+    g.n = r->frame->n;
+    g.s0 = r->s0;
+    g.W = r->W;
+    g.div.d = (uint64_t)r->interval;
+    g.div.inv_rd = std::nextafter(1.0 / (double)r->interval, 0.0);
+    g.early_rows = r->early_rows;
+    // rows before s0 stay in window 0 iff that window holds a row in [S0, E0) — or exactly at E0 when the
+    // iteration is inclusive (rolling.go:194-211: they are only part of the slice if lastRowIndex is set)
+    g.early_keep = 0;
+    if (r->early_rows > 0 && r->has_after_early) {
+        const uint64_t rel = (uint64_t)r->t_after_early - (uint64_t)r->s0;
+        g.early_keep = rel < (uint64_t)r->interval || (inclusive_eff && rel == (uint64_t)r->interval);
+    }
+    g._pad = 0;
+    return g;
+}
+
+bool agg_is_basic(int op) { return op >= BOWGPU_AGG_COUNT && op <= BOWGPU_AGG_LAST; }
+bool agg_is_integral(int op) { return op >= BOWGPU_AGG_INTEGRAL_STEP && op <= BOWGPU_AGG_WAVG_LINEAR; }
+
+}  // namespace
+
+// ================================================================================================
+// context
+// ================================================================================================
+extern "C" int32_t bowgpu_abi_version(void) { return BOWGPU_ABI_VERSION; }
+
+extern "C" const char *bowgpu_status_string(int32_t s) {
+    switch (s) {
+    case BOWGPU_OK: return "ok";
+    case BOWGPU_EINVAL: return "invalid argument";
+    case BOWGPU_ETYPE: return "unsupported column type";
+    case BOWGPU_EFIRSTNULL: return "first value of the interval column is null";
+    case BOWGPU_EPREVROW: return "prevRow must have only one row";
+    case BOWGPU_ENOINTERVALCOL: return "must keep interval column";
+    case BOWGPU_ECAPACITY: return "output capacity too small";
+    case BOWGPU_EUNSORTED: return "interval column is not sorted";
+    case BOWGPU_ENULLTIME: return "interval column holds nulls";
+    case BOWGPU_ECUDA: return "CUDA error";
+    case BOWGPU_ENOMEM: return "out of memory";
+    case BOWGPU_EUNSUPPORTED: return "not supported by the GPU backend";
+    }
+    return "unknown status";
+}
+
+extern "C" int32_t bowgpu_ctx_create(int32_t device, void *stream, bowgpu_ctx **out) {
+    if (!out) return BOWGPU_EINVAL;
+    *out = nullptr;
+    bowgpu_ctx *ctx = new (std::nothrow) bowgpu_ctx();
+    if (!ctx) return BOWGPU_ENOMEM;
+    ctx->device = device;
+    auto bail = [&](int32_t code) {
+        delete ctx;
+        return code;
+    };
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return bail(BOWGPU_ECUDA);
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return bail(BOWGPU_ECUDA);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(BOWGPU_ECUDA);
+    if (prop.major != 10) return bail(BOWGPU_EUNSUPPORTED);  // kernels are built for sm_100a only
+    ctx->sm_count = prop.multiProcessorCount;
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(BOWGPU_ECUDA);
+        ctx->own_stream = true;
+    }
+    if (cudaMalloc(&ctx->d_status, 256) != cudaSuccess) return bail(BOWGPU_ENOMEM);
+    ctx->d_scalars = (int64_t *)((char *)ctx->d_status + 64);
+    cudaMemsetAsync(ctx->d_status, 0, 256, ctx->stream);
+    cudaEventCreate(&ctx->ev_total[0]);
+    cudaEventCreate(&ctx->ev_total[1]);
+    cudaStreamSynchronize(ctx->stream);
+    *out = ctx;
+    return BOWGPU_OK;
+}
+
+extern "C" void bowgpu_ctx_destroy(bowgpu_ctx *ctx) {
+    if (!ctx) return;
+    Guard gd(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->d_status) cudaFree(ctx->d_status);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
+        if (ctx->pinned_ev[i]) cudaEventDestroy(ctx->pinned_ev[i]);
+        if (ctx->ev_total[i]) cudaEventDestroy(ctx->ev_total[i]);
+    }
+    for (auto e : ctx->ev_main) cudaEventDestroy(e);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char *bowgpu_last_error(const bowgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int32_t bowgpu_ctx_synchronize(bowgpu_ctx *ctx) {
+    if (!ctx) return BOWGPU_EINVAL;
+    Guard gd(ctx);
+    return check_status(ctx);
+}
+
+extern "C" int32_t bowgpu_ctx_enable_timing(bowgpu_ctx *ctx, int32_t enable) {
+    if (!ctx) return BOWGPU_EINVAL;
+    ctx->timing = enable;
+    ctx->launches = ctx->main_launches = ctx->ev_main_used = 0;
+    return BOWGPU_OK;
+}
+
+extern "C" int32_t bowgpu_ctx_last_timing(bowgpu_ctx *ctx, bowgpu_timing *out) {
+    if (!ctx || !out) return BOWGPU_EINVAL;
+    Guard gd(ctx);
+    memset(out, 0, sizeof *out);
+    out->launches = ctx->launches;
+    out->main_launches = ctx->main_launches;
+    if (!ctx->timing) return BOWGPU_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventElapsedTime(&out->total_ms, ctx->ev_total[0], ctx->ev_total[1]));
+    float acc = 0.f;
+    for (int i = 0; i + 1 < ctx->ev_main_used; i += 2) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->ev_main[i], ctx->ev_main[i + 1]));
+        acc += ms;
+    }
+    out->main_ms = acc;
+    if (ctx->timing == 2) ctx->launches = ctx->main_launches = ctx->ev_main_used = 0;
+    return BOWGPU_OK;
+}
+
+extern "C" int32_t bowgpu_ctx_sm_count(const bowgpu_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+
+// ================================================================================================
+// frames
+// ================================================================================================
+namespace {
+
+void free_col(DevCol &c) {
+    if (c.own_values && c.values) cudaFree(c.values);
+    if (c.own_validity && c.validity) cudaFree(c.validity);
+    c = DevCol();
+}
+
+// allocates an owned column of n rows (values padded to a 16-byte multiple + one spare vector)
+int32_t alloc_col(bowgpu_ctx *ctx, DevCol &c, int64_t n, int32_t dtype, bool with_validity) {
+    c.dtype = dtype;
+    size_t vb = align_up((size_t)n * 8, 16) + 32;
+    CK(cudaMalloc((void **)&c.values, vb));
+    c.own_values = true;
+    if (with_validity) {
+        size_t bb = (size_t)bitmap_bytes_padded(n);
+        CK(cudaMalloc((void **)&c.validity, bb));
+        c.own_validity = true;
+        CK(cudaMemsetAsync(c.validity, 0, bb, ctx->stream));
+    }
+    return BOWGPU_OK;
+}
+
+int32_t count_nulls(bowgpu_ctx *ctx, DevCol &c, int64_t n) {
+    unsigned long long *d = (unsigned long long *)ctx->d_scalars;
+    CK(cudaMemsetAsync(d, 0, 8, ctx->stream));
+    CK(launch_bitmap_popcount(c.validity, n, d, ctx->stream));
+    unsigned long long h = 0;
+    CK(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    c.null_count = n - (int64_t)h;
+    return BOWGPU_OK;
+}
+
+}  // namespace
+
+extern "C" int32_t bowgpu_frame_create(bowgpu_ctx *ctx, const bowgpu_col *cols, int32_t ncols, int32_t mem,
+                                       bowgpu_frame **out) {
+    if (!ctx || !out || ncols < 0 || (ncols > 0 && !cols)) return BOWGPU_EINVAL;
+    *out = nullptr;
+    Guard gd(ctx);
+    const int64_t n = ncols ? cols[0].length : 0;
+    for (int j = 0; j < ncols; ++j) {
+        if (cols[j].length != n || cols[j].offset < 0 || n < 0)
+            return fail(ctx, BOWGPU_EINVAL, "column %d: length %lld != %lld", j, (long long)cols[j].length, (long long)n);
+        if (cols[j].dtype != BOWGPU_FLOAT64 && cols[j].dtype != BOWGPU_INT64)
+            return fail(ctx, BOWGPU_ETYPE, "column %d: only Int64 / Float64 columns run on the GPU path", j);
+        if (n > 0 && !cols[j].values) return fail(ctx, BOWGPU_EINVAL, "column %d: null values buffer", j);
+    }
+    bowgpu_frame *f = new (std::nothrow) bowgpu_frame();
+    if (!f) return BOWGPU_ENOMEM;
+    f->ctx = ctx;
+    f->n = n;
+    f->cols.resize(ncols);
+    int32_t rc = BOWGPU_OK;
+    arena_reset(ctx);
+    for (int j = 0; j < ncols && rc == BOWGPU_OK; ++j) {
+        const bowgpu_col &s = cols[j];
+        DevCol &c = f->cols[j];
+        const bool want_validity = s.validity != nullptr && s.null_count != 0 && n > 0;
+        const char *vsrc = (const char *)s.values + s.offset * 8;
+        if (mem == BOWGPU_MEM_DEVICE && n > 0 && ((uintptr_t)vsrc & 15) == 0) {
+            c.values = (uint64_t *)vsrc;  // zero copy
+            c.dtype = s.dtype;
+            if (want_validity) {
+                size_t bb = (size_t)bitmap_bytes_padded(n);
+                cudaError_t e = cudaMalloc((void **)&c.validity, bb);
+                if (e != cudaSuccess) {
+                    rc = fail(ctx, BOWGPU_ENOMEM, "cudaMalloc(%zu): %s", bb, cudaGetErrorString(e));
+                    break;
+                }
+                c.own_validity = true;
+            }
+        } else {
+            rc = alloc_col(ctx, c, n, s.dtype, want_validity);
+            if (rc) break;
+            if (n > 0) {
+                if (mem == BOWGPU_MEM_DEVICE) {
+                    cudaError_t e = cudaMemcpyAsync(c.values, vsrc, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream);
+                    if (e != cudaSuccess) rc = fail(ctx, BOWGPU_ECUDA, "D2D copy: %s", cudaGetErrorString(e));
+                } else {
+                    rc = copy_h2d(ctx, c.values, vsrc, (size_t)n * 8);
+                }
+            }
+        }
+        if (rc == BOWGPU_OK && want_validity) {
+            const int64_t byte0 = s.offset >> 3;
+            const int64_t bit_off = s.offset & 7;
+            const int64_t nbytes = ((s.offset + n + 7) >> 3) - byte0;
+            const uint8_t *bsrc = s.validity + byte0;
+            const int64_t dst_bytes = bitmap_bytes_padded(n);
+            if (mem == BOWGPU_MEM_HOST) {
+                rc = arena_reserve(ctx, (size_t)nbytes + 256);
+                if (rc) break;
+                arena_reset(ctx);
+                uint8_t *tmp = (uint8_t *)arena_take(ctx, (size_t)nbytes);
+                rc = copy_h2d(ctx, tmp, bsrc, (size_t)nbytes);
+                bsrc = tmp;
+            }
+            if (rc == BOWGPU_OK) {
+                int e = launch_bitmap_realign(bsrc, bit_off, n, c.validity, dst_bytes, ctx->stream);
+                if (e) rc = fail(ctx, BOWGPU_ECUDA, "bitmap_realign: %s", cudaGetErrorString((cudaError_t)e));
+            }
+            if (rc == BOWGPU_OK) {
+                c.null_count = s.null_count;
+                if (s.null_count < 0) rc = count_nulls(ctx, c, n);
+                if (rc == BOWGPU_OK && c.null_count == 0) {  // bitmap without nulls: drop it (faster kernels)
+                    cudaStreamSynchronize(ctx->stream);
+                    if (c.own_validity) cudaFree(c.validity);
+                    c.validity = nullptr;
+                    c.own_validity = false;
+                }
+            }
+        }
+    }
+    if (rc == BOWGPU_OK) {
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);  // Go may release its buffers after return
+        if (e != cudaSuccess) rc = fail(ctx, BOWGPU_ECUDA, "frame upload: %s", cudaGetErrorString(e));
+    }
+    if (rc != BOWGPU_OK) {
+        cudaStreamSynchronize(ctx->stream);
+        for (auto &c : f->cols) free_col(c);
+        delete f;
+        return rc;
+    }
+    *out = f;
+    return BOWGPU_OK;
+}
+
+extern "C" void bowgpu_frame_destroy(bowgpu_frame *f) {
+    if (!f) return;
+    Guard gd(f->ctx);
+    cudaStreamSynchronize(f->ctx->stream);
+    for (auto &c : f->cols) free_col(c);
+    delete f;
+}
+
+extern "C" int64_t bowgpu_frame_num_rows(const bowgpu_frame *f) { return f ? f->n : 0; }
+extern "C" int32_t bowgpu_frame_num_cols(const bowgpu_frame *f) { return f ? (int32_t)f->cols.size() : 0; }
+extern "C" int32_t bowgpu_frame_col_dtype(const bowgpu_frame *f, int32_t col) {
+    return (f && col >= 0 && col < (int32_t)f->cols.size()) ? f->cols[col].dtype : 0;
+}
+extern "C" int32_t bowgpu_frame_col_has_validity(const bowgpu_frame *f, int32_t col) {
+    return (f && col >= 0 && col < (int32_t)f->cols.size()) ? f->cols[col].validity != nullptr : 0;
+}
+extern "C" int32_t bowgpu_frame_col_device_ptrs(const bowgpu_frame *f, int32_t col, void **values, uint8_t **validity) {
+    if (!f || col < 0 || col >= (int32_t)f->cols.size()) return BOWGPU_EINVAL;
+    if (values) *values = f->cols[col].values;
+    if (validity) *validity = f->cols[col].validity;
+    return BOWGPU_OK;
+}
+
+extern "C" int32_t bowgpu_frame_download_range(const bowgpu_frame *f, int64_t row0, int64_t nrows, bowgpu_out_col *outs,
+                                               int32_t ncols) {
+    if (!f || !outs || ncols != (int32_t)f->cols.size() || row0 < 0 || nrows < 0 || row0 + nrows > f->n)
+        return BOWGPU_EINVAL;
+    bowgpu_ctx *ctx = f->ctx;
+    Guard gd(ctx);
+    for (int j = 0; j < ncols; ++j) {
+        const DevCol &c = f->cols[j];
+        outs[j].dtype = c.dtype;
+        if (nrows == 0) continue;
+        int32_t rc = copy_d2h(ctx, outs[j].values, c.values + row0, (size_t)nrows * 8);
+        if (rc) return rc;
+        if (!outs[j].validity) continue;
+        const size_t ob = (size_t)((nrows + 7) / 8);
+        if (!c.validity) {
+            memset(outs[j].validity, 0xff, ob);
+            if (nrows & 7) outs[j].validity[ob - 1] = (uint8_t)((1u << (nrows & 7)) - 1u);
+            continue;
+        }
+        if (row0 == 0 && nrows == f->n) {
+            rc = copy_d2h(ctx, outs[j].validity, c.validity, ob);
+            if (rc) return rc;
+        } else {  // realign the sub-range on the device, then copy
+            const int64_t dst_bytes = bitmap_bytes_padded(nrows);
+            rc = arena_reserve(ctx, (size_t)dst_bytes + 256);
+            if (rc) return rc;
+            arena_reset(ctx);
+            uint8_t *tmp = (uint8_t *)arena_take(ctx, (size_t)dst_bytes);
+            CK(launch_bitmap_realign(c.validity + (row0 >> 3), row0 & 7, nrows, tmp, dst_bytes, ctx->stream));
+            rc = copy_d2h(ctx, outs[j].validity, tmp, ob);
+            if (rc) return rc;
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BOWGPU_OK;
+}
+
+extern "C" int32_t bowgpu_frame_download(const bowgpu_frame *f, bowgpu_out_col *outs, int32_t ncols) {
+    return bowgpu_frame_download_range(f, 0, f ? f->n : 0, outs, ncols);
+}
+
+extern "C" int32_t bowgpu_frame_generate(bowgpu_ctx *ctx, const bowgpu_gen_spec *spec, bowgpu_frame **out) {
+    if (!ctx || !spec || !out || spec->nrows < 0 || spec->ncols < 0 || spec->ncols > 31) return BOWGPU_EINVAL;
+    *out = nullptr;
+    Guard gd(ctx);
+    if (spec->kind != BOWGPU_GEN_REGULAR) return fail(ctx, BOWGPU_EUNSUPPORTED, "generator kind %d", spec->kind);
+    bowgpu_frame *f = new (std::nothrow) bowgpu_frame();
+    if (!f) return BOWGPU_ENOMEM;
+    f->ctx = ctx;
+    f->n = spec->nrows;
+    f->cols.resize(spec->ncols + 1);
+    int32_t rc = alloc_col(ctx, f->cols[0], f->n, BOWGPU_INT64, false);
+    if (rc == BOWGPU_OK) {
+        int e = launch_gen_regular((int64_t *)f->cols[0].values, f->n, spec->row0, spec->t0, spec->step, ctx->stream);
+        if (e) rc = fail(ctx, BOWGPU_ECUDA, "gen_time: %s", cudaGetErrorString((cudaError_t)e));
+    }
+    for (int c = 0; c < spec->ncols && rc == BOWGPU_OK; ++c) {
+        DevCol &dc = f->cols[c + 1];
+        const bool nulls = ((spec->null_mask >> c) & 1u) && spec->null_mod > 0;
+        const bool is_int = (spec->int_mask >> c) & 1u;
+        rc = alloc_col(ctx, dc, f->n, is_int ? BOWGPU_INT64 : BOWGPU_FLOAT64, nulls);
+        if (rc) break;
+        int e = launch_gen_values(dc.values, dc.validity, f->n, spec->row0, spec->seed, (uint64_t)(c + 1), is_int,
+                                  nulls ? spec->null_mod : 0, ctx->stream);
+        if (e) rc = fail(ctx, BOWGPU_ECUDA, "gen_values: %s", cudaGetErrorString((cudaError_t)e));
+        if (rc == BOWGPU_OK && nulls) rc = count_nulls(ctx, dc, f->n);
+    }
+    if (rc == BOWGPU_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+        rc = fail(ctx, BOWGPU_ECUDA, "generate: %s", cudaGetErrorString(cudaGetLastError()));
+    if (rc != BOWGPU_OK) {
+        for (auto &c : f->cols) free_col(c);
+        delete f;
+        return rc;
+    }
+    *out = f;
+    return BOWGPU_OK;
+}
+
+// ================================================================================================
+// rolling
+// ================================================================================================
+extern "C" int32_t bowgpu_rolling_create(bowgpu_frame *frame, int32_t time_col, int64_t interval, int64_t offset,
+                                         int32_t inclusive, const bowgpu_col *prev_row, bowgpu_rolling **out) {
+    if (!frame || !out) return BOWGPU_EINVAL;
+    *out = nullptr;
+    bowgpu_ctx *ctx = frame->ctx;
+    Guard gd(ctx);
+    const int ncols = (int)frame->cols.size();
+    if (time_col < 0 || time_col >= ncols) return fail(ctx, BOWGPU_EINVAL, "time column index %d out of range", time_col);
+    if (frame->cols[time_col].dtype != BOWGPU_INT64)  // rolling.go:70-73
+        return fail(ctx, BOWGPU_ETYPE, "impossible to create a new intervalRolling on column of type float64");
+    if (interval <= 0) return fail(ctx, BOWGPU_EINVAL, "strictly positive interval required");  // rolling.go:115-117
+    if (offset >= interval || offset <= -interval) offset %= interval;                           // rolling.go:119-126
+    if (offset < 0) offset += interval;
+    bowgpu_rolling *r = new (std::nothrow) bowgpu_rolling();
+    if (!r) return BOWGPU_ENOMEM;
+    r->frame = frame;
+    r->time_col = time_col;
+    r->interval = interval;
+    r->offset = offset;
+    r->inclusive = inclusive != 0;
+    auto bail = [&](int32_t code) {
+        delete r;
+        return code;
+    };
+    if (prev_row) {  // enforcePrevRow, rolling.go:130-141
+        if (prev_row[0].length == 0) {
+            prev_row = nullptr;
+        } else if (prev_row[0].length != 1) {
+            return bail(fail(ctx, BOWGPU_EPREVROW, "prevRow must have only one row"));
+        }
+    }
+    if (prev_row) {
+        r->has_prev = true;
+        r->prev.resize(ncols);
+        for (int j = 0; j < ncols; ++j) {
+            const bowgpu_col &p = prev_row[j];
+            PrevCell &pc = r->prev[j];
+            pc.dtype = p.dtype;
+            pc.valid = 1;
+            if (p.validity) pc.valid = (p.validity[p.offset >> 3] >> (p.offset & 7)) & 1;
+            memcpy(&pc.bits, (const char *)p.values + p.offset * 8, 8);
+        }
+    }
+    const DevCol &tc = frame->cols[time_col];
+    const int64_t n = frame->n;
+    if (tc.validity && tc.null_count != 0)
+        return bail(fail(ctx, BOWGPU_ENULLTIME, "interval column holds %lld nulls: the GPU path requires a non-null, sorted interval column",
+                         (long long)tc.null_count));
+    if (n > 0) {
+        int64_t ends[2];
+        if (cudaMemcpyAsync(&ends[0], tc.values, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaMemcpyAsync(&ends[1], tc.values + (n - 1), 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+            return bail(fail(ctx, BOWGPU_ECUDA, "reading interval column ends: %s", cudaGetErrorString(cudaGetLastError())));
+        r->t_first = ends[0];
+        r->t_last = ends[1];
+        // first window start, rolling.go:96-99 (Go '/' truncates toward zero, like C)
+        int64_t s0 = (int64_t)((uint64_t)((r->t_first / interval) * interval) + (uint64_t)offset);
+        if (s0 > r->t_first) s0 = (int64_t)((uint64_t)s0 - (uint64_t)interval);
+        r->s0 = s0;
+        // countWindows, rolling.go:143-154
+        r->W = s0 > r->t_last ? 0 : (int64_t)(((uint64_t)r->t_last - (uint64_t)s0) / (uint64_t)interval) + 1;
+        if (r->t_first < s0) {  // negative timestamps: leading rows before the first window start
+            int e = launch_lower_bound((const int64_t *)tc.values, n, s0, ctx->d_scalars, ctx->stream);
+            int64_t p = 0;
+            if (e || cudaMemcpyAsync(&p, ctx->d_scalars, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+                return bail(fail(ctx, BOWGPU_ECUDA, "lower_bound: %s", cudaGetErrorString(cudaGetLastError())));
+            r->early_rows = p;
+            if (p < n) {
+                int64_t tp = 0;
+                if (cudaMemcpyAsync(&tp, tc.values + p, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                    cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+                    return bail(fail(ctx, BOWGPU_ECUDA, "reading time: %s", cudaGetErrorString(cudaGetLastError())));
+                r->t_after_early = tp;
+                r->has_after_early = true;
+            }
+        }
+    }
+    *out = r;
+    return BOWGPU_OK;
+}
+
+extern "C" int32_t bowgpu_rolling_create_shard(bowgpu_frame *frame, int32_t time_col, int64_t interval, int64_t s0,
+                                               int64_t num_windows, int32_t inclusive, const bowgpu_col *prev_row,
+                                               bowgpu_rolling **out) {
+    if (!frame || !out || num_windows < 0) return BOWGPU_EINVAL;
+    bowgpu_rolling *r = nullptr;
+    int32_t rc = bowgpu_rolling_create(frame, time_col, interval, 0, inclusive, prev_row, &r);
+    if (rc) return rc;
+    if (frame->n > 0 && r->t_first < s0) {
+        delete r;
+        return fail(frame->ctx, BOWGPU_EINVAL, "shard starts before its first window (t[0]=%lld < s0=%lld)",
+                    (long long)r->t_first, (long long)s0);
+    }
+    r->s0 = s0;
+    r->W = num_windows;
+    r->offset = 0;
+    r->early_rows = 0;
+    r->has_after_early = false;
+    *out = r;
+    return BOWGPU_OK;
+}
+
+extern "C" void bowgpu_rolling_destroy(bowgpu_rolling *r) { delete r; }
+extern "C" int64_t bowgpu_rolling_num_windows(const bowgpu_rolling *r) { return r ? r->W : 0; }
+extern "C" int64_t bowgpu_rolling_first_window_start(const bowgpu_rolling *r) { return r ? r->s0 : 0; }
+extern "C" int32_t bowgpu_rolling_inclusive(const bowgpu_rolling *r) { return r ? r->inclusive : 0; }
+extern "C" int64_t bowgpu_rolling_early_rows(const bowgpu_rolling *r, int32_t *kept) {
+    if (!r) return 0;
+    if (kept) *kept = make_geom(r, r->inclusive).early_keep;
+    return r->early_rows;
+}
+
+extern "C" int32_t bowgpu_rolling_bounds(bowgpu_rolling *r, int64_t *first, uint8_t *inclusive_bitmap) {
+    if (!r || !first) return BOWGPU_EINVAL;
+    bowgpu_ctx *ctx = r->frame->ctx;
+    Guard gd(ctx);
+    const WindowGeom g = make_geom(r, r->inclusive);
+    const int64_t W = g.W;
+    if (g.n == 0 || W == 0) {
+        for (int64_t k = 0; k <= W; ++k) first[k] = g.n;  // first[W] = n; a row-less shard only has empty windows
+        if (inclusive_bitmap) memset(inclusive_bitmap, 0, (size_t)((W + 7) / 8));
+        return BOWGPU_OK;
+    }
+    const size_t fb = (size_t)(W + 1) * 8, ib = (size_t)((W + 7) / 8) + 64;
+    int32_t rc = arena_reserve(ctx, fb + ib + 1024);
+    if (rc) return rc;
+    arena_reset(ctx);
+    int64_t *d_first = (int64_t *)arena_take(ctx, fb);
+    uint8_t *d_inc = (uint8_t *)arena_take(ctx, ib);
+    timing_begin(ctx);
+    BoundsLaunch L;
+    L.time = (const int64_t *)r->frame->cols[r->time_col].values;
+    L.g = g;
+    L.first = d_first;
+    L.status = ctx->d_status;
+    cudaEvent_t e0, e1;
+    timing_main_pair(ctx, &e0, &e1);
+    CK(launch_bounds(L, ctx->sm_count, ctx->stream, e0, e1));
+    count_launch(ctx, 1, true);
+    if (inclusive_bitmap) {
+        if (r->inclusive) {
+            CK(launch_inclusive_bitmap(L.time, d_first, g, d_inc, ctx->stream));
+            count_launch(ctx);
+        } else {
+            CK(cudaMemsetAsync(d_inc, 0, ib, ctx->stream));
+        }
+    }
+    timing_end(ctx);
+    rc = copy_d2h(ctx, first, d_first, fb);
+    if (rc) return rc;
+    if (inclusive_bitmap) {
+        rc = copy_d2h(ctx, inclusive_bitmap, d_inc, (size_t)((W + 7) / 8));
+        if (rc) return rc;
+    }
+    return check_status(ctx);
+}
+
+extern "C" int32_t bowgpu_agg_return_type(int32_t op, int32_t input_dtype) {
+    switch (op) {
+    case BOWGPU_AGG_WINDOW_START: return BOWGPU_INT64;  // IteratorDependent; the iterator column is Int64
+    case BOWGPU_AGG_COUNT: return BOWGPU_INT64;
+    case BOWGPU_AGG_FIRST:
+    case BOWGPU_AGG_LAST: return input_dtype;  // InputDependent
+    default: return BOWGPU_FLOAT64;
+    }
+}
+extern "C" int32_t bowgpu_agg_needs_inclusive(int32_t op) {
+    return op == BOWGPU_AGG_INTEGRAL_TRAPEZOID || op == BOWGPU_AGG_WAVG_LINEAR;
+}
+
+extern "C" int32_t bowgpu_rolling_aggregate(bowgpu_rolling *r, const bowgpu_agg_spec *specs, int32_t nspecs,
+                                            bowgpu_out_col *outs, int32_t mem) {
+    if (!r || !specs || !outs || nspecs <= 0) return BOWGPU_EINVAL;
+    bowgpu_frame *f = r->frame;
+    bowgpu_ctx *ctx = f->ctx;
+    Guard gd(ctx);
+    const int ncols = (int)f->cols.size();
+    bool keeps_interval = false, inclusive_eff = r->inclusive != 0;
+    for (int j = 0; j < nspecs; ++j) {  // validateAggregation, aggregation.go:171-188
+        if (specs[j].col < 0 || specs[j].col >= ncols) return fail(ctx, BOWGPU_EINVAL, "aggregation %d: no column %d", j, specs[j].col);
+        if (specs[j].op < 0 || specs[j].op >= BOWGPU_AGG__COUNT) return fail(ctx, BOWGPU_EUNSUPPORTED, "aggregation %d: unknown opcode %d", j, specs[j].op);
+        if (specs[j].nfactors < 0 || specs[j].nfactors > 4) return fail(ctx, BOWGPU_EINVAL, "aggregation %d: at most 4 factors", j);
+        if (bowgpu_agg_needs_inclusive(specs[j].op)) inclusive_eff = true;
+        if (specs[j].col == r->time_col) keeps_interval = true;
+        if (agg_is_integral(specs[j].op)) return fail(ctx, BOWGPU_EUNSUPPORTED, "aggregation %d: integral family not built yet", j);
+    }
+    if (!keeps_interval) return fail(ctx, BOWGPU_ENOINTERVALCOL, "must keep interval column");  // aggregation.go:163-166
+    for (int j = 0; j < nspecs; ++j) outs[j].dtype = bowgpu_agg_return_type(specs[j].op, f->cols[specs[j].col].dtype);
+    const WindowGeom g = make_geom(r, inclusive_eff);
+    const int64_t W = g.W;
+    if (W == 0) return BOWGPU_OK;
+
+    // ---- plan: one streaming launch per distinct input column of the basic family --------------------
+    std::vector<int> basic_cols;
+    for (int j = 0; j < nspecs; ++j)
+        if (agg_is_basic(specs[j].op) && std::find(basic_cols.begin(), basic_cols.end(), specs[j].col) == basic_cols.end())
+            basic_cols.push_back(specs[j].col);
+    const size_t wv = align_up((size_t)W * 8, 256), wb = align_up((size_t)((W + 7) / 8) + 16, 256);
+    size_t need = 4096 + basic_cols.size() * wv + seg_carry_bytes(g.n) + 512;
+    if (mem == BOWGPU_MEM_HOST) need += (size_t)nspecs * (wv + wb);
+    int32_t rc = arena_reserve(ctx, need);
+    if (rc) return rc;
+    arena_reset(ctx);
+    std::vector<void *> dvals(nspecs);
+    std::vector<uint8_t *> dbits(nspecs);
+    for (int j = 0; j < nspecs; ++j) {
+        if (mem == BOWGPU_MEM_DEVICE) {
+            dvals[j] = outs[j].values;
+            dbits[j] = outs[j].validity;
+        } else {
+            dvals[j] = arena_take(ctx, wv);
+            dbits[j] = (uint8_t *)arena_take(ctx, wb);
+        }
+        if (!dvals[j] || !dbits[j]) return fail(ctx, BOWGPU_EINVAL, "aggregation %d: null output buffer", j);
+    }
+    BasicCarry *carry = (BasicCarry *)arena_take(ctx, seg_carry_bytes(g.n));
+    const int64_t ntiles = seg_num_tiles(g.n);
+
+    timing_begin(ctx);
+    std::vector<EpilogueSpec> epi(nspecs);
+    std::vector<int64_t *> col_cnt(ncols, nullptr);
+    for (int c : basic_cols) {
+        const DevCol &dc = f->cols[c];
+        SegLaunch L;
+        memset(&L, 0, sizeof L);
+        L.time = (const int64_t *)f->cols[r->time_col].values;
+        L.values = dc.values;
+        L.validity = dc.validity;
+        L.is_int = dc.dtype == BOWGPU_INT64;
+        L.g = g;
+        L.carry_head = carry;
+        L.carry_tail = carry + ntiles;
+        L.status = ctx->d_status;
+        // first spec of each op on this column receives the kernel output; duplicates are copied afterwards
+        int primary[BOWGPU_AGG__COUNT];
+        for (int &p : primary) p = -1;
+        for (int j = 0; j < nspecs; ++j)
+            if (specs[j].col == c && agg_is_basic(specs[j].op) && primary[specs[j].op] < 0) primary[specs[j].op] = j;
+        // the valid-row count drives every validity bitmap: Count output if it can be used as is, else scratch
+        int64_t *cnt = nullptr;
+        if (primary[BOWGPU_AGG_COUNT] >= 0 && specs[primary[BOWGPU_AGG_COUNT]].nfactors == 0)
+            cnt = (int64_t *)dvals[primary[BOWGPU_AGG_COUNT]];
+        else
+            cnt = (int64_t *)arena_take(ctx, wv);
+        col_cnt[c] = cnt;
+        CK(cudaMemsetAsync(cnt, 0, (size_t)W * 8, ctx->stream));
+        L.out.cnt = cnt;
+        auto prim = [&](int op) -> void * { return primary[op] >= 0 ? dvals[primary[op]] : nullptr; };
+        L.out.sum = (double *)prim(BOWGPU_AGG_SUM);
+        L.out.mean = (double *)prim(BOWGPU_AGG_MEAN);
+        L.out.mn = (double *)prim(BOWGPU_AGG_MIN);
+        L.out.mx = (double *)prim(BOWGPU_AGG_MAX);
+        L.out.first = (uint64_t *)prim(BOWGPU_AGG_FIRST);
+        L.out.last = (uint64_t *)prim(BOWGPU_AGG_LAST);
+        L.ops = OPS_SUMCNT;
+        if (L.out.mn || L.out.mx) L.ops |= OPS_MINMAX;
+        if (L.out.first || L.out.last) L.ops |= OPS_FIRSTLAST;
+        cudaEvent_t e0, e1;
+        timing_main_pair(ctx, &e0, &e1);
+        CK(launch_segreduce_basic(L, ctx->sm_count, ctx->stream, e0, e1));
+        count_launch(ctx, 1, true);
+        count_launch(ctx, 1);
+        for (int j = 0; j < nspecs; ++j) {  // duplicates of an (op, column) pair
+            if (specs[j].col != c || !agg_is_basic(specs[j].op)) continue;
+            const int p = primary[specs[j].op];
+            if (p == j) continue;
+            const void *srcv = specs[j].op == BOWGPU_AGG_COUNT ? (const void *)cnt : dvals[p];
+            CK(cudaMemcpyAsync(dvals[j], srcv, (size_t)W * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+    }
+    for (int j = 0; j < nspecs; ++j) {
+        EpilogueSpec &e = epi[j];
+        memset(&e, 0, sizeof e);
+        e.op = specs[j].op;
+        e.out_is_int = outs[j].dtype == BOWGPU_INT64;
+        e.cnt = agg_is_basic(specs[j].op) ? col_cnt[specs[j].col] : nullptr;
+        e.ok = nullptr;
+        e.values = dvals[j];
+        e.validity = dbits[j];
+        e.nfactors = specs[j].nfactors;
+        for (int i = 0; i < e.nfactors; ++i) e.factors[i] = specs[j].factors[i];
+    }
+    CK(launch_epilogue(epi.data(), nspecs, g, ctx->stream));
+    count_launch(ctx, (nspecs + 15) / 16);
+    timing_end(ctx);
+    if (mem == BOWGPU_MEM_DEVICE) return BOWGPU_OK;  // asynchronous: errors surface in bowgpu_ctx_synchronize
+    for (int j = 0; j < nspecs; ++j) {
+        rc = copy_d2h(ctx, outs[j].values, dvals[j], (size_t)W * 8);
+        if (rc) return rc;
+        rc = copy_d2h(ctx, outs[j].validity, dbits[j], (size_t)((W + 7) / 8));
+        if (rc) return rc;
+    }
+    return check_status(ctx);
+}
+
+extern "C" int32_t bowgpu_rolling_interpolate(bowgpu_rolling *r, const int32_t *ops, int32_t nops, bowgpu_frame **out_frame,
+                                              int64_t *n_out) {
+    if (!r || !ops || !out_frame || !n_out) return BOWGPU_EINVAL;
+    return fail(r->frame->ctx, BOWGPU_EUNSUPPORTED, "interpolate not built yet");
+}

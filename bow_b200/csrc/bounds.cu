@@ -1,0 +1,216 @@
+// bounds — window-boundary computation for rolling.IntervalRolling.
+//
+// Replaces the reference's row-at-a-time iterator (HasNext/Next, rolling/rolling.go:162-239) by one
+// coalesced streaming pass over the sorted int64 time column: first[k] = Window.FirstIndex of
+// window k (= lower bound of S_k; 0 for k == 0), first[W] = n.  The same pass verifies the GPU
+// path's precondition (time sorted ascending).  Row tiles are staged by TMA bulk copies
+// (tile_pipe.cuh); thread t owns R consecutive rows and walks them with a running window end, so
+// there is one exact 64-bit division per thread and tile, not per row.  The thread that owns the
+// last row of a window writes the start index of every window up to the next non-empty one, so
+// empty windows need no second pass.
+#include "kernels.h"
+#include "tile_pipe.cuh"
+
+namespace bowgpu {
+
+namespace {
+
+constexpr int BND_NT = 128;
+constexpr int BND_R = 17;
+using BndG = TileGeom<BND_NT, BND_R>;
+constexpr int BND_STAGE_BYTES = BndG::TIME_BYTES;
+constexpr int BND_HEADER_BYTES = 128;
+constexpr int BND_STAGES = 4;
+
+__global__ void __launch_bounds__(BND_NT, 4) bounds_kernel(const BoundsLaunch P, const int64_t ntiles) {
+    using G = BndG;
+    constexpr int R = G::R;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
+    uint8_t *stages = smem_raw + BND_HEADER_BYTES;
+    const int tid = threadIdx.x;
+    const WindowGeom &g = P.g;
+    const uint64_t d = g.div.d;
+    TileSrc src{P.time, nullptr, nullptr, g.n};
+
+    if (tid == 0) {
+        for (int s = 0; s < BND_STAGES; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int64_t tl = blockIdx.x;
+        for (int s = 0; s < BND_STAGES && tl < ntiles; ++s, tl += gridDim.x)
+            issue_tile<G, false>(src, tl, stages + (size_t)s * BND_STAGE_BYTES, &full[s]);
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    bool bad = false;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        mbar_wait(&full[stage], phase);
+        const int64_t *tsm = reinterpret_cast<const int64_t *>(stages + (size_t)stage * BND_STAGE_BYTES);
+        const int64_t r0 = tile * G::T;
+        const int64_t nrem = g.n - r0;
+        const int ti0 = tid * R;
+        const bool early_tile = r0 < g.early_rows;
+        auto xrel = [&](int64_t x, int64_t ti) -> uint64_t {
+            if (early_tile && r0 + ti < g.early_rows) return 0;
+            return (uint64_t)x - (uint64_t)g.s0;
+        };
+        if (ti0 < nrem) {
+            int64_t x[R + 1];
+#pragma unroll
+            for (int j = 0; j <= R; ++j) x[j] = tsm[ti0 + 2 + j];
+            if (r0 + ti0 > 0) bad |= x[0] < tsm[ti0 + 1];
+#pragma unroll
+            for (int j = 1; j < R; ++j)
+                if (ti0 + j < nrem) bad |= x[j] < x[j - 1];
+            uint64_t kcur = div_u64(xrel(x[0], ti0), g.div);
+            uint64_t erel = (kcur + 1) * d;
+            const uint64_t Wu = (uint64_t)g.W;
+            if (r0 + ti0 == 0)  // owner of row 0 (kcur > 0 only for a shard with leading empty windows)
+                for (uint64_t k = 0; k <= kcur && k <= Wu; ++k) P.first[k] = 0;
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                if (ti0 + j + 1 < nrem) {
+                    const uint64_t xn = xrel(x[j + 1], ti0 + j + 1);
+                    if (xn >= erel) {  // row j+1 starts window knew; windows kcur+1..knew begin there
+                        uint64_t knew;
+                        if (xn - erel < d) {
+                            knew = kcur + 1;
+                        } else {
+                            knew = div_u64(xn, g.div);
+                        }
+                        const int64_t row = r0 + ti0 + j + 1;
+                        for (uint64_t k = kcur + 1; k <= knew && k <= Wu; ++k) P.first[k] = row;
+                        kcur = knew;
+                        erel = (kcur + 1) * d;
+                    }
+                } else if (ti0 + j + 1 == nrem) {  // owner of the last row: trailing (empty) windows end at n
+                    for (uint64_t k = kcur + 1; k <= Wu; ++k) P.first[k] = g.n;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const int64_t nxt = tile + (int64_t)BND_STAGES * gridDim.x;
+            if (nxt < ntiles) issue_tile<G, false>(src, nxt, stages + (size_t)stage * BND_STAGE_BYTES, &full[stage]);
+        }
+        if (++stage == BND_STAGES) {
+            stage = 0;
+            phase ^= 1u;
+        }
+    }
+    if (bad) atomicOr(P.status, ST_UNSORTED);
+}
+
+// inc[k] = first[k+1] < n && t[first[k+1]] == S_{k+1}  (Window.IsInclusive, rolling.go:201-209)
+__global__ void inclusive_bitmap_kernel(const int64_t *time, const int64_t *first, WindowGeom g, uint8_t *bitmap) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool inc = false;
+    if (k < g.W) {
+        const int64_t b = first[k + 1];
+        const uint64_t erel = ((uint64_t)k + 1) * g.div.d;
+        if (b < g.n && b >= g.early_rows) inc = ((uint64_t)time[b] - (uint64_t)g.s0) == erel;
+    }
+    const uint32_t ball = __ballot_sync(0xffffffffu, inc);
+    const int lane = threadIdx.x & 31;
+    if ((lane & 7) == 0 && k < g.W) bitmap[k >> 3] = (uint8_t)(ball >> lane);
+}
+
+__global__ void lower_bound_kernel(const int64_t *time, int64_t n, int64_t x, int64_t *out) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t mid = lo + ((hi - lo) >> 1);
+        if (time[mid] < x)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    *out = lo;
+}
+
+// dst word w holds bits [32w, 32w+32) of the logical bitmap = src bits [off+32w, ...)
+__global__ void bitmap_realign_kernel(const uint8_t *src, int64_t off, int64_t nbits, uint32_t *dst, int64_t dst_words) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= dst_words) return;
+    const int64_t b0 = w * 32;
+    uint32_t v = 0;
+    if (b0 < nbits) {
+        const int64_t sbit = off + b0;
+        const int64_t sbyte = sbit >> 3;
+        const int sh = (int)(sbit & 7);
+        const int64_t last_byte = (off + nbits - 1) >> 3;
+        uint64_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+            if (sbyte + i <= last_byte) acc |= (uint64_t)src[sbyte + i] << (8 * i);
+        v = (uint32_t)(acc >> sh);
+        const int64_t rem = nbits - b0;
+        if (rem < 32) v &= (1u << rem) - 1u;
+    }
+    dst[w] = v;
+}
+
+__global__ void bitmap_popcount_kernel(const uint32_t *bm, int64_t nwords, unsigned long long *out) {
+    unsigned long long c = 0;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (int64_t)gridDim.x * blockDim.x)
+        c += __popc(bm[w]);
+    for (int o = 16; o; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+}  // namespace
+
+int launch_bounds(const BoundsLaunch &L, int sm_count, cudaStream_t stream, cudaEvent_t e0, cudaEvent_t e1) {
+    const int64_t ntiles = (L.g.n + BndG::T - 1) / BndG::T;
+    if (ntiles == 0) return 0;
+    const int smem = BND_HEADER_BYTES + BND_STAGES * BND_STAGE_BYTES;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(bounds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    int64_t grid = (int64_t)sm_count * 3;
+    if (grid > ntiles) grid = ntiles;
+    if (e0) cudaEventRecord(e0, stream);
+    bounds_kernel<<<(unsigned)grid, BND_NT, smem, stream>>>(L, ntiles);
+    if (e1) cudaEventRecord(e1, stream);
+    return (int)cudaGetLastError();
+}
+
+int launch_inclusive_bitmap(const int64_t *time, const int64_t *first, WindowGeom g, uint8_t *bitmap,
+                            cudaStream_t stream) {
+    if (g.W <= 0) return 0;
+    const int nt = 256;
+    inclusive_bitmap_kernel<<<(unsigned)((g.W + nt - 1) / nt), nt, 0, stream>>>(time, first, g, bitmap);
+    return (int)cudaGetLastError();
+}
+
+int launch_lower_bound(const int64_t *time, int64_t n, int64_t x, int64_t *out, cudaStream_t stream) {
+    lower_bound_kernel<<<1, 1, 0, stream>>>(time, n, x, out);
+    return (int)cudaGetLastError();
+}
+
+int launch_bitmap_realign(const uint8_t *src, int64_t off, int64_t nbits, uint8_t *dst, int64_t dst_bytes,
+                          cudaStream_t stream) {
+    const int64_t words = dst_bytes / 4;
+    if (words == 0) return 0;
+    const int nt = 256;
+    bitmap_realign_kernel<<<(unsigned)((words + nt - 1) / nt), nt, 0, stream>>>(src, off, nbits, (uint32_t *)dst, words);
+    return (int)cudaGetLastError();
+}
+
+int launch_bitmap_popcount(const uint8_t *bm, int64_t nbits, unsigned long long *out, cudaStream_t stream) {
+    const int64_t words = (nbits + 31) / 32;
+    if (words == 0) return 0;
+    const int nt = 256;
+    int64_t grid = (words + nt - 1) / nt;
+    if (grid > 1184) grid = 1184;
+    bitmap_popcount_kernel<<<(unsigned)grid, nt, 0, stream>>>((const uint32_t *)bm, words, out);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace bowgpu

@@ -1,0 +1,108 @@
+// Host-callable launchers of the libbowgpu kernels (internal; the public boundary is include/bowgpu.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace bowgpu {
+
+// Window geometry shared by every kernel (SURVEY 8 notation):
+//   S_k = s0 + k*I, window of row i: k(i) = floor((t[i]-s0)/I); rows [0, early_rows) have t < s0
+//   (only possible for negative timestamps, rolling.go:96-99) and belong to window 0 iff early_keep.
+struct WindowGeom {
+    int64_t n;           // rows
+    int64_t s0;          // first window start (rolling.go:96-99)
+    int64_t W;           // number of windows (rolling.go:143-154)
+    DivU64 div;          // interval
+    int64_t early_rows;
+    int32_t early_keep;
+    int32_t _pad;
+};
+
+// status word bits written by the kernels
+enum { ST_UNSORTED = 1 };
+
+// ---- carry record of one tile edge (segreduce) ------------------------------------------------
+struct alignas(16) BasicCarry {
+    int64_t key;     // window index, -1 = none
+    int64_t cnt;     // valid rows; bit 62 set on head records = window closed inside the tile
+    double sum;
+    double mn, mx;
+    uint64_t first, last;  // raw bits of first / last valid value
+    uint64_t _pad;
+};
+
+struct BasicOut {  // per-window outputs of one input column (any pointer may be null)
+    int64_t *cnt;
+    double *sum;
+    double *mean;
+    double *mn;
+    double *mx;
+    uint64_t *first;
+    uint64_t *last;
+};
+
+// ops bit mask of the basic family
+enum { OPS_SUMCNT = 1, OPS_MINMAX = 2, OPS_FIRSTLAST = 4 };
+
+struct SegLaunch {
+    const int64_t *time;
+    const uint64_t *values;
+    const uint8_t *validity;  // null = all valid
+    int32_t is_int;           // values are int64 (converted with (double)) else float64 bits
+    uint32_t ops;             // OPS_* mask
+    WindowGeom g;
+    BasicOut out;
+    BasicCarry *carry_head;   // [ntiles]
+    BasicCarry *carry_tail;   // [ntiles]
+    int32_t *status;
+};
+
+int64_t seg_num_tiles(int64_t n);
+size_t seg_carry_bytes(int64_t n);  // bytes for carry_head + carry_tail
+// launches main + fixup kernels on `stream`; returns cudaError_t as int
+int launch_segreduce_basic(const SegLaunch &L, int sm_count, cudaStream_t stream, cudaEvent_t ev_main0,
+                           cudaEvent_t ev_main1);
+
+// ---- bounds ------------------------------------------------------------------------------------
+struct BoundsLaunch {
+    const int64_t *time;
+    WindowGeom g;
+    int64_t *first;     // [W+1] device
+    int32_t *status;
+};
+int launch_bounds(const BoundsLaunch &L, int sm_count, cudaStream_t stream, cudaEvent_t ev0, cudaEvent_t ev1);
+// inclusive flags: inc[k] = first[k+1] < n && t[first[k+1]] == S_{k+1}; bitmap of ceil(W/8) bytes
+int launch_inclusive_bitmap(const int64_t *time, const int64_t *first, WindowGeom g, uint8_t *bitmap,
+                            cudaStream_t stream);
+
+// ---- per-window epilogue (validity bitmaps, defaults of empty windows, WindowStart, Factor) -----
+struct EpilogueSpec {
+    int32_t op;          // BOWGPU_AGG_*
+    int32_t out_is_int;  // output dtype is int64
+    const int64_t *cnt;  // valid-row count of the input column per window (null for WindowStart)
+    const uint8_t *ok;   // optional per-window validity bytes overriding cnt > 0 (integral family)
+    void *values;        // [W]
+    uint8_t *validity;   // [ceil(W/8)] bytes
+    int32_t nfactors;
+    int32_t _pad;
+    double factors[4];
+};
+int launch_epilogue(const EpilogueSpec *specs_host, int nspecs, WindowGeom g, cudaStream_t stream);
+
+// ---- utilities ------------------------------------------------------------------------------------
+// dst bitmap (bit offset 0, padded bytes zeroed up to dst_bytes) from src bitmap at bit offset `off`
+int launch_bitmap_realign(const uint8_t *src, int64_t off, int64_t nbits, uint8_t *dst, int64_t dst_bytes,
+                          cudaStream_t stream);
+// number of set bits among the first nbits of a bit-offset-0 bitmap -> *out (device int64, must be zeroed)
+int launch_bitmap_popcount(const uint8_t *bm, int64_t nbits, unsigned long long *out, cudaStream_t stream);
+// lower bound of `x` in sorted time[0..n) -> *out (device)
+int launch_lower_bound(const int64_t *time, int64_t n, int64_t x, int64_t *out, cudaStream_t stream);
+
+// ---- synthetic generators (generate.cu) ----------------------------------------------------------
+int launch_gen_regular(int64_t *time, int64_t n, int64_t row0, int64_t t0, int64_t step, cudaStream_t stream);
+int launch_gen_values(uint64_t *v, uint8_t *validity, int64_t n, int64_t row0, uint64_t seed, uint64_t col, int is_int,
+                      uint32_t null_mod, cudaStream_t stream);
+
+}  // namespace bowgpu

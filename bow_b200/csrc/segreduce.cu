@@ -1,0 +1,410 @@
+// segreduce — the segmented-reduction kernel family behind Rolling.Aggregate.
+//
+// Replaces, for one input column, the reference's per-aggregation re-iteration of every window
+// (rolling/aggregation.go:190-238) and the per-window closures Count / Sum / ArithmeticMean / Min /
+// Max / First / Last (rolling/aggregation/{count,sum,arithmeticmean,minmax,firstlast}.go) by ONE
+// streaming pass over the time column and the value column.
+//
+// Work decomposition (load balance independent of window sizes, SURVEY 7 "hard parts"):
+//   * fixed-size ROW tiles (T = NT*R rows) are assigned round-robin to persistent CTAs and staged
+//     into shared memory by TMA bulk copies (tile_pipe.cuh);
+//   * thread t reduces its R consecutive rows sequentially, left to right, exactly like the
+//     reference closure does inside a window.  A window "closes" after row i when row i+1 lies in a
+//     later window; the thread owning row i detects that from its R+1 timestamps;
+//   * partial states of windows spanning several threads are stitched by a warp-shuffle segmented
+//     scan (flags = "a window closed inside this thread") plus a short cross-warp pass;
+//   * partial states of windows spanning several tiles go to per-tile head / tail carry records
+//     and are stitched left to right by a tiny fix-up kernel (deterministic, no atomics).
+//
+// Window state (a monoid; combine(L, R) keeps the left operand on ties, which reproduces the
+// reference's sequential semantics bit-exactly for Count/Min/Max/First/Last):
+//   cnt   valid rows                                           count.go:8-20
+//   sum   sum of float64(v) over valid rows                    sum.go:8-25, arithmeticmean.go:8-30
+//   mn/mx min / max over the non-NaN valid values, earliest wins on ties (minmax.go:20, `v < m`)
+//   fi/li index of the first / last valid row                  firstlast.go:8-36
+// Min/Max of the reference start from the FIRST valid value and only replace on a strict compare,
+// so a leading NaN is sticky and later NaNs are ignored: result = isnan(first) ? first : mn.
+#include "kernels.h"
+#include "tile_pipe.cuh"
+
+#include <math_constants.h>
+
+namespace bowgpu {
+
+namespace {
+
+constexpr int SEG_NT = 128;
+constexpr int SEG_R = 17;
+constexpr int SEG_MAX_STAGES = 8;
+using SegG = TileGeom<SEG_NT, SEG_R>;
+constexpr int SEG_NW = SEG_NT / 32;
+constexpr int SEG_STAGE_BYTES = SegG::TIME_BYTES + SegG::VAL_BYTES + SegG::BITS_STRIDE;
+constexpr int SEG_HEADER_BYTES = 1024;
+constexpr int64_t CLOSED_BIT = (int64_t)1 << 62;
+
+struct BState {
+    uint32_t cnt;
+    uint32_t fi, li;  // tile-relative row index of the first / last valid row
+    double sum, mn, mx;
+};
+
+template <uint32_t OPS>
+__device__ __forceinline__ BState st_identity() {
+    BState s;
+    s.cnt = 0;
+    s.fi = 0;
+    s.li = 0;
+    s.sum = 0.0;
+    s.mn = CUDART_INF;
+    s.mx = -CUDART_INF;
+    return s;
+}
+
+template <uint32_t OPS>
+__device__ __forceinline__ BState st_combine(const BState &L, const BState &R) {
+    BState o;
+    o.cnt = L.cnt + R.cnt;
+    o.sum = L.sum + R.sum;
+    if (OPS & OPS_MINMAX) {
+        o.mn = (R.mn < L.mn) ? R.mn : L.mn;
+        o.mx = (R.mx > L.mx) ? R.mx : L.mx;
+    }
+    if (OPS & (OPS_MINMAX | OPS_FIRSTLAST)) o.fi = L.cnt ? L.fi : R.fi;
+    if (OPS & OPS_FIRSTLAST) o.li = R.cnt ? R.li : L.li;
+    return o;
+}
+
+template <uint32_t OPS>
+__device__ __forceinline__ BState st_shfl_up(const BState &s, int d) {
+    BState o;
+    o.cnt = __shfl_up_sync(0xffffffffu, s.cnt, d);
+    o.sum = __shfl_up_sync(0xffffffffu, s.sum, d);
+    if (OPS & OPS_MINMAX) {
+        o.mn = __shfl_up_sync(0xffffffffu, s.mn, d);
+        o.mx = __shfl_up_sync(0xffffffffu, s.mx, d);
+    }
+    if (OPS & (OPS_MINMAX | OPS_FIRSTLAST)) o.fi = __shfl_up_sync(0xffffffffu, s.fi, d);
+    if (OPS & OPS_FIRSTLAST) o.li = __shfl_up_sync(0xffffffffu, s.li, d);
+    return o;
+}
+
+template <uint32_t OPS, bool IS_INT>
+__device__ __forceinline__ void st_accumulate(BState &s, uint64_t raw, uint32_t idx) {
+    const double v = IS_INT ? (double)(int64_t)raw : bits_as_f64(raw);  // GetFloat64, bowgetters.go:218-229
+    if (OPS & (OPS_MINMAX | OPS_FIRSTLAST)) s.fi = s.cnt ? s.fi : idx;
+    if (OPS & OPS_FIRSTLAST) s.li = idx;
+    s.cnt += 1;
+    s.sum += v;
+    if (OPS & OPS_MINMAX) {
+        if (v < s.mn) s.mn = v;
+        if (v > s.mx) s.mx = v;
+    }
+}
+
+struct WarpTotal {
+    BState st;
+    uint32_t flag;
+    uint32_t _pad;
+};
+
+// Final per-window write (values only; validity bitmaps and empty-window defaults are produced by
+// the epilogue from cnt).  first/last are raw value bits.
+template <bool IS_INT>
+__device__ __forceinline__ void write_window(const BasicOut &o, int64_t W, int64_t k, int64_t cnt, double sum,
+                                             double mn, double mx, uint64_t first, uint64_t last) {
+    if ((uint64_t)k >= (uint64_t)W || cnt == 0) return;
+    if (o.cnt) o.cnt[k] = cnt;
+    if (o.sum) o.sum[k] = sum;
+    if (o.mean) o.mean[k] = sum / (double)cnt;  // arithmeticmean.go:28
+    if (o.mn || o.mx) {
+        const double f = bits_as_f64(first);
+        const bool sticky = !IS_INT && (f != f);  // first valid value is NaN (minmax.go:14-24)
+        if (o.mn) o.mn[k] = sticky ? f : mn;
+        if (o.mx) o.mx[k] = sticky ? f : mx;
+    }
+    if (o.first) o.first[k] = first;
+    if (o.last) o.last[k] = last;
+}
+
+template <uint32_t OPS, bool IS_INT, bool HAS_NULLS>
+__global__ void __launch_bounds__(SEG_NT, 2)
+    segreduce_basic_kernel(const SegLaunch P, const int64_t ntiles, const int nstages) {
+    using G = SegG;
+    constexpr int R = G::R;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);                       // [SEG_MAX_STAGES]
+    WarpTotal *wtot = reinterpret_cast<WarpTotal *>(smem_raw + 64);                // [SEG_NW]
+    volatile int *sh_flags = reinterpret_cast<volatile int *>(smem_raw + 64 + SEG_NW * sizeof(WarpTotal));
+    uint8_t *stages = smem_raw + SEG_HEADER_BYTES;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const WindowGeom &g = P.g;
+    const uint64_t d = g.div.d;
+    TileSrc src{P.time, P.values, HAS_NULLS ? P.validity : nullptr, g.n};
+
+    if (tid == 0) {
+        for (int s = 0; s < nstages; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int64_t tl = blockIdx.x;
+        for (int s = 0; s < nstages && tl < ntiles; ++s, tl += gridDim.x)
+            issue_tile<G, true>(src, tl, stages + (size_t)s * SEG_STAGE_BYTES, &full[s]);
+    }
+
+    int stage = 0;
+    uint32_t phase = 0;
+    bool bad = false;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        mbar_wait(&full[stage], phase);
+        const uint8_t *sb = stages + (size_t)stage * SEG_STAGE_BYTES;
+        const int64_t *tsm = reinterpret_cast<const int64_t *>(sb);
+        const uint64_t *vsm = reinterpret_cast<const uint64_t *>(sb + G::TIME_BYTES);
+        const uint32_t *bsm = reinterpret_cast<const uint32_t *>(sb + G::TIME_BYTES + G::VAL_BYTES);
+        const int64_t r0 = tile * G::T;
+        const int64_t nrem = g.n - r0;  // rows from the tile start to the end of the column (> 0)
+        const int ti0 = tid * R;
+        const bool early_tile = r0 < g.early_rows;
+
+        // window-relative time of a row (rows before s0 collapse onto window 0, see WindowGeom)
+        auto xrel = [&](int64_t x, int64_t ti) -> uint64_t {
+            if (early_tile && r0 + ti < g.early_rows) return 0;
+            return (uint64_t)x - (uint64_t)g.s0;
+        };
+
+        uint32_t vbits = (1u << R) - 1u;
+        if (HAS_NULLS) {
+            const uint32_t lo = bsm[ti0 >> 5], hi = bsm[(ti0 >> 5) + 1];
+            vbits &= __funnelshift_r(lo, hi, ti0 & 31);
+        }
+        if (early_tile && !g.early_keep) {
+#pragma unroll
+            for (int j = 0; j < R; ++j)
+                if (r0 + ti0 + j < g.early_rows) vbits &= ~(1u << j);
+        }
+
+        int64_t x[R + 1];
+        uint64_t raw[R];
+#pragma unroll
+        for (int j = 0; j <= R; ++j) x[j] = tsm[ti0 + 2 + j];
+#pragma unroll
+        for (int j = 0; j < R; ++j) raw[j] = vsm[ti0 + j];
+
+        // precondition check: time sorted ascending (every adjacent pair is checked exactly once)
+        if (ti0 < nrem && r0 + ti0 > 0) bad |= x[0] < tsm[ti0 + 1];
+#pragma unroll
+        for (int j = 1; j < R; ++j)
+            if (ti0 + j < nrem) bad |= x[j] < x[j - 1];
+
+        BState st = st_identity<OPS>();
+        BState head = st_identity<OPS>();
+        int nclosed = 0;
+        uint64_t kcur = 0, kf = 0, erel = 0;
+        if (ti0 < nrem) {
+            kcur = div_u64(xrel(x[0], ti0), g.div);
+            kf = kcur;
+            erel = (kcur + 1) * d;
+        }
+        if (tid == 0) {
+            int lo_open = 0;
+            if (r0 > 0) lo_open = div_u64(xrel(tsm[1], -1), g.div) == kcur;
+            sh_flags[0] = lo_open;
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            if (ti0 + j < nrem) {
+                if ((vbits >> j) & 1u) st_accumulate<OPS, IS_INT>(st, raw[j], (uint32_t)(ti0 + j));
+                const bool next_exists = ti0 + j + 1 < nrem;
+                const uint64_t xn = xrel(x[j + 1], ti0 + j + 1);
+                if (!next_exists || xn >= erel) {  // the window of row j closes here
+                    if (nclosed == 0) {
+                        head = st;
+                    } else {
+                        const uint64_t fb = st.cnt ? vsm[st.fi] : 0, lb = st.cnt ? vsm[st.li] : 0;
+                        write_window<IS_INT>(P.out, g.W, (int64_t)kcur, st.cnt, st.sum, st.mn, st.mx, fb, lb);
+                    }
+                    ++nclosed;
+                    st = st_identity<OPS>();
+                    if (next_exists) {
+                        if (xn - erel < d) {
+                            ++kcur;
+                            erel += d;
+                        } else {
+                            kcur = div_u64(xn, g.div);
+                            erel = (kcur + 1) * d;
+                        }
+                    }
+                }
+            }
+        }
+
+        // ---- stitch windows spanning threads: segmented inclusive scan of the tails -------------
+        uint32_t f = nclosed > 0;
+        BState sc = st;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            const BState o = st_shfl_up<OPS>(sc, dd);
+            const uint32_t of = __shfl_up_sync(0xffffffffu, f, dd);
+            if (lane >= dd) {
+                if (!f) sc = st_combine<OPS>(o, sc);
+                f |= of;
+            }
+        }
+        const uint32_t ball = __ballot_sync(0xffffffffu, nclosed > 0);
+        if (lane == 31) {
+            wtot[warp].st = sc;
+            wtot[warp].flag = ball != 0;
+        }
+        BState ex = st_shfl_up<OPS>(sc, 1);
+        if (lane == 0) ex = st_identity<OPS>();
+        __syncthreads();
+        const bool left_open = sh_flags[0] != 0;
+        BState acc = st_identity<OPS>();
+        bool any_prev = false;
+        for (int u = 0; u < warp; ++u) {
+            const BState ws = wtot[u].st;
+            if (wtot[u].flag) {
+                acc = ws;
+                any_prev = true;
+            } else {
+                acc = st_combine<OPS>(acc, ws);
+            }
+        }
+        const bool flag_before = (ball & ((1u << lane) - 1u)) != 0;
+        const BState excl = flag_before ? ex : st_combine<OPS>(acc, ex);
+        const bool any_excl = any_prev || flag_before;
+
+        if (nclosed > 0) {  // this thread closes the window that was open at its left edge
+            const BState h = st_combine<OPS>(excl, head);
+            const uint64_t fb = h.cnt ? vsm[h.fi] : 0, lb = h.cnt ? vsm[h.li] : 0;
+            if (!any_excl && left_open) {
+                BasicCarry c;
+                c.key = (int64_t)kf;
+                c.cnt = (int64_t)h.cnt | CLOSED_BIT;
+                c.sum = h.sum;
+                c.mn = h.mn;
+                c.mx = h.mx;
+                c.first = fb;
+                c.last = lb;
+                c._pad = 0;
+                P.carry_head[tile] = c;
+            } else {
+                write_window<IS_INT>(P.out, g.W, (int64_t)kf, h.cnt, h.sum, h.mn, h.mx, fb, lb);
+            }
+        }
+        if (tid == SEG_NT - 1) {  // tile-level records: the window open at the right edge
+            const bool flag_incl = flag_before || nclosed > 0;
+            const BState incl = flag_incl ? sc : st_combine<OPS>(acc, sc);
+            const bool any_incl = any_prev || flag_incl;
+            const int64_t lim = nrem < G::T ? nrem : (int64_t)G::T;
+            const int64_t lastrow = lim - 1;
+            const bool next_exists = lim < nrem;
+            const uint64_t klast = div_u64(xrel(tsm[lastrow + 2], lastrow), g.div);
+            const bool closes = !next_exists || div_u64(xrel(tsm[lastrow + 3], lastrow + 1), g.div) != klast;
+            BasicCarry c;
+            c.key = (int64_t)klast;
+            c.cnt = (int64_t)incl.cnt;
+            c.sum = incl.sum;
+            c.mn = incl.mn;
+            c.mx = incl.mx;
+            c.first = incl.cnt ? vsm[incl.fi] : 0;
+            c.last = incl.cnt ? vsm[incl.li] : 0;
+            c._pad = 0;
+            BasicCarry none = c;
+            none.key = -1;
+            if (!any_incl && left_open) {  // the whole tile lies inside one window that began earlier
+                P.carry_head[tile] = c;    // not closed
+                P.carry_tail[tile] = none;
+            } else {
+                if (!left_open) P.carry_head[tile] = none;
+                P.carry_tail[tile] = closes ? none : c;
+            }
+        }
+        __syncthreads();  // every read of this stage (and of wtot) is done
+        if (tid == 0) {
+            const int64_t nxt = tile + (int64_t)nstages * gridDim.x;
+            if (nxt < ntiles) issue_tile<G, true>(src, nxt, stages + (size_t)stage * SEG_STAGE_BYTES, &full[stage]);
+        }
+        if (++stage == nstages) {
+            stage = 0;
+            phase ^= 1u;
+        }
+    }
+    if (bad) atomicOr(P.status, ST_UNSORTED);
+}
+
+// Stitches windows spanning tiles, strictly left to right: tail of tile j, then the head records
+// of the following tiles until the one where the window closes.
+__global__ void seg_fixup_kernel(const SegLaunch P, const int64_t ntiles) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ntiles) return;
+    BasicCarry a = P.carry_tail[j];
+    if (a.key < 0) return;
+    for (int64_t i = j + 1; i < ntiles; ++i) {
+        const BasicCarry h = P.carry_head[i];
+        if (h.key != a.key) break;
+        const int64_t hc = h.cnt & ~CLOSED_BIT;
+        a.sum = a.sum + h.sum;
+        a.mn = (h.mn < a.mn) ? h.mn : a.mn;
+        a.mx = (h.mx > a.mx) ? h.mx : a.mx;
+        a.first = a.cnt ? a.first : h.first;
+        a.last = hc ? h.last : a.last;
+        a.cnt += hc;
+        if (h.cnt & CLOSED_BIT) break;
+    }
+    if (P.is_int)
+        write_window<true>(P.out, P.g.W, a.key, a.cnt, a.sum, a.mn, a.mx, a.first, a.last);
+    else
+        write_window<false>(P.out, P.g.W, a.key, a.cnt, a.sum, a.mn, a.mx, a.first, a.last);
+}
+
+template <uint32_t OPS, bool IS_INT, bool HAS_NULLS>
+int launch_inst(const SegLaunch &L, int64_t ntiles, int sm_count, cudaStream_t stream, cudaEvent_t e0,
+                cudaEvent_t e1) {
+    auto kern = segreduce_basic_kernel<OPS, IS_INT, HAS_NULLS>;
+    int nstages = 3;
+    const int smem = SEG_HEADER_BYTES + nstages * SEG_STAGE_BYTES;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    int64_t grid = (int64_t)sm_count * 2;
+    if (grid > ntiles) grid = ntiles;
+    if (e0) cudaEventRecord(e0, stream);
+    kern<<<(unsigned)grid, SEG_NT, smem, stream>>>(L, ntiles, nstages);
+    if (e1) cudaEventRecord(e1, stream);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    const int fb = 128;
+    seg_fixup_kernel<<<(unsigned)((ntiles + fb - 1) / fb), fb, 0, stream>>>(L, ntiles);
+    return (int)cudaGetLastError();
+}
+
+template <uint32_t OPS>
+int launch_ops(const SegLaunch &L, int64_t ntiles, int sm, cudaStream_t s, cudaEvent_t e0, cudaEvent_t e1) {
+    const bool nulls = L.validity != nullptr;
+    if (L.is_int)
+        return nulls ? launch_inst<OPS, true, true>(L, ntiles, sm, s, e0, e1)
+                     : launch_inst<OPS, true, false>(L, ntiles, sm, s, e0, e1);
+    return nulls ? launch_inst<OPS, false, true>(L, ntiles, sm, s, e0, e1)
+                 : launch_inst<OPS, false, false>(L, ntiles, sm, s, e0, e1);
+}
+
+}  // namespace
+
+int64_t seg_num_tiles(int64_t n) { return (n + SegG::T - 1) / SegG::T; }
+size_t seg_carry_bytes(int64_t n) { return (size_t)seg_num_tiles(n) * 2 * sizeof(BasicCarry); }
+
+int launch_segreduce_basic(const SegLaunch &L, int sm_count, cudaStream_t stream, cudaEvent_t e0, cudaEvent_t e1) {
+    const int64_t ntiles = seg_num_tiles(L.g.n);
+    if (ntiles == 0) return 0;
+    if (L.ops & OPS_FIRSTLAST) return launch_ops<OPS_SUMCNT | OPS_MINMAX | OPS_FIRSTLAST>(L, ntiles, sm_count, stream, e0, e1);
+    if (L.ops & OPS_MINMAX) return launch_ops<OPS_SUMCNT | OPS_MINMAX>(L, ntiles, sm_count, stream, e0, e1);
+    return launch_ops<OPS_SUMCNT>(L, ntiles, sm_count, stream, e0, e1);
+}
+
+}  // namespace bowgpu

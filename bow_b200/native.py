@@ -1,0 +1,358 @@
+"""ctypes binding of libbowgpu.so (include/bowgpu.h) — the same C ABI the Go cgo shim binds.
+
+This module holds no algorithm: it marshals Arrow-layout buffers (numpy / pyarrow / raw device
+pointers) into `bowgpu_col` descriptors and calls the library.  If the library is missing or no
+B200 is visible it raises — there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbowgpu.so")
+
+FLOAT64, INT64 = 1, 2
+MEM_HOST, MEM_DEVICE = 0, 1
+
+AGG = dict(WindowStart=0, Count=1, Sum=2, ArithmeticMean=3, Min=4, Max=5, First=6, Last=7,
+           IntegralStep=8, IntegralTrapezoid=9, WeightedAverageStep=10, WeightedAverageLinear=11)
+INTERP = dict(WindowStart=0, Linear=1, StepPrevious=2, None_=3)
+STATUS = {0: "OK", 1: "EINVAL", 2: "ETYPE", 3: "EFIRSTNULL", 4: "EPREVROW", 5: "ENOINTERVALCOL", 6: "ECAPACITY",
+          7: "EUNSORTED", 8: "ENULLTIME", 9: "ECUDA", 10: "ENOMEM", 11: "EUNSUPPORTED"}
+
+# every symbol include/bowgpu.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "bowgpu_abi_version", "bowgpu_ctx_create", "bowgpu_ctx_destroy", "bowgpu_last_error", "bowgpu_status_string",
+    "bowgpu_ctx_synchronize", "bowgpu_ctx_enable_timing", "bowgpu_ctx_last_timing", "bowgpu_ctx_sm_count",
+    "bowgpu_frame_create", "bowgpu_frame_destroy", "bowgpu_frame_num_rows", "bowgpu_frame_num_cols",
+    "bowgpu_frame_col_dtype", "bowgpu_frame_col_has_validity", "bowgpu_frame_col_device_ptrs",
+    "bowgpu_frame_download", "bowgpu_frame_download_range", "bowgpu_frame_generate",
+    "bowgpu_rolling_create", "bowgpu_rolling_create_shard", "bowgpu_rolling_destroy", "bowgpu_rolling_num_windows",
+    "bowgpu_rolling_first_window_start", "bowgpu_rolling_inclusive", "bowgpu_rolling_early_rows",
+    "bowgpu_rolling_bounds", "bowgpu_rolling_aggregate", "bowgpu_agg_return_type", "bowgpu_agg_needs_inclusive",
+    "bowgpu_rolling_interpolate",
+]
+
+
+class BowGpuError(RuntimeError):
+    def __init__(self, code: int, msg: str = ""):
+        self.code = code
+        self.status = STATUS.get(code, str(code))
+        super().__init__(f"{self.status}: {msg}" if msg else self.status)
+
+
+class Col(C.Structure):
+    _fields_ = [("values", C.c_void_p), ("validity", C.c_void_p), ("offset", C.c_int64), ("length", C.c_int64),
+                ("null_count", C.c_int64), ("dtype", C.c_int32), ("_pad", C.c_int32)]
+
+
+class AggSpec(C.Structure):
+    _fields_ = [("op", C.c_int32), ("col", C.c_int32), ("nfactors", C.c_int32), ("_pad", C.c_int32),
+                ("factors", C.c_double * 4)]
+
+
+class OutCol(C.Structure):
+    _fields_ = [("values", C.c_void_p), ("validity", C.c_void_p), ("dtype", C.c_int32), ("_pad", C.c_int32)]
+
+
+class Timing(C.Structure):
+    _fields_ = [("total_ms", C.c_float), ("main_ms", C.c_float), ("launches", C.c_int32),
+                ("main_launches", C.c_int32)]
+
+
+class GenSpec(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("ncols", C.c_int32), ("nrows", C.c_int64), ("row0", C.c_int64),
+                ("t0", C.c_int64), ("step", C.c_int64), ("seed", C.c_uint64), ("null_mask", C.c_uint32),
+                ("int_mask", C.c_uint32), ("null_mod", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+_lib = None
+
+
+def lib():
+    """Loads libbowgpu.so (built by __graft_entry__.build()).  Fails loudly when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(bow_b200 has no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.bowgpu_last_error.restype = C.c_char_p
+        L.bowgpu_status_string.restype = C.c_char_p
+        for name in ("bowgpu_frame_num_rows", "bowgpu_rolling_num_windows", "bowgpu_rolling_first_window_start",
+                     "bowgpu_rolling_early_rows"):
+            getattr(L, name).restype = C.c_int64
+        L.bowgpu_ctx_destroy.restype = None
+        L.bowgpu_frame_destroy.restype = None
+        L.bowgpu_rolling_destroy.restype = None
+        L.bowgpu_ctx_create.argtypes = [C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.bowgpu_frame_create.argtypes = [C.c_void_p, C.POINTER(Col), C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+        L.bowgpu_frame_generate.argtypes = [C.c_void_p, C.POINTER(GenSpec), C.POINTER(C.c_void_p)]
+        L.bowgpu_frame_download.argtypes = [C.c_void_p, C.POINTER(OutCol), C.c_int32]
+        L.bowgpu_frame_download_range.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(OutCol), C.c_int32]
+        L.bowgpu_frame_col_device_ptrs.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p),
+                                                   C.POINTER(C.c_void_p)]
+        L.bowgpu_rolling_create.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.POINTER(Col),
+                                            C.POINTER(C.c_void_p)]
+        L.bowgpu_rolling_create_shard.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
+                                                  C.POINTER(Col), C.POINTER(C.c_void_p)]
+        L.bowgpu_rolling_bounds.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.bowgpu_rolling_aggregate.argtypes = [C.c_void_p, C.POINTER(AggSpec), C.c_int32, C.POINTER(OutCol),
+                                               C.c_int32]
+        L.bowgpu_rolling_interpolate.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int32,
+                                                 C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+        L.bowgpu_rolling_early_rows.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
+        for name in ("bowgpu_ctx_destroy", "bowgpu_frame_destroy", "bowgpu_rolling_destroy", "bowgpu_last_error",
+                     "bowgpu_ctx_synchronize", "bowgpu_ctx_sm_count", "bowgpu_frame_num_rows",
+                     "bowgpu_frame_num_cols", "bowgpu_rolling_num_windows", "bowgpu_rolling_first_window_start",
+                     "bowgpu_rolling_inclusive"):
+            getattr(L, name).argtypes = [C.c_void_p]
+        L.bowgpu_ctx_enable_timing.argtypes = [C.c_void_p, C.c_int32]
+        L.bowgpu_ctx_last_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
+        L.bowgpu_frame_col_dtype.argtypes = [C.c_void_p, C.c_int32]
+        L.bowgpu_frame_col_has_validity.argtypes = [C.c_void_p, C.c_int32]
+        assert L.bowgpu_abi_version() == 1
+        _lib = L
+    return _lib
+
+
+def pack_bits(mask: np.ndarray, offset: int = 0) -> np.ndarray:
+    """LSB-first Arrow validity bitmap with `offset` leading bits (set, so misuse shows)."""
+    full = np.concatenate([np.ones(offset, dtype=bool), np.asarray(mask, dtype=bool)])
+    return np.packbits(full, bitorder="little")
+
+
+def unpack_bits(bitmap: np.ndarray, n: int) -> np.ndarray:
+    return np.unpackbits(np.asarray(bitmap, dtype=np.uint8), bitorder="little")[:n].astype(bool)
+
+
+NpCol = Tuple[np.ndarray, Optional[np.ndarray]]
+
+
+def cols_from_numpy(cols: Sequence[NpCol], offset: int = 0):
+    """-> (ctypes Col array, keep-alive list).  cols: (values int64|float64, bool mask | None)."""
+    keep = []
+    arr = (Col * max(1, len(cols)))()
+    for j, (v, m) in enumerate(cols):
+        v = np.ascontiguousarray(v)
+        assert v.dtype in (np.int64, np.float64), v.dtype
+        n = len(v)
+        if offset:
+            v = np.concatenate([np.full(offset, 123456789, dtype=v.dtype), v])
+        bm = pack_bits(m, offset) if m is not None else None
+        keep += [v, bm]
+        arr[j].values = v.ctypes.data
+        arr[j].validity = bm.ctypes.data if bm is not None else None
+        arr[j].offset = offset
+        arr[j].length = n
+        arr[j].null_count = int(n - np.count_nonzero(m)) if m is not None else 0
+        arr[j].dtype = INT64 if v.dtype == np.int64 else FLOAT64
+    return arr, keep
+
+
+class Ctx:
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self.h = C.c_void_p()
+        rc = lib().bowgpu_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(self.h))
+        if rc:
+            raise BowGpuError(rc, "bowgpu_ctx_create failed (is a B200 visible? bow_b200 has no CPU fallback)")
+        self.device = device
+
+    def check(self, rc: int):
+        if rc:
+            raise BowGpuError(rc, lib().bowgpu_last_error(self.h).decode())
+
+    def synchronize(self):
+        self.check(lib().bowgpu_ctx_synchronize(self.h))
+
+    def enable_timing(self, on: bool = True):
+        self.check(lib().bowgpu_ctx_enable_timing(self.h, int(on)))
+
+    def last_timing(self) -> Timing:
+        t = Timing()
+        self.check(lib().bowgpu_ctx_last_timing(self.h, C.byref(t)))
+        return t
+
+    @property
+    def sm_count(self) -> int:
+        return lib().bowgpu_ctx_sm_count(self.h)
+
+    def close(self):
+        if self.h:
+            lib().bowgpu_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Frame:
+    """Device-resident Bow."""
+
+    def __init__(self, ctx: Ctx, handle: C.c_void_p, keep=None):
+        self.ctx, self.h, self.keep = ctx, handle, keep
+
+    @classmethod
+    def from_numpy(cls, ctx: Ctx, cols: Sequence[NpCol], offset: int = 0) -> "Frame":
+        arr, keep = cols_from_numpy(cols, offset)
+        h = C.c_void_p()
+        ctx.check(lib().bowgpu_frame_create(ctx.h, arr, len(cols), MEM_HOST, C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def from_col_descs(cls, ctx: Ctx, arr, ncols: int, mem: int, keep=None) -> "Frame":
+        h = C.c_void_p()
+        ctx.check(lib().bowgpu_frame_create(ctx.h, arr, ncols, mem, C.byref(h)))
+        return cls(ctx, h, keep if mem == MEM_DEVICE else None)
+
+    @classmethod
+    def generate(cls, ctx: Ctx, nrows: int, ncols: int = 1, row0: int = 0, t0: int = 1_700_000_000_000_000_000,
+                 step: int = 1_000_000_000, seed: int = 42, null_mask: int = 0, int_mask: int = 0,
+                 null_mod: int = 10, kind: int = 0) -> "Frame":
+        g = GenSpec(kind, ncols, nrows, row0, t0, step, seed, null_mask, int_mask, null_mod, 0)
+        h = C.c_void_p()
+        ctx.check(lib().bowgpu_frame_generate(ctx.h, C.byref(g), C.byref(h)))
+        return cls(ctx, h)
+
+    @property
+    def num_rows(self) -> int:
+        return lib().bowgpu_frame_num_rows(self.h)
+
+    @property
+    def num_cols(self) -> int:
+        return lib().bowgpu_frame_num_cols(self.h)
+
+    def dtype(self, j: int) -> int:
+        return lib().bowgpu_frame_col_dtype(self.h, j)
+
+    def device_ptrs(self, j: int) -> Tuple[int, int]:
+        v, b = C.c_void_p(), C.c_void_p()
+        self.ctx.check(lib().bowgpu_frame_col_device_ptrs(self.h, j, C.byref(v), C.byref(b)))
+        return v.value or 0, b.value or 0
+
+    def download(self, row0: int = 0, nrows: Optional[int] = None) -> List[NpCol]:
+        n = self.num_rows - row0 if nrows is None else nrows
+        nc = self.num_cols
+        outs = (OutCol * max(1, nc))()
+        bufs = []
+        for j in range(nc):
+            v = np.zeros(max(n, 1), dtype=np.int64)
+            b = np.zeros((n + 7) // 8 + 1, dtype=np.uint8)
+            bufs.append((v, b))
+            outs[j].values, outs[j].validity = v.ctypes.data, b.ctypes.data
+        self.ctx.check(lib().bowgpu_frame_download_range(self.h, row0, n, outs, nc))
+        res = []
+        for j, (v, b) in enumerate(bufs):
+            vals = v[:n] if outs[j].dtype == INT64 else v[:n].view(np.float64)
+            res.append((vals, unpack_bits(b, n)))
+        return res
+
+    def close(self):
+        if self.h:
+            lib().bowgpu_frame_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def make_specs(specs: Sequence[tuple]):
+    """specs: (op name|code, col index[, [factors]])"""
+    arr = (AggSpec * len(specs))()
+    for j, s in enumerate(specs):
+        arr[j].op = AGG[s[0]] if isinstance(s[0], str) else int(s[0])
+        arr[j].col = s[1]
+        fs = list(s[2]) if len(s) > 2 and s[2] else []
+        arr[j].nfactors = len(fs)
+        for k, f in enumerate(fs):
+            arr[j].factors[k] = f
+    return arr
+
+
+class Rolling:
+    """intervalRolling on a device frame (bowgpu_rolling)."""
+
+    def __init__(self, frame: Frame, time_col: int, interval: int, offset: int = 0, inclusive: bool = False,
+                 prev_row: Optional[Sequence[NpCol]] = None, shard: Optional[Tuple[int, int]] = None):
+        """shard = (s0, num_windows): range-partitioned variant (bowgpu_rolling_create_shard)."""
+        self.frame, self.ctx = frame, frame.ctx
+        self.h = C.c_void_p()
+        parr, self._keep = (None, None)
+        if prev_row is not None:
+            parr, self._keep = cols_from_numpy(prev_row)
+        if shard is not None:
+            self.ctx.check(lib().bowgpu_rolling_create_shard(frame.h, time_col, interval, shard[0], shard[1],
+                                                             int(inclusive), parr, C.byref(self.h)))
+        else:
+            self.ctx.check(lib().bowgpu_rolling_create(frame.h, time_col, interval, offset, int(inclusive), parr,
+                                                       C.byref(self.h)))
+
+    @property
+    def num_windows(self) -> int:
+        return lib().bowgpu_rolling_num_windows(self.h)
+
+    @property
+    def first_window_start(self) -> int:
+        return lib().bowgpu_rolling_first_window_start(self.h)
+
+    def early_rows(self) -> Tuple[int, bool]:
+        kept = C.c_int32()
+        n = lib().bowgpu_rolling_early_rows(self.h, C.byref(kept))
+        return n, bool(kept.value)
+
+    def bounds(self):
+        """-> (first[W+1] int64, inclusive[W] bool)"""
+        W = self.num_windows
+        first = np.zeros(W + 1, dtype=np.int64)
+        inc = np.zeros((W + 7) // 8 + 1, dtype=np.uint8)
+        self.ctx.check(lib().bowgpu_rolling_bounds(self.h, first.ctypes.data, inc.ctypes.data))
+        return first, unpack_bits(inc, W)
+
+    def aggregate(self, specs: Sequence[tuple]):
+        """-> list of (values ndarray, valid mask ndarray), host memory"""
+        W = self.num_windows
+        arr = make_specs(specs)
+        outs = (OutCol * len(specs))()
+        bufs = []
+        for j in range(len(specs)):
+            v = np.full(max(W, 1), -7, dtype=np.int64)          # poisoned: every slot must be written
+            b = np.full((W + 7) // 8 + 1, 0xAA, dtype=np.uint8)
+            bufs.append((v, b))
+            outs[j].values, outs[j].validity = v.ctypes.data, b.ctypes.data
+        self.ctx.check(lib().bowgpu_rolling_aggregate(self.h, arr, len(specs), outs, MEM_HOST))
+        res = []
+        for j, (v, b) in enumerate(bufs):
+            vals = v[:W] if outs[j].dtype == INT64 else v[:W].view(np.float64)
+            res.append((vals, unpack_bits(b, W)))
+        return res
+
+    def aggregate_device(self, specs_arr, nspecs: int, outs) -> None:
+        """Asynchronous: results stay on the device (outs: OutCol array of device pointers)."""
+        self.ctx.check(lib().bowgpu_rolling_aggregate(self.h, specs_arr, nspecs, outs, MEM_DEVICE))
+
+    def interpolate(self, ops: Sequence) -> Frame:
+        codes = (C.c_int32 * len(ops))(*[INTERP[o] if isinstance(o, str) else int(o) for o in ops])
+        h, n_out = C.c_void_p(), C.c_int64()
+        self.ctx.check(lib().bowgpu_rolling_interpolate(self.h, codes, len(ops), C.byref(h), C.byref(n_out)))
+        return Frame(self.ctx, h)
+
+    def close(self):
+        if self.h:
+            lib().bowgpu_rolling_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass

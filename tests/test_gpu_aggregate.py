@@ -1,0 +1,215 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle: window bounds and the basic
+aggregation family.  Bit-exact for bounds / Count / Min / Max / First / Last / WindowStart and for
+validity bitmaps; float64 Sum / ArithmeticMean within 1e-12 * max(|ref|, sum|terms|) (reduction
+order differs from the reference's left-to-right loop)."""
+import numpy as np
+import pytest
+
+from oracle import literal as L
+from oracle import refc as R
+from tests import helpers as H
+from tests.golden import reference_vectors as G
+
+pytestmark = pytest.mark.gpu
+
+EXACT = {"WindowStart", "Count", "Min", "Max", "First", "Last"}
+TOL = 1e-12
+BASIC = ["WindowStart", "Count", "Sum", "ArithmeticMean", "Min", "Max", "First", "Last"]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from bow_b200 import native as N
+    c = N.Ctx(0)
+    yield c
+    c.close()
+
+
+def bits(a):
+    return np.asarray(a).view(np.int64) if np.asarray(a).dtype == np.float64 else np.asarray(a)
+
+
+def compare_aggs(names, got, want, abs_sums=None, what=""):
+    assert len(got) == len(want)
+    for j, name in enumerate(names):
+        (gv, gm), (wv, wm) = got[j], want[j]
+        assert gv.dtype == wv.dtype, (what, name, gv.dtype, wv.dtype)
+        assert np.array_equal(gm, wm), f"{what} {name}: validity differs at {np.flatnonzero(gm != wm)[:10]}"
+        if name in EXACT:
+            bad = np.flatnonzero(bits(gv) != bits(wv))
+            # NaN payloads are not compared (see tests/helpers.same_value)
+            if gv.dtype == np.float64:
+                bad = bad[~(np.isnan(gv[bad]) & np.isnan(wv[bad]))]
+            assert bad.size == 0, f"{what} {name}: {bad[:10]} got {gv[bad[:10]]} want {wv[bad[:10]]}"
+        else:
+            scale = np.maximum(np.abs(wv), abs_sums if abs_sums is not None else 0.0)
+            with np.errstate(invalid="ignore"):
+                err = np.abs(gv - wv)
+            same = (bits(gv) == bits(wv)) | (np.isnan(gv) & np.isnan(wv))
+            bad = np.flatnonzero(~same & ~(err <= TOL * scale))
+            assert bad.size == 0, f"{what} {name}: {bad[:10]} got {gv[bad[:10]]} want {wv[bad[:10]]}"
+        # null slots hold value 0 (bowbuffer.go:22-40)
+        assert not np.any(bits(gv)[~gm]), f"{what} {name}: non-zero value in a null slot"
+
+
+def run_both(ctx, cols, interval, specs, offset=0, inclusive=False, slice_offset=0):
+    from bow_b200 import native as N
+    fr = N.Frame.from_numpy(ctx, cols, offset=slice_offset)
+    r = N.Rolling(fr, 0, interval, offset=offset, inclusive=inclusive)
+    got = r.aggregate(specs)
+    ref = R.RefRolling(R.Frame(cols), 0, interval, offset=offset, inclusive=inclusive)
+    assert r.num_windows == ref.num_windows
+    assert r.first_window_start == ref.first_window_start or len(cols[0][0]) == 0
+    want = ref.aggregate(specs)
+    # sum |v| per window for the tolerance of the float reductions
+    abs_sums = None
+    vcol = specs[-1][1]
+    if cols[vcol][0].dtype == np.float64 or True:
+        v, m = cols[vcol]
+        av = np.abs(v.astype(np.float64))
+        av = np.where(np.isfinite(av), av, 0.0)
+        abs_ref = R.RefRolling(R.Frame([cols[0], (av, m)]), 0, interval, offset=offset, inclusive=inclusive)
+        abs_sums = abs_ref.aggregate([("Sum", 1)])[0][0]
+    r.close()
+    fr.close()
+    return got, want, abs_sums
+
+
+@pytest.mark.parametrize("agg,fixture,factor,vtype,expected,cite", G.AGGREGATIONS,
+                         ids=[f"{c[0]}-{c[1]}-{c[2]}" for c in G.AGGREGATIONS])
+def test_golden_aggregations(ctx, agg, fixture, factor, vtype, expected, cite):
+    from bow_b200 import native as N
+    if N.AGG[agg] >= 8:
+        pytest.skip("integral family: see test_gpu_integral.py")
+    rows = G.FIXTURES[fixture]
+    cols = H.np_cols_from_lists([[r[0] for r in rows], [r[1] for r in rows]], [L.INT64, L.FLOAT64])
+    fr = N.Frame.from_numpy(ctx, cols)
+    r = N.Rolling(fr, 0, 10)
+    out = H.lists_from_np(r.aggregate([("WindowStart", 0), (agg, 1, [factor] if factor is not None else [])]))
+    H.assert_cols_equal(out, [[r[0] for r in expected], [r[1] for r in expected]], cite)
+
+
+@pytest.mark.parametrize("name,opts,expected", G.ITERATE, ids=[c[0] for c in G.ITERATE])
+def test_golden_bounds(ctx, name, opts, expected):
+    from bow_b200 import native as N
+    cols = H.np_cols_from_lists(G.ITERATE_COLS, [L.INT64, L.FLOAT64])
+    fr = N.Frame.from_numpy(ctx, cols)
+    r = N.Rolling(fr, 0, G.ITERATE_INTERVAL, **opts)
+    first, inc = r.bounds()
+    s0 = r.first_window_start
+    got = []
+    for k in range(r.num_windows):
+        lo, hi = int(first[k]), int(first[k + 1]) + int(inc[k])
+        got.append((k, s0 + k * G.ITERATE_INTERVAL, s0 + (k + 1) * G.ITERATE_INTERVAL, lo,
+                    G.ITERATE_COLS[0][lo:hi], G.ITERATE_COLS[1][lo:hi]))
+    assert got == expected
+
+
+CASES = []
+for kind in ("regular", "dense", "sparse", "bursty"):
+    for n in (1, 2, 16, 17, 18, 300, 2175, 2176, 2177, 2178, 4352, 4353, 10000, 70001):
+        CASES.append((kind, n))
+
+
+@pytest.mark.parametrize("kind,n", CASES, ids=[f"{k}-{n}" for k, n in CASES])
+def test_random_vs_oracle(ctx, kind, n):
+    rng = np.random.default_rng(hash((kind, n)) & 0xFFFF)
+    for trial in range(4):
+        t = H.random_times(rng, n, kind)
+        dtype = np.int64 if trial == 1 else np.float64
+        null_p = [0.0, 0.3, 0.1, 0.9][trial]
+        v = H.random_values(rng, n, dtype, null_p, specials=(trial == 2))
+        interval = int(rng.choice([1, 2, 5, 10, 60, 1000, 100000]))
+        offset = int(rng.integers(-2 * interval, 2 * interval))
+        inclusive = bool(rng.integers(0, 2))
+        cols = [(t, None), v]
+        specs = [("WindowStart", 0)] + [(a, 1) for a in BASIC[1:]]
+        got, want, abs_sums = run_both(ctx, cols, interval, specs, offset=offset, inclusive=inclusive,
+                                       slice_offset=int(rng.integers(0, 70)) if trial == 3 else 0)
+        compare_aggs(BASIC, got, want, abs_sums, what=f"{kind} n={n} I={interval} off={offset} inc={inclusive}")
+
+
+@pytest.mark.parametrize("kind", ["regular", "dense", "sparse", "bursty"])
+def test_random_bounds_vs_oracle(ctx, kind):
+    from bow_b200 import native as N
+    rng = np.random.default_rng(7)
+    for n in (1, 5, 100, 2176, 2177, 30000):
+        for trial in range(3):
+            t = H.random_times(rng, n, kind)
+            interval = int(rng.choice([1, 3, 10, 500]))
+            offset = int(rng.integers(-interval, interval))
+            inclusive = bool(trial % 2)
+            cols = [(t, None)]
+            fr = N.Frame.from_numpy(ctx, cols)
+            r = N.Rolling(fr, 0, interval, offset=offset, inclusive=inclusive)
+            first, inc = r.bounds()
+            w = R.RefRolling(R.Frame(cols), 0, interval, offset=offset, inclusive=inclusive).windows()
+            W = r.num_windows
+            assert W == len(w["lo"])
+            early, kept = r.early_rows()
+            assert np.array_equal(first[:W], w["first_index"]), (kind, n, interval, offset)
+            hi = first[1:] + inc
+            lo = first[:W].copy()
+            if early and not kept:      # rows before s0 are dropped with an empty window 0
+                hi[0] = lo[0]
+            nonempty = w["hi"] > w["lo"]
+            assert np.array_equal(hi[nonempty], w["hi"][nonempty]), (kind, n, interval, offset, inclusive)
+            assert np.array_equal(hi[~nonempty], lo[~nonempty])
+            assert np.array_equal(inc, w["is_inclusive"])
+            assert first[W] == n
+
+
+def test_multi_column_and_duplicates(ctx):
+    rng = np.random.default_rng(3)
+    n = 20000
+    t = H.random_times(rng, n, "regular")
+    a = H.random_values(rng, n, np.float64, 0.2)
+    b = H.random_values(rng, n, np.int64, 0.0)
+    cols = [(t, None), a, b]
+    specs = [("Sum", 1), ("WindowStart", 0), ("Sum", 1), ("Count", 2), ("Count", 2, [2.5]), ("Max", 2), ("Last", 2),
+             ("Count", 0), ("First", 0), ("ArithmeticMean", 1, [0.1]), ("Min", 1, [3.0, -1.0])]
+    names = [s[0] for s in specs]
+    from bow_b200 import native as N
+    fr = N.Frame.from_numpy(ctx, cols)
+    r = N.Rolling(fr, 0, 37, offset=5)
+    got = r.aggregate(specs)
+    want = R.RefRolling(R.Frame(cols), 0, 37, offset=5).aggregate(specs)
+    tolerant = {"Sum", "ArithmeticMean", "Min"}   # Min here carries factors applied to an exact value: still exact
+    for j, name in enumerate(names):
+        (gv, gm), (wv, wm) = got[j], want[j]
+        assert np.array_equal(gm, wm), name
+        if name in ("Sum", "ArithmeticMean"):
+            assert np.allclose(gv, wv, rtol=1e-12, atol=1e-9), name
+        else:
+            assert np.array_equal(bits(gv), bits(wv)), (j, name)
+
+
+def test_errors(ctx):
+    from bow_b200 import native as N
+    t = np.array([3, 2, 1, 5], dtype=np.int64)
+    v = np.array([1.0, 2.0, 3.0, 4.0])
+    fr = N.Frame.from_numpy(ctx, [(t, None), (v, None)])
+    with pytest.raises(N.BowGpuError, match="EINVAL"):
+        N.Rolling(fr, 0, 0)
+    with pytest.raises(N.BowGpuError, match="ETYPE"):
+        N.Rolling(fr, 1, 10)
+    r = N.Rolling(fr, 0, 10)
+    with pytest.raises(N.BowGpuError, match="ENOINTERVALCOL"):
+        r.aggregate([("Sum", 1)])
+    with pytest.raises(N.BowGpuError, match="EUNSORTED"):
+        r.aggregate([("WindowStart", 0), ("Sum", 1)])
+    with pytest.raises(N.BowGpuError, match="EUNSORTED"):
+        r.bounds()
+    # the sticky flag is cleared: a sorted frame works afterwards
+    fr2 = N.Frame.from_numpy(ctx, [(np.sort(t), None), (v, None)])
+    out = N.Rolling(fr2, 0, 10).aggregate([("WindowStart", 0), ("Sum", 1)])
+    assert out[1][0][0] == 10.0
+    tn = (np.array([1, 2, 3], dtype=np.int64), np.array([True, False, True]))
+    fr3 = N.Frame.from_numpy(ctx, [tn])
+    with pytest.raises(N.BowGpuError, match="ENULLTIME"):
+        N.Rolling(fr3, 0, 10)
+    # empty frame
+    fr4 = N.Frame.from_numpy(ctx, [(np.zeros(0, dtype=np.int64), None), (np.zeros(0), None)])
+    r4 = N.Rolling(fr4, 0, 10)
+    assert r4.num_windows == 0
+    assert r4.aggregate([("WindowStart", 0), ("Sum", 1)])[0][0].size == 0
