@@ -29,6 +29,8 @@
 
 #include <math_constants.h>
 
+#include <cstdlib>
+
 namespace bowgpu {
 
 namespace {
@@ -36,6 +38,7 @@ namespace {
 constexpr int SEG_NT = 128;
 constexpr int SEG_R = 17;
 constexpr int SEG_MAX_STAGES = 8;
+constexpr int SEG_MIN_CTAS = 2;
 using SegG = TileGeom<SEG_NT, SEG_R>;
 constexpr int SEG_NW = SEG_NT / 32;
 constexpr int SEG_STAGE_BYTES = SegG::TIME_BYTES + SegG::VAL_BYTES + SegG::BITS_STRIDE;
@@ -126,23 +129,238 @@ __device__ __forceinline__ void write_window(const BasicOut &o, int64_t W, int64
     if (o.last) o.last[k] = last;
 }
 
-template <uint32_t OPS, bool IS_INT, bool HAS_NULLS>
-__global__ void __launch_bounds__(SEG_NT, 2)
-    segreduce_basic_kernel(const SegLaunch P, const int64_t ntiles, const int nstages) {
+// exact division on the rare path (a gap of two or more windows between consecutive rows)
+__device__ __noinline__ uint64_t div_slow(uint64_t x, uint64_t d, double inv_rd) {
+    DivU64 dv{d, inv_rd};
+    return div_u64(x, dv);
+}
+
+// Windows that begin AND end strictly inside one thread's rows (only when windows are shorter than
+// R rows): rows (jfirst, jlast] of the thread are re-reduced window by window from shared memory in a
+// rolled loop and written out directly.  Kept out of line so the unrolled fast path stays small.
+template <uint32_t OPS, bool IS_INT>
+__device__ __noinline__ void middle_windows(const BasicOut *outp, int64_t W, uint64_t d, double inv_rd, int64_t s0,
+                                            const int64_t *trow, const uint64_t *vrow, uint32_t vbits, int ti0,
+                                            int jfirst, int jlast, uint64_t kstart) {
+    const BasicOut o = *outp;
+    BState st = st_identity<OPS>();
+    uint64_t kcur = kstart;
+    uint64_t erel = (kcur + 1) * d;
+    for (int j = jfirst + 1; j <= jlast; ++j) {
+        if ((vbits >> j) & 1u) st_accumulate<OPS, IS_INT>(st, vrow[j], (uint32_t)(ti0 + j));
+        const uint64_t xn = (uint64_t)trow[j + 1] - (uint64_t)s0;
+        if (j == jlast || xn >= erel) {
+            const uint64_t fb = st.cnt ? vrow[st.fi - ti0] : 0, lb = st.cnt ? vrow[st.li - ti0] : 0;
+            write_window<IS_INT>(o, W, (int64_t)kcur, st.cnt, st.sum, st.mn, st.mx, fb, lb);
+            st = st_identity<OPS>();
+            if (xn - erel < d) {
+                ++kcur;
+                erel += d;
+            } else {
+                kcur = div_slow(xn, d, inv_rd);
+                erel = (kcur + 1) * d;
+            }
+        }
+    }
+}
+
+// One tile.  FULL: every row of the tile, the row before it and the row after it exist and no row
+// lies before s0 — the common case, free of per-row existence predicates.
+template <uint32_t OPS, bool IS_INT, bool HAS_NULLS, bool FULL>
+__device__ __forceinline__ void seg_tile(const SegLaunch &P, const BasicOut *sh_out, const int64_t tile,
+                                         const uint8_t *sb, WarpTotal *wtot, volatile int *sh_flags, bool &bad) {
     using G = SegG;
     constexpr int R = G::R;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const WindowGeom &g = P.g;
+    const uint64_t d = g.div.d;
+    const int64_t *tsm = reinterpret_cast<const int64_t *>(sb);
+    const uint64_t *vsm = reinterpret_cast<const uint64_t *>(sb + G::TIME_BYTES);
+    const uint32_t *bsm = reinterpret_cast<const uint32_t *>(sb + G::TIME_BYTES + G::VAL_BYTES);
+    const int64_t r0 = tile * G::T;
+    const int64_t nrem = g.n - r0;  // rows from the tile start to the end of the column (> 0)
+    const int nrem_i = nrem > G::T + 2 ? G::T + 2 : (int)nrem;
+    const int ti0 = tid * R;
+    const bool early_tile = !FULL && r0 < g.early_rows;
+
+    // window-relative time of a row (rows before s0 collapse onto window 0, see WindowGeom)
+    auto xrel = [&](int64_t x, int ti) -> uint64_t {
+        if (!FULL && early_tile && r0 + ti < g.early_rows) return 0;
+        return (uint64_t)x - (uint64_t)g.s0;
+    };
+    auto exists = [&](int ti) -> bool { return FULL || ti < nrem_i; };
+
+    uint32_t vbits = (1u << R) - 1u;
+    if (HAS_NULLS) {
+        const uint32_t lo = bsm[ti0 >> 5], hi = bsm[(ti0 >> 5) + 1];
+        vbits &= __funnelshift_r(lo, hi, ti0 & 31);
+    }
+    if (!FULL && early_tile && !g.early_keep) {
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+            if (r0 + ti0 + j < g.early_rows) vbits &= ~(1u << j);
+    }
+
+    int64_t x[R + 1];
+    uint64_t raw[R];
+#pragma unroll
+    for (int j = 0; j <= R; ++j) x[j] = tsm[ti0 + 2 + j];
+#pragma unroll
+    for (int j = 0; j < R; ++j) raw[j] = vsm[ti0 + j];
+
+    // precondition check: time sorted ascending (every adjacent pair is checked exactly once)
+    if (FULL || (exists(ti0) && r0 + ti0 > 0)) bad |= x[0] < tsm[ti0 + 1];
+#pragma unroll
+    for (int j = 1; j < R; ++j)
+        if (exists(ti0 + j)) bad |= x[j] < x[j - 1];
+
+    BState st = st_identity<OPS>();
+    BState head = st_identity<OPS>();
+    int nclosed = 0, jfirst = 0, jlast = 0;
+    uint64_t kcur = 0, kf = 0, kmid = 0, erel = 0;
+    if (exists(ti0)) {
+        kcur = div_u64(xrel(x[0], ti0), g.div);
+        kf = kcur;
+        erel = (kcur + 1) * d;
+    }
+    if (tid == 0) {
+        int lo_open = 0;
+        if (r0 > 0) lo_open = div_u64(xrel(tsm[1], -1), g.div) == kcur;
+        sh_flags[0] = lo_open;
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        if (exists(ti0 + j)) {
+            if ((vbits >> j) & 1u) st_accumulate<OPS, IS_INT>(st, raw[j], (uint32_t)(ti0 + j));
+            const bool next_exists = exists(ti0 + j + 1);
+            const uint64_t xn = xrel(x[j + 1], ti0 + j + 1);
+            if (!next_exists || xn >= erel) {  // the window of row j closes here
+                if (nclosed == 0) {
+                    head = st;
+                    jfirst = j;
+                }
+                ++nclosed;
+                jlast = j;
+                st = st_identity<OPS>();
+                if (next_exists) {
+                    if (xn - erel < d) {
+                        ++kcur;
+                        erel += d;
+                    } else {
+                        kcur = div_slow(xn, d, g.div.inv_rd);
+                        erel = (kcur + 1) * d;
+                    }
+                    if (nclosed == 1) kmid = kcur;
+                }
+            }
+        }
+    }
+    // windows lying strictly inside this thread's rows (short windows only)
+    if (nclosed >= 2)
+        middle_windows<OPS, IS_INT>(sh_out, g.W, d, g.div.inv_rd, g.s0, tsm + ti0 + 2, vsm + ti0, vbits, ti0, jfirst,
+                                    jlast, kmid);
+
+    // ---- stitch windows spanning threads: segmented inclusive scan of the tails -------------
+    uint32_t f = nclosed > 0;
+    BState sc = st;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) {
+        const BState o = st_shfl_up<OPS>(sc, dd);
+        const uint32_t of = __shfl_up_sync(0xffffffffu, f, dd);
+        if (lane >= dd) {
+            if (!f) sc = st_combine<OPS>(o, sc);
+            f |= of;
+        }
+    }
+    const uint32_t ball = __ballot_sync(0xffffffffu, nclosed > 0);
+    if (lane == 31) {
+        wtot[warp].st = sc;
+        wtot[warp].flag = ball != 0;
+    }
+    BState ex = st_shfl_up<OPS>(sc, 1);
+    if (lane == 0) ex = st_identity<OPS>();
+    __syncthreads();
+    const bool left_open = sh_flags[0] != 0;
+    BState acc = st_identity<OPS>();
+    bool any_prev = false;
+    for (int u = 0; u < warp; ++u) {
+        const BState ws = wtot[u].st;
+        if (wtot[u].flag) {
+            acc = ws;
+            any_prev = true;
+        } else {
+            acc = st_combine<OPS>(acc, ws);
+        }
+    }
+    const bool flag_before = (ball & ((1u << lane) - 1u)) != 0;
+    const BState excl = flag_before ? ex : st_combine<OPS>(acc, ex);
+    const bool any_excl = any_prev || flag_before;
+
+    if (nclosed > 0) {  // this thread closes the window that was open at its left edge
+        const BState h = st_combine<OPS>(excl, head);
+        const uint64_t fb = h.cnt ? vsm[h.fi] : 0, lb = h.cnt ? vsm[h.li] : 0;
+        if (!any_excl && left_open) {
+            BasicCarry c;
+            c.key = (int64_t)kf;
+            c.cnt = (int64_t)h.cnt | CLOSED_BIT;
+            c.sum = h.sum;
+            c.mn = h.mn;
+            c.mx = h.mx;
+            c.first = fb;
+            c.last = lb;
+            c._pad = 0;
+            P.carry_head[tile] = c;
+        } else {
+            write_window<IS_INT>(P.out, g.W, (int64_t)kf, h.cnt, h.sum, h.mn, h.mx, fb, lb);
+        }
+    }
+    if (tid == SEG_NT - 1) {  // tile-level records: the window open at the right edge
+        const bool flag_incl = flag_before || nclosed > 0;
+        const BState incl = flag_incl ? sc : st_combine<OPS>(acc, sc);
+        const bool any_incl = any_prev || flag_incl;
+        const int lim = nrem < G::T ? (int)nrem : G::T;
+        const int lastrow = lim - 1;
+        const bool next_exists = lim < nrem;
+        const uint64_t klast = div_u64(xrel(tsm[lastrow + 2], lastrow), g.div);
+        const bool closes = !next_exists || div_u64(xrel(tsm[lastrow + 3], lastrow + 1), g.div) != klast;
+        BasicCarry c;
+        c.key = (int64_t)klast;
+        c.cnt = (int64_t)incl.cnt;
+        c.sum = incl.sum;
+        c.mn = incl.mn;
+        c.mx = incl.mx;
+        c.first = incl.cnt ? vsm[incl.fi] : 0;
+        c.last = incl.cnt ? vsm[incl.li] : 0;
+        c._pad = 0;
+        BasicCarry none = c;
+        none.key = -1;
+        if (!any_incl && left_open) {  // the whole tile lies inside one window that began earlier
+            P.carry_head[tile] = c;    // not closed
+            P.carry_tail[tile] = none;
+        } else {
+            if (!left_open) P.carry_head[tile] = none;
+            P.carry_tail[tile] = closes ? none : c;
+        }
+    }
+}
+
+template <uint32_t OPS, bool IS_INT, bool HAS_NULLS>
+__global__ void __launch_bounds__(SEG_NT, SEG_MIN_CTAS)
+    segreduce_basic_kernel(const SegLaunch P, const int64_t ntiles, const int nstages) {
+    using G = SegG;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);                       // [SEG_MAX_STAGES]
     WarpTotal *wtot = reinterpret_cast<WarpTotal *>(smem_raw + 64);                // [SEG_NW]
     volatile int *sh_flags = reinterpret_cast<volatile int *>(smem_raw + 64 + SEG_NW * sizeof(WarpTotal));
+    BasicOut *sh_out = reinterpret_cast<BasicOut *>(smem_raw + 512);
     uint8_t *stages = smem_raw + SEG_HEADER_BYTES;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const WindowGeom &g = P.g;
-    const uint64_t d = g.div.d;
     TileSrc src{P.time, P.values, HAS_NULLS ? P.validity : nullptr, g.n};
 
     if (tid == 0) {
+        *sh_out = P.out;
         for (int s = 0; s < nstages; ++s) mbar_init(&full[s], 1);
         fence_mbar_init();
         fence_proxy_async();
@@ -160,168 +378,12 @@ __global__ void __launch_bounds__(SEG_NT, 2)
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         mbar_wait(&full[stage], phase);
         const uint8_t *sb = stages + (size_t)stage * SEG_STAGE_BYTES;
-        const int64_t *tsm = reinterpret_cast<const int64_t *>(sb);
-        const uint64_t *vsm = reinterpret_cast<const uint64_t *>(sb + G::TIME_BYTES);
-        const uint32_t *bsm = reinterpret_cast<const uint32_t *>(sb + G::TIME_BYTES + G::VAL_BYTES);
         const int64_t r0 = tile * G::T;
-        const int64_t nrem = g.n - r0;  // rows from the tile start to the end of the column (> 0)
-        const int ti0 = tid * R;
-        const bool early_tile = r0 < g.early_rows;
-
-        // window-relative time of a row (rows before s0 collapse onto window 0, see WindowGeom)
-        auto xrel = [&](int64_t x, int64_t ti) -> uint64_t {
-            if (early_tile && r0 + ti < g.early_rows) return 0;
-            return (uint64_t)x - (uint64_t)g.s0;
-        };
-
-        uint32_t vbits = (1u << R) - 1u;
-        if (HAS_NULLS) {
-            const uint32_t lo = bsm[ti0 >> 5], hi = bsm[(ti0 >> 5) + 1];
-            vbits &= __funnelshift_r(lo, hi, ti0 & 31);
-        }
-        if (early_tile && !g.early_keep) {
-#pragma unroll
-            for (int j = 0; j < R; ++j)
-                if (r0 + ti0 + j < g.early_rows) vbits &= ~(1u << j);
-        }
-
-        int64_t x[R + 1];
-        uint64_t raw[R];
-#pragma unroll
-        for (int j = 0; j <= R; ++j) x[j] = tsm[ti0 + 2 + j];
-#pragma unroll
-        for (int j = 0; j < R; ++j) raw[j] = vsm[ti0 + j];
-
-        // precondition check: time sorted ascending (every adjacent pair is checked exactly once)
-        if (ti0 < nrem && r0 + ti0 > 0) bad |= x[0] < tsm[ti0 + 1];
-#pragma unroll
-        for (int j = 1; j < R; ++j)
-            if (ti0 + j < nrem) bad |= x[j] < x[j - 1];
-
-        BState st = st_identity<OPS>();
-        BState head = st_identity<OPS>();
-        int nclosed = 0;
-        uint64_t kcur = 0, kf = 0, erel = 0;
-        if (ti0 < nrem) {
-            kcur = div_u64(xrel(x[0], ti0), g.div);
-            kf = kcur;
-            erel = (kcur + 1) * d;
-        }
-        if (tid == 0) {
-            int lo_open = 0;
-            if (r0 > 0) lo_open = div_u64(xrel(tsm[1], -1), g.div) == kcur;
-            sh_flags[0] = lo_open;
-        }
-#pragma unroll
-        for (int j = 0; j < R; ++j) {
-            if (ti0 + j < nrem) {
-                if ((vbits >> j) & 1u) st_accumulate<OPS, IS_INT>(st, raw[j], (uint32_t)(ti0 + j));
-                const bool next_exists = ti0 + j + 1 < nrem;
-                const uint64_t xn = xrel(x[j + 1], ti0 + j + 1);
-                if (!next_exists || xn >= erel) {  // the window of row j closes here
-                    if (nclosed == 0) {
-                        head = st;
-                    } else {
-                        const uint64_t fb = st.cnt ? vsm[st.fi] : 0, lb = st.cnt ? vsm[st.li] : 0;
-                        write_window<IS_INT>(P.out, g.W, (int64_t)kcur, st.cnt, st.sum, st.mn, st.mx, fb, lb);
-                    }
-                    ++nclosed;
-                    st = st_identity<OPS>();
-                    if (next_exists) {
-                        if (xn - erel < d) {
-                            ++kcur;
-                            erel += d;
-                        } else {
-                            kcur = div_u64(xn, g.div);
-                            erel = (kcur + 1) * d;
-                        }
-                    }
-                }
-            }
-        }
-
-        // ---- stitch windows spanning threads: segmented inclusive scan of the tails -------------
-        uint32_t f = nclosed > 0;
-        BState sc = st;
-#pragma unroll
-        for (int dd = 1; dd < 32; dd <<= 1) {
-            const BState o = st_shfl_up<OPS>(sc, dd);
-            const uint32_t of = __shfl_up_sync(0xffffffffu, f, dd);
-            if (lane >= dd) {
-                if (!f) sc = st_combine<OPS>(o, sc);
-                f |= of;
-            }
-        }
-        const uint32_t ball = __ballot_sync(0xffffffffu, nclosed > 0);
-        if (lane == 31) {
-            wtot[warp].st = sc;
-            wtot[warp].flag = ball != 0;
-        }
-        BState ex = st_shfl_up<OPS>(sc, 1);
-        if (lane == 0) ex = st_identity<OPS>();
-        __syncthreads();
-        const bool left_open = sh_flags[0] != 0;
-        BState acc = st_identity<OPS>();
-        bool any_prev = false;
-        for (int u = 0; u < warp; ++u) {
-            const BState ws = wtot[u].st;
-            if (wtot[u].flag) {
-                acc = ws;
-                any_prev = true;
-            } else {
-                acc = st_combine<OPS>(acc, ws);
-            }
-        }
-        const bool flag_before = (ball & ((1u << lane) - 1u)) != 0;
-        const BState excl = flag_before ? ex : st_combine<OPS>(acc, ex);
-        const bool any_excl = any_prev || flag_before;
-
-        if (nclosed > 0) {  // this thread closes the window that was open at its left edge
-            const BState h = st_combine<OPS>(excl, head);
-            const uint64_t fb = h.cnt ? vsm[h.fi] : 0, lb = h.cnt ? vsm[h.li] : 0;
-            if (!any_excl && left_open) {
-                BasicCarry c;
-                c.key = (int64_t)kf;
-                c.cnt = (int64_t)h.cnt | CLOSED_BIT;
-                c.sum = h.sum;
-                c.mn = h.mn;
-                c.mx = h.mx;
-                c.first = fb;
-                c.last = lb;
-                c._pad = 0;
-                P.carry_head[tile] = c;
-            } else {
-                write_window<IS_INT>(P.out, g.W, (int64_t)kf, h.cnt, h.sum, h.mn, h.mx, fb, lb);
-            }
-        }
-        if (tid == SEG_NT - 1) {  // tile-level records: the window open at the right edge
-            const bool flag_incl = flag_before || nclosed > 0;
-            const BState incl = flag_incl ? sc : st_combine<OPS>(acc, sc);
-            const bool any_incl = any_prev || flag_incl;
-            const int64_t lim = nrem < G::T ? nrem : (int64_t)G::T;
-            const int64_t lastrow = lim - 1;
-            const bool next_exists = lim < nrem;
-            const uint64_t klast = div_u64(xrel(tsm[lastrow + 2], lastrow), g.div);
-            const bool closes = !next_exists || div_u64(xrel(tsm[lastrow + 3], lastrow + 1), g.div) != klast;
-            BasicCarry c;
-            c.key = (int64_t)klast;
-            c.cnt = (int64_t)incl.cnt;
-            c.sum = incl.sum;
-            c.mn = incl.mn;
-            c.mx = incl.mx;
-            c.first = incl.cnt ? vsm[incl.fi] : 0;
-            c.last = incl.cnt ? vsm[incl.li] : 0;
-            c._pad = 0;
-            BasicCarry none = c;
-            none.key = -1;
-            if (!any_incl && left_open) {  // the whole tile lies inside one window that began earlier
-                P.carry_head[tile] = c;    // not closed
-                P.carry_tail[tile] = none;
-            } else {
-                if (!left_open) P.carry_head[tile] = none;
-                P.carry_tail[tile] = closes ? none : c;
-            }
-        }
+        const bool full_tile = r0 > 0 && g.n - r0 > G::T && r0 >= g.early_rows;
+        if (full_tile)
+            seg_tile<OPS, IS_INT, HAS_NULLS, true>(P, sh_out, tile, sb, wtot, sh_flags, bad);
+        else
+            seg_tile<OPS, IS_INT, HAS_NULLS, false>(P, sh_out, tile, sb, wtot, sh_flags, bad);
         __syncthreads();  // every read of this stage (and of wtot) is done
         if (tid == 0) {
             const int64_t nxt = tile + (int64_t)nstages * gridDim.x;
@@ -364,7 +426,16 @@ template <uint32_t OPS, bool IS_INT, bool HAS_NULLS>
 int launch_inst(const SegLaunch &L, int64_t ntiles, int sm_count, cudaStream_t stream, cudaEvent_t e0,
                 cudaEvent_t e1) {
     auto kern = segreduce_basic_kernel<OPS, IS_INT, HAS_NULLS>;
-    int nstages = 3;
+    // tuning knobs (defaults chosen on B200): pipeline depth and resident CTAs per SM
+    static int nstages = 0, ctas = 0;
+    if (!nstages) {
+        const char *a = getenv("BOWGPU_SEG_STAGES"), *b = getenv("BOWGPU_SEG_CTAS");
+        nstages = a ? atoi(a) : 3;
+        ctas = b ? atoi(b) : 2;
+        if (nstages < 1) nstages = 1;
+        if (nstages > SEG_MAX_STAGES) nstages = SEG_MAX_STAGES;
+        while (nstages > 1 && (SEG_HEADER_BYTES + nstages * SEG_STAGE_BYTES + 1024) * ctas > 232448) --nstages;
+    }
     const int smem = SEG_HEADER_BYTES + nstages * SEG_STAGE_BYTES;
     static bool configured = false;
     if (!configured) {
@@ -372,7 +443,7 @@ int launch_inst(const SegLaunch &L, int64_t ntiles, int sm_count, cudaStream_t s
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
-    int64_t grid = (int64_t)sm_count * 2;
+    int64_t grid = (int64_t)sm_count * ctas;
     if (grid > ntiles) grid = ntiles;
     if (e0) cudaEventRecord(e0, stream);
     kern<<<(unsigned)grid, SEG_NT, smem, stream>>>(L, ntiles, nstages);
