@@ -821,7 +821,7 @@ extern "C" int32_t bowgpu_rolling_aggregate(bowgpu_rolling *r, const bowgpu_agg_
         if (agg_is_basic(specs[j].op) && std::find(basic_cols.begin(), basic_cols.end(), specs[j].col) == basic_cols.end())
             basic_cols.push_back(specs[j].col);
     const size_t wv = align_up((size_t)W * 8, 256), wb = align_up((size_t)((W + 7) / 8) + 16, 256);
-    size_t need = 4096 + basic_cols.size() * wv + seg_carry_bytes(g.n) + 512;
+    size_t need = 4096 + basic_cols.size() * 2 * (wv + 256) + seg_carry_bytes(g.n) + 512;
     if (mem == BOWGPU_MEM_HOST) need += (size_t)nspecs * (wv + wb);
     int32_t rc = arena_reserve(ctx, need);
     if (rc) return rc;
@@ -844,6 +844,7 @@ extern "C" int32_t bowgpu_rolling_aggregate(bowgpu_rolling *r, const bowgpu_agg_
     timing_begin(ctx);
     std::vector<EpilogueSpec> epi(nspecs);
     std::vector<int64_t *> col_cnt(ncols, nullptr);
+    std::vector<double *> col_sum(ncols, nullptr);
     for (int c : basic_cols) {
         const DevCol &dc = f->cols[c];
         SegLaunch L;
@@ -871,8 +872,21 @@ extern "C" int32_t bowgpu_rolling_aggregate(bowgpu_rolling *r, const bowgpu_agg_
         CK(cudaMemsetAsync(cnt, 0, (size_t)W * 8, ctx->stream));
         L.out.cnt = cnt;
         auto prim = [&](int op) -> void * { return primary[op] >= 0 ? dvals[primary[op]] : nullptr; };
-        L.out.sum = (double *)prim(BOWGPU_AGG_SUM);
-        L.out.mean = (double *)prim(BOWGPU_AGG_MEAN);
+        // sums feed both Sum and ArithmeticMean (divided by cnt in the epilogue); they land in the Sum output
+        // unless that one is rescaled in place by a Factor while a mean still needs the raw sums
+        const int ps = primary[BOWGPU_AGG_SUM], pm = primary[BOWGPU_AGG_MEAN];
+        int n_sum = 0, n_mean = 0;
+        for (int j = 0; j < nspecs; ++j)
+            if (specs[j].col == c) n_sum += specs[j].op == BOWGPU_AGG_SUM, n_mean += specs[j].op == BOWGPU_AGG_MEAN;
+        double *sum_dst = nullptr;
+        if (ps >= 0 && (specs[ps].nfactors == 0 || n_mean == 0))
+            sum_dst = (double *)dvals[ps];  // means only read it; a Factor rescales it in place when no mean needs it
+        else if (n_mean == 1 && n_sum == 0)
+            sum_dst = (double *)dvals[pm];  // divided in place
+        else if (n_mean > 0)
+            sum_dst = (double *)arena_take(ctx, wv);
+        L.out.sum = sum_dst;
+        col_sum[c] = sum_dst;
         L.out.mn = (double *)prim(BOWGPU_AGG_MIN);
         L.out.mx = (double *)prim(BOWGPU_AGG_MAX);
         L.out.first = (uint64_t *)prim(BOWGPU_AGG_FIRST);
@@ -888,8 +902,10 @@ extern "C" int32_t bowgpu_rolling_aggregate(bowgpu_rolling *r, const bowgpu_agg_
         for (int j = 0; j < nspecs; ++j) {  // duplicates of an (op, column) pair
             if (specs[j].col != c || !agg_is_basic(specs[j].op)) continue;
             const int p = primary[specs[j].op];
-            if (p == j) continue;
+            if (specs[j].op == BOWGPU_AGG_MEAN) continue;  // every mean divides the shared sums itself
             const void *srcv = specs[j].op == BOWGPU_AGG_COUNT ? (const void *)cnt : dvals[p];
+            if (specs[j].op == BOWGPU_AGG_SUM) srcv = sum_dst;
+            if (srcv == dvals[j]) continue;
             CK(cudaMemcpyAsync(dvals[j], srcv, (size_t)W * 8, cudaMemcpyDeviceToDevice, ctx->stream));
         }
     }
@@ -900,6 +916,7 @@ extern "C" int32_t bowgpu_rolling_aggregate(bowgpu_rolling *r, const bowgpu_agg_
         e.out_is_int = outs[j].dtype == BOWGPU_INT64;
         e.cnt = agg_is_basic(specs[j].op) ? col_cnt[specs[j].col] : nullptr;
         e.ok = nullptr;
+        e.sum_src = specs[j].op == BOWGPU_AGG_MEAN ? col_sum[specs[j].col] : nullptr;
         e.values = dvals[j];
         e.validity = dbits[j];
         e.nfactors = specs[j].nfactors;

@@ -39,6 +39,9 @@ __global__ void epilogue_kernel(const EpiBatch B, const WindowGeom g) {
         } else if (sp.ok ? sp.ok[k] == 0 : c == 0) {
             bits = 0;  // null slot, or Sum of an empty / all-null window = 0.0
             have = true;
+        } else if (sp.op == BOWGPU_AGG_MEAN) {
+            bits = f64_as_bits(__ddiv_rn(sp.sum_src[k], (double)c));  // arithmeticmean.go:28
+            have = true;
         }
         if (valid && sp.nfactors > 0) {
             if (!have) bits = vals[k];

@@ -35,8 +35,7 @@ struct alignas(16) BasicCarry {
 
 struct BasicOut {  // per-window outputs of one input column (any pointer may be null)
     int64_t *cnt;
-    double *sum;
-    double *mean;
+    double *sum;   // also the numerator of ArithmeticMean (the epilogue divides by cnt)
     double *mn;
     double *mx;
     uint64_t *first;
@@ -83,6 +82,7 @@ struct EpilogueSpec {
     int32_t out_is_int;  // output dtype is int64
     const int64_t *cnt;  // valid-row count of the input column per window (null for WindowStart)
     const uint8_t *ok;   // optional per-window validity bytes overriding cnt > 0 (integral family)
+    const double *sum_src;  // ArithmeticMean: per-window sums (may alias values)
     void *values;        // [W]
     uint8_t *validity;   // [ceil(W/8)] bytes
     int32_t nfactors;

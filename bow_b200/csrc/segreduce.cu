@@ -10,7 +10,11 @@
 //     into shared memory by TMA bulk copies (tile_pipe.cuh);
 //   * thread t reduces its R consecutive rows sequentially, left to right, exactly like the
 //     reference closure does inside a window.  A window "closes" after row i when row i+1 lies in a
-//     later window; the thread owning row i detects that from its R+1 timestamps;
+//     later window; the thread owning row i detects that from its R+1 timestamps by comparing
+//     against a running absolute window end (one exact division per thread and tile, none per row);
+//   * the thread keeps the state of the rows before its first closing (head) and after its last
+//     closing (tail); windows lying strictly inside one thread (windows shorter than R rows) are
+//     handled by an out-of-line rolled loop;
 //   * partial states of windows spanning several threads are stitched by a warp-shuffle segmented
 //     scan (flags = "a window closed inside this thread") plus a short cross-warp pass;
 //   * partial states of windows spanning several tiles go to per-tile head / tail carry records
@@ -22,8 +26,10 @@
 //   sum   sum of float64(v) over valid rows                    sum.go:8-25, arithmeticmean.go:8-30
 //   mn/mx min / max over the non-NaN valid values, earliest wins on ties (minmax.go:20, `v < m`)
 //   fi/li index of the first / last valid row                  firstlast.go:8-36
-// Min/Max of the reference start from the FIRST valid value and only replace on a strict compare,
-// so a leading NaN is sticky and later NaNs are ignored: result = isnan(first) ? first : mn.
+// cnt / fi / li never cost anything per row: they are popcount / ffs / fls of the thread's validity
+// bits masked to the segment.  Min/Max of the reference start from the FIRST valid value and only
+// replace on a strict compare, so a leading NaN is sticky and later NaNs are ignored:
+// result = isnan(first) ? first : mn.  ArithmeticMean = sum / float64(cnt) is formed by the epilogue.
 #include "kernels.h"
 #include "tile_pipe.cuh"
 
@@ -38,70 +44,76 @@ namespace {
 constexpr int SEG_NT = 128;
 constexpr int SEG_R = 17;
 constexpr int SEG_MAX_STAGES = 8;
-constexpr int SEG_MIN_CTAS = 2;
+constexpr int SEG_MIN_CTAS = 3;
 using SegG = TileGeom<SEG_NT, SEG_R>;
 constexpr int SEG_NW = SEG_NT / 32;
 constexpr int SEG_STAGE_BYTES = SegG::TIME_BYTES + SegG::VAL_BYTES + SegG::BITS_STRIDE;
 constexpr int SEG_HEADER_BYTES = 1024;
 constexpr int64_t CLOSED_BIT = (int64_t)1 << 62;
+static_assert(SegG::T < 4096, "cnt / fi are packed in 12 bits each");
 
+// state of a run of rows; meta = cnt | fi << 12 (tile-relative first valid row), li = last valid row
 struct BState {
-    uint32_t cnt;
-    uint32_t fi, li;  // tile-relative row index of the first / last valid row
     double sum, mn, mx;
+    uint32_t meta;
+    uint32_t li;
 };
+__device__ __forceinline__ uint32_t st_cnt(const BState &s) { return s.meta & 0xFFFu; }
+__device__ __forceinline__ uint32_t st_fi(const BState &s) { return s.meta >> 12; }
 
-template <uint32_t OPS>
 __device__ __forceinline__ BState st_identity() {
     BState s;
-    s.cnt = 0;
-    s.fi = 0;
-    s.li = 0;
     s.sum = 0.0;
     s.mn = CUDART_INF;
     s.mx = -CUDART_INF;
+    s.meta = 0;
+    s.li = 0;
     return s;
 }
 
 template <uint32_t OPS>
 __device__ __forceinline__ BState st_combine(const BState &L, const BState &R) {
     BState o;
-    o.cnt = L.cnt + R.cnt;
     o.sum = L.sum + R.sum;
     if (OPS & OPS_MINMAX) {
         o.mn = (R.mn < L.mn) ? R.mn : L.mn;
         o.mx = (R.mx > L.mx) ? R.mx : L.mx;
     }
-    if (OPS & (OPS_MINMAX | OPS_FIRSTLAST)) o.fi = L.cnt ? L.fi : R.fi;
-    if (OPS & OPS_FIRSTLAST) o.li = R.cnt ? R.li : L.li;
+    const uint32_t lc = L.meta & 0xFFFu, rc = R.meta & 0xFFFu;
+    o.meta = (lc + rc) | ((lc ? L.meta : R.meta) & 0xFFF000u);
+    if (OPS & OPS_FIRSTLAST) o.li = rc ? R.li : L.li;
     return o;
 }
 
 template <uint32_t OPS>
 __device__ __forceinline__ BState st_shfl_up(const BState &s, int d) {
     BState o;
-    o.cnt = __shfl_up_sync(0xffffffffu, s.cnt, d);
     o.sum = __shfl_up_sync(0xffffffffu, s.sum, d);
     if (OPS & OPS_MINMAX) {
         o.mn = __shfl_up_sync(0xffffffffu, s.mn, d);
         o.mx = __shfl_up_sync(0xffffffffu, s.mx, d);
     }
-    if (OPS & (OPS_MINMAX | OPS_FIRSTLAST)) o.fi = __shfl_up_sync(0xffffffffu, s.fi, d);
+    o.meta = __shfl_up_sync(0xffffffffu, s.meta, d);
     if (OPS & OPS_FIRSTLAST) o.li = __shfl_up_sync(0xffffffffu, s.li, d);
     return o;
 }
 
 template <uint32_t OPS, bool IS_INT>
-__device__ __forceinline__ void st_accumulate(BState &s, uint64_t raw, uint32_t idx) {
+__device__ __forceinline__ void st_accumulate(BState &s, uint64_t raw) {
     const double v = IS_INT ? (double)(int64_t)raw : bits_as_f64(raw);  // GetFloat64, bowgetters.go:218-229
-    if (OPS & (OPS_MINMAX | OPS_FIRSTLAST)) s.fi = s.cnt ? s.fi : idx;
-    if (OPS & OPS_FIRSTLAST) s.li = idx;
-    s.cnt += 1;
     s.sum += v;
     if (OPS & OPS_MINMAX) {
         if (v < s.mn) s.mn = v;
         if (v > s.mx) s.mx = v;
     }
+}
+
+// cnt / fi / li of the rows selected by `mask` (bit j = row ti0 + j of the tile)
+__device__ __forceinline__ void st_set_meta(BState &s, uint32_t mask, int ti0) {
+    const uint32_t cnt = __popc(mask);
+    const uint32_t fi = mask ? (uint32_t)(ti0 + __ffs(mask) - 1) : 0u;
+    s.meta = cnt | (fi << 12);
+    s.li = mask ? (uint32_t)(ti0 + 31 - __clz(mask)) : 0u;
 }
 
 struct WarpTotal {
@@ -110,15 +122,14 @@ struct WarpTotal {
     uint32_t _pad;
 };
 
-// Final per-window write (values only; validity bitmaps and empty-window defaults are produced by
-// the epilogue from cnt).  first/last are raw value bits.
+// Final per-window write (values only; validity bitmaps, the mean division and empty-window defaults
+// are produced by the epilogue from cnt).  first/last are raw value bits.
 template <bool IS_INT>
 __device__ __forceinline__ void write_window(const BasicOut &o, int64_t W, int64_t k, int64_t cnt, double sum,
                                              double mn, double mx, uint64_t first, uint64_t last) {
     if ((uint64_t)k >= (uint64_t)W || cnt == 0) return;
-    if (o.cnt) o.cnt[k] = cnt;
+    o.cnt[k] = cnt;
     if (o.sum) o.sum[k] = sum;
-    if (o.mean) o.mean[k] = sum / (double)cnt;  // arithmeticmean.go:28
     if (o.mn || o.mx) {
         const double f = bits_as_f64(first);
         const bool sticky = !IS_INT && (f != f);  // first valid value is NaN (minmax.go:14-24)
@@ -129,7 +140,7 @@ __device__ __forceinline__ void write_window(const BasicOut &o, int64_t W, int64
     if (o.last) o.last[k] = last;
 }
 
-// exact division on the rare path (a gap of two or more windows between consecutive rows)
+// exact division on the rare paths
 __device__ __noinline__ uint64_t div_slow(uint64_t x, uint64_t d, double inv_rd) {
     DivU64 dv{d, inv_rd};
     return div_u64(x, dv);
@@ -140,19 +151,24 @@ __device__ __noinline__ uint64_t div_slow(uint64_t x, uint64_t d, double inv_rd)
 // rolled loop and written out directly.  Kept out of line so the unrolled fast path stays small.
 template <uint32_t OPS, bool IS_INT>
 __device__ __noinline__ void middle_windows(const BasicOut *outp, int64_t W, uint64_t d, double inv_rd, int64_t s0,
-                                            const int64_t *trow, const uint64_t *vrow, uint32_t vbits, int ti0,
-                                            int jfirst, int jlast, uint64_t kstart) {
+                                            const int64_t *trow, const uint64_t *vrow, uint32_t vbits, int jfirst,
+                                            int jlast) {
     const BasicOut o = *outp;
-    BState st = st_identity<OPS>();
-    uint64_t kcur = kstart;
+    BState st = st_identity();
+    uint32_t seg = 0;  // valid rows of the current window
+    uint64_t kcur = div_slow((uint64_t)trow[jfirst + 1] - (uint64_t)s0, d, inv_rd);
     uint64_t erel = (kcur + 1) * d;
     for (int j = jfirst + 1; j <= jlast; ++j) {
-        if ((vbits >> j) & 1u) st_accumulate<OPS, IS_INT>(st, vrow[j], (uint32_t)(ti0 + j));
+        if ((vbits >> j) & 1u) {
+            st_accumulate<OPS, IS_INT>(st, vrow[j]);
+            seg |= 1u << j;
+        }
         const uint64_t xn = (uint64_t)trow[j + 1] - (uint64_t)s0;
         if (j == jlast || xn >= erel) {
-            const uint64_t fb = st.cnt ? vrow[st.fi - ti0] : 0, lb = st.cnt ? vrow[st.li - ti0] : 0;
-            write_window<IS_INT>(o, W, (int64_t)kcur, st.cnt, st.sum, st.mn, st.mx, fb, lb);
-            st = st_identity<OPS>();
+            const uint64_t fb = seg ? vrow[__ffs(seg) - 1] : 0, lb = seg ? vrow[31 - __clz(seg)] : 0;
+            write_window<IS_INT>(o, W, (int64_t)kcur, __popc(seg), st.sum, st.mn, st.mx, fb, lb);
+            st = st_identity();
+            seg = 0;
             if (xn - erel < d) {
                 ++kcur;
                 erel += d;
@@ -179,26 +195,22 @@ __device__ __forceinline__ void seg_tile(const SegLaunch &P, const BasicOut *sh_
     const uint32_t *bsm = reinterpret_cast<const uint32_t *>(sb + G::TIME_BYTES + G::VAL_BYTES);
     const int64_t r0 = tile * G::T;
     const int64_t nrem = g.n - r0;  // rows from the tile start to the end of the column (> 0)
-    const int nrem_i = nrem > G::T + 2 ? G::T + 2 : (int)nrem;
+    const int nrem_i = FULL ? G::T + 2 : (nrem > G::T + 2 ? G::T + 2 : (int)nrem);
     const int ti0 = tid * R;
+    const int nmine = FULL ? R : (nrem_i - ti0 < 0 ? 0 : (nrem_i - ti0 > R ? R : nrem_i - ti0));  // rows I own
     const bool early_tile = !FULL && r0 < g.early_rows;
-
-    // window-relative time of a row (rows before s0 collapse onto window 0, see WindowGeom)
-    auto xrel = [&](int64_t x, int ti) -> uint64_t {
-        if (!FULL && early_tile && r0 + ti < g.early_rows) return 0;
-        return (uint64_t)x - (uint64_t)g.s0;
-    };
-    auto exists = [&](int ti) -> bool { return FULL || ti < nrem_i; };
 
     uint32_t vbits = (1u << R) - 1u;
     if (HAS_NULLS) {
         const uint32_t lo = bsm[ti0 >> 5], hi = bsm[(ti0 >> 5) + 1];
         vbits &= __funnelshift_r(lo, hi, ti0 & 31);
     }
-    if (!FULL && early_tile && !g.early_keep) {
-#pragma unroll
-        for (int j = 0; j < R; ++j)
-            if (r0 + ti0 + j < g.early_rows) vbits &= ~(1u << j);
+    if (!FULL) {
+        vbits &= (1u << nmine) - 1u;
+        if (early_tile && !g.early_keep) {  // rows before s0 are dropped (see WindowGeom)
+            const int64_t e = g.early_rows - (r0 + ti0);
+            if (e > 0) vbits &= e >= R ? 0u : ~((1u << (int)e) - 1u);
+        }
     }
 
     int64_t x[R + 1];
@@ -209,59 +221,63 @@ __device__ __forceinline__ void seg_tile(const SegLaunch &P, const BasicOut *sh_
     for (int j = 0; j < R; ++j) raw[j] = vsm[ti0 + j];
 
     // precondition check: time sorted ascending (every adjacent pair is checked exactly once)
-    if (FULL || (exists(ti0) && r0 + ti0 > 0)) bad |= x[0] < tsm[ti0 + 1];
+    if (FULL || (nmine > 0 && r0 + ti0 > 0)) bad |= x[0] < tsm[ti0 + 1];
 #pragma unroll
     for (int j = 1; j < R; ++j)
-        if (exists(ti0 + j)) bad |= x[j] < x[j - 1];
+        if (FULL || j < nmine) bad |= x[j] < x[j - 1];
 
-    BState st = st_identity<OPS>();
-    BState head = st_identity<OPS>();
-    int nclosed = 0, jfirst = 0, jlast = 0;
-    uint64_t kcur = 0, kf = 0, kmid = 0, erel = 0;
-    if (exists(ti0)) {
-        kcur = div_u64(xrel(x[0], ti0), g.div);
-        kf = kcur;
-        erel = (kcur + 1) * d;
+    // window of my first row (rows before s0 collapse onto window 0) and its absolute end
+    uint64_t kf = 0;
+    if (nmine > 0) {
+        const bool early0 = early_tile && r0 + ti0 < g.early_rows;
+        kf = early0 ? 0 : div_u64((uint64_t)x[0] - (uint64_t)g.s0, g.div);
     }
-    if (tid == 0) {
+    int64_t eabs = (int64_t)((uint64_t)g.s0 + (kf + 1) * d);
+    if (tid == 0) {  // does the window of my first row continue from the previous tile?
         int lo_open = 0;
-        if (r0 > 0) lo_open = div_u64(xrel(tsm[1], -1), g.div) == kcur;
+        if (r0 > 0) {
+            const bool earlyp = early_tile && r0 - 1 < g.early_rows;
+            lo_open = earlyp ? kf == 0 : (uint64_t)tsm[1] - (uint64_t)g.s0 >= kf * d;
+        }
         sh_flags[0] = lo_open;
     }
+
+    BState st = st_identity();
+    BState head = st_identity();
+    uint32_t cmask = 0;  // bit j: the window of row j closes after row j
 #pragma unroll
     for (int j = 0; j < R; ++j) {
-        if (exists(ti0 + j)) {
-            if ((vbits >> j) & 1u) st_accumulate<OPS, IS_INT>(st, raw[j], (uint32_t)(ti0 + j));
-            const bool next_exists = exists(ti0 + j + 1);
-            const uint64_t xn = xrel(x[j + 1], ti0 + j + 1);
-            if (!next_exists || xn >= erel) {  // the window of row j closes here
-                if (nclosed == 0) {
-                    head = st;
-                    jfirst = j;
-                }
-                ++nclosed;
-                jlast = j;
-                st = st_identity<OPS>();
+        if (FULL || j < nmine) {
+            if ((vbits >> j) & 1u) st_accumulate<OPS, IS_INT>(st, raw[j]);
+            const bool next_exists = FULL || ti0 + j + 1 < nrem_i;
+            if (!next_exists || x[j + 1] >= eabs) {
+                if (cmask == 0) head = st;
+                cmask |= 1u << j;
+                st = st_identity();
                 if (next_exists) {
-                    if (xn - erel < d) {
-                        ++kcur;
-                        erel += d;
+                    if ((uint64_t)x[j + 1] - (uint64_t)eabs < d) {
+                        eabs = (int64_t)((uint64_t)eabs + d);
                     } else {
-                        kcur = div_slow(xn, d, g.div.inv_rd);
-                        erel = (kcur + 1) * d;
+                        const uint64_t k = div_slow((uint64_t)x[j + 1] - (uint64_t)g.s0, d, g.div.inv_rd);
+                        eabs = (int64_t)((uint64_t)g.s0 + (k + 1) * d);
                     }
-                    if (nclosed == 1) kmid = kcur;
                 }
             }
         }
     }
+    const int jfirst = __ffs(cmask) - 1, jlast = 31 - __clz(cmask);  // valid when cmask != 0
+    if (cmask) {
+        st_set_meta(head, vbits & ((2u << jfirst) - 1u), ti0);
+        st_set_meta(st, vbits & ~((2u << jlast) - 1u), ti0);
+    } else {
+        st_set_meta(st, vbits, ti0);
+    }
     // windows lying strictly inside this thread's rows (short windows only)
-    if (nclosed >= 2)
-        middle_windows<OPS, IS_INT>(sh_out, g.W, d, g.div.inv_rd, g.s0, tsm + ti0 + 2, vsm + ti0, vbits, ti0, jfirst,
-                                    jlast, kmid);
+    if (jlast > jfirst)
+        middle_windows<OPS, IS_INT>(sh_out, g.W, d, g.div.inv_rd, g.s0, tsm + ti0 + 2, vsm + ti0, vbits, jfirst, jlast);
 
     // ---- stitch windows spanning threads: segmented inclusive scan of the tails -------------
-    uint32_t f = nclosed > 0;
+    uint32_t f = cmask != 0;
     BState sc = st;
 #pragma unroll
     for (int dd = 1; dd < 32; dd <<= 1) {
@@ -272,16 +288,16 @@ __device__ __forceinline__ void seg_tile(const SegLaunch &P, const BasicOut *sh_
             f |= of;
         }
     }
-    const uint32_t ball = __ballot_sync(0xffffffffu, nclosed > 0);
+    const uint32_t ball = __ballot_sync(0xffffffffu, cmask != 0);
     if (lane == 31) {
         wtot[warp].st = sc;
         wtot[warp].flag = ball != 0;
     }
     BState ex = st_shfl_up<OPS>(sc, 1);
-    if (lane == 0) ex = st_identity<OPS>();
+    if (lane == 0) ex = st_identity();
     __syncthreads();
     const bool left_open = sh_flags[0] != 0;
-    BState acc = st_identity<OPS>();
+    BState acc = st_identity();
     bool any_prev = false;
     for (int u = 0; u < warp; ++u) {
         const BState ws = wtot[u].st;
@@ -296,13 +312,14 @@ __device__ __forceinline__ void seg_tile(const SegLaunch &P, const BasicOut *sh_
     const BState excl = flag_before ? ex : st_combine<OPS>(acc, ex);
     const bool any_excl = any_prev || flag_before;
 
-    if (nclosed > 0) {  // this thread closes the window that was open at its left edge
+    if (cmask) {  // this thread closes the window that was open at its left edge
         const BState h = st_combine<OPS>(excl, head);
-        const uint64_t fb = h.cnt ? vsm[h.fi] : 0, lb = h.cnt ? vsm[h.li] : 0;
+        const uint32_t hc = st_cnt(h);
+        const uint64_t fb = hc ? vsm[st_fi(h)] : 0, lb = hc ? vsm[h.li] : 0;
         if (!any_excl && left_open) {
             BasicCarry c;
             c.key = (int64_t)kf;
-            c.cnt = (int64_t)h.cnt | CLOSED_BIT;
+            c.cnt = (int64_t)hc | CLOSED_BIT;
             c.sum = h.sum;
             c.mn = h.mn;
             c.mx = h.mx;
@@ -311,30 +328,29 @@ __device__ __forceinline__ void seg_tile(const SegLaunch &P, const BasicOut *sh_
             c._pad = 0;
             P.carry_head[tile] = c;
         } else {
-            write_window<IS_INT>(P.out, g.W, (int64_t)kf, h.cnt, h.sum, h.mn, h.mx, fb, lb);
+            write_window<IS_INT>(P.out, g.W, (int64_t)kf, hc, h.sum, h.mn, h.mx, fb, lb);
         }
     }
     if (tid == SEG_NT - 1) {  // tile-level records: the window open at the right edge
-        const bool flag_incl = flag_before || nclosed > 0;
+        const bool flag_incl = flag_before || cmask != 0;
         const BState incl = flag_incl ? sc : st_combine<OPS>(acc, sc);
         const bool any_incl = any_prev || flag_incl;
-        const int lim = nrem < G::T ? (int)nrem : G::T;
-        const int lastrow = lim - 1;
-        const bool next_exists = lim < nrem;
-        const uint64_t klast = div_u64(xrel(tsm[lastrow + 2], lastrow), g.div);
-        const bool closes = !next_exists || div_u64(xrel(tsm[lastrow + 3], lastrow + 1), g.div) != klast;
+        // the last row of the tile closes its window: end of data, or my last row closed
+        const bool closes = nrem <= G::T || ((cmask >> (R - 1)) & 1u);
+        const uint32_t ic = st_cnt(incl);
         BasicCarry c;
-        c.key = (int64_t)klast;
-        c.cnt = (int64_t)incl.cnt;
+        c.key = 0;  // tail records take their window index from the next tile's head record
+        c.cnt = (int64_t)ic;
         c.sum = incl.sum;
         c.mn = incl.mn;
         c.mx = incl.mx;
-        c.first = incl.cnt ? vsm[incl.fi] : 0;
-        c.last = incl.cnt ? vsm[incl.li] : 0;
+        c.first = ic ? vsm[st_fi(incl)] : 0;
+        c.last = ic ? vsm[incl.li] : 0;
         c._pad = 0;
         BasicCarry none = c;
         none.key = -1;
         if (!any_incl && left_open) {  // the whole tile lies inside one window that began earlier
+            c.key = (int64_t)kf;       // (every thread of the tile has the same kf)
             P.carry_head[tile] = c;    // not closed
             P.carry_tail[tile] = none;
         } else {
@@ -404,9 +420,11 @@ __global__ void seg_fixup_kernel(const SegLaunch P, const int64_t ntiles) {
     if (j >= ntiles) return;
     BasicCarry a = P.carry_tail[j];
     if (a.key < 0) return;
+    int64_t key = -1;
     for (int64_t i = j + 1; i < ntiles; ++i) {
         const BasicCarry h = P.carry_head[i];
-        if (h.key != a.key) break;
+        if (h.key < 0 || (key >= 0 && h.key != key)) break;
+        key = h.key;
         const int64_t hc = h.cnt & ~CLOSED_BIT;
         a.sum = a.sum + h.sum;
         a.mn = (h.mn < a.mn) ? h.mn : a.mn;
@@ -416,10 +434,11 @@ __global__ void seg_fixup_kernel(const SegLaunch P, const int64_t ntiles) {
         a.cnt += hc;
         if (h.cnt & CLOSED_BIT) break;
     }
+    if (key < 0) return;  // cannot happen: an open tail is always continued by the next tile's head
     if (P.is_int)
-        write_window<true>(P.out, P.g.W, a.key, a.cnt, a.sum, a.mn, a.mx, a.first, a.last);
+        write_window<true>(P.out, P.g.W, key, a.cnt, a.sum, a.mn, a.mx, a.first, a.last);
     else
-        write_window<false>(P.out, P.g.W, a.key, a.cnt, a.sum, a.mn, a.mx, a.first, a.last);
+        write_window<false>(P.out, P.g.W, key, a.cnt, a.sum, a.mn, a.mx, a.first, a.last);
 }
 
 template <uint32_t OPS, bool IS_INT, bool HAS_NULLS>
@@ -430,8 +449,8 @@ int launch_inst(const SegLaunch &L, int64_t ntiles, int sm_count, cudaStream_t s
     static int nstages = 0, ctas = 0;
     if (!nstages) {
         const char *a = getenv("BOWGPU_SEG_STAGES"), *b = getenv("BOWGPU_SEG_CTAS");
-        nstages = a ? atoi(a) : 3;
-        ctas = b ? atoi(b) : 2;
+        nstages = a ? atoi(a) : 2;
+        ctas = b ? atoi(b) : 3;
         if (nstages < 1) nstages = 1;
         if (nstages > SEG_MAX_STAGES) nstages = SEG_MAX_STAGES;
         while (nstages > 1 && (SEG_HEADER_BYTES + nstages * SEG_STAGE_BYTES + 1024) * ctas > 232448) --nstages;
