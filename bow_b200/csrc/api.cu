@@ -807,7 +807,6 @@ extern "C" int32_t bowgpu_rolling_aggregate(bowgpu_rolling *r, const bowgpu_agg_
         if (specs[j].nfactors < 0 || specs[j].nfactors > 4) return fail(ctx, BOWGPU_EINVAL, "aggregation %d: at most 4 factors", j);
         if (bowgpu_agg_needs_inclusive(specs[j].op)) inclusive_eff = true;
         if (specs[j].col == r->time_col) keeps_interval = true;
-        if (agg_is_integral(specs[j].op)) return fail(ctx, BOWGPU_EUNSUPPORTED, "aggregation %d: integral family not built yet", j);
     }
     if (!keeps_interval) return fail(ctx, BOWGPU_ENOINTERVALCOL, "must keep interval column");  // aggregation.go:163-166
     for (int j = 0; j < nspecs; ++j) outs[j].dtype = bowgpu_agg_return_type(specs[j].op, f->cols[specs[j].col].dtype);
@@ -815,13 +814,23 @@ extern "C" int32_t bowgpu_rolling_aggregate(bowgpu_rolling *r, const bowgpu_agg_
     const int64_t W = g.W;
     if (W == 0) return BOWGPU_OK;
 
-    // ---- plan: one streaming launch per distinct input column of the basic family --------------------
-    std::vector<int> basic_cols;
-    for (int j = 0; j < nspecs; ++j)
-        if (agg_is_basic(specs[j].op) && std::find(basic_cols.begin(), basic_cols.end(), specs[j].col) == basic_cols.end())
-            basic_cols.push_back(specs[j].col);
+    // ---- plan: per distinct input column one streaming launch per kernel family ------------------------
+    std::vector<int> cols_used;
+    int n_basic_cols = 0, n_int_cols = 0;
+    for (int j = 0; j < nspecs; ++j) {
+        if (specs[j].op == BOWGPU_AGG_WINDOW_START) continue;
+        if (std::find(cols_used.begin(), cols_used.end(), specs[j].col) == cols_used.end()) cols_used.push_back(specs[j].col);
+    }
+    for (int c : cols_used) {
+        bool b = false, i = false;
+        for (int j = 0; j < nspecs; ++j)
+            if (specs[j].col == c) b |= agg_is_basic(specs[j].op), i |= agg_is_integral(specs[j].op);
+        n_basic_cols += b;
+        n_int_cols += i;
+    }
     const size_t wv = align_up((size_t)W * 8, 256), wb = align_up((size_t)((W + 7) / 8) + 16, 256);
-    size_t need = 4096 + basic_cols.size() * 2 * (wv + 256) + seg_carry_bytes(g.n) + 512;
+    const size_t carry_bytes = std::max(seg_carry_bytes(g.n), integral_carry_bytes(g.n));
+    size_t need = 8192 + (size_t)n_basic_cols * 2 * (wv + 256) + (size_t)n_int_cols * 4 * (wv + 256) + carry_bytes + 512;
     if (mem == BOWGPU_MEM_HOST) need += (size_t)nspecs * (wv + wb);
     int32_t rc = arena_reserve(ctx, need);
     if (rc) return rc;
@@ -838,75 +847,127 @@ extern "C" int32_t bowgpu_rolling_aggregate(bowgpu_rolling *r, const bowgpu_agg_
         }
         if (!dvals[j] || !dbits[j]) return fail(ctx, BOWGPU_EINVAL, "aggregation %d: null output buffer", j);
     }
-    BasicCarry *carry = (BasicCarry *)arena_take(ctx, seg_carry_bytes(g.n));
-    const int64_t ntiles = seg_num_tiles(g.n);
+    uint8_t *carry = (uint8_t *)arena_take(ctx, carry_bytes);
 
     timing_begin(ctx);
     std::vector<EpilogueSpec> epi(nspecs);
-    std::vector<int64_t *> col_cnt(ncols, nullptr);
-    std::vector<double *> col_sum(ncols, nullptr);
-    for (int c : basic_cols) {
+    // per spec: the per-window count that decides validity, and the base quantity a derived op divides
+    std::vector<const int64_t *> spec_cnt(nspecs, nullptr);
+    std::vector<const double *> spec_src(nspecs, nullptr);
+    for (int c : cols_used) {
         const DevCol &dc = f->cols[c];
-        SegLaunch L;
-        memset(&L, 0, sizeof L);
-        L.time = (const int64_t *)f->cols[r->time_col].values;
-        L.values = dc.values;
-        L.validity = dc.validity;
-        L.is_int = dc.dtype == BOWGPU_INT64;
-        L.g = g;
-        L.carry_head = carry;
-        L.carry_tail = carry + ntiles;
-        L.status = ctx->d_status;
         // first spec of each op on this column receives the kernel output; duplicates are copied afterwards
-        int primary[BOWGPU_AGG__COUNT];
-        for (int &p : primary) p = -1;
+        int primary[BOWGPU_AGG__COUNT], count[BOWGPU_AGG__COUNT];
+        for (int o = 0; o < BOWGPU_AGG__COUNT; ++o) primary[o] = -1, count[o] = 0;
         for (int j = 0; j < nspecs; ++j)
-            if (specs[j].col == c && agg_is_basic(specs[j].op) && primary[specs[j].op] < 0) primary[specs[j].op] = j;
-        // the valid-row count drives every validity bitmap: Count output if it can be used as is, else scratch
-        int64_t *cnt = nullptr;
-        if (primary[BOWGPU_AGG_COUNT] >= 0 && specs[primary[BOWGPU_AGG_COUNT]].nfactors == 0)
-            cnt = (int64_t *)dvals[primary[BOWGPU_AGG_COUNT]];
-        else
-            cnt = (int64_t *)arena_take(ctx, wv);
-        col_cnt[c] = cnt;
-        CK(cudaMemsetAsync(cnt, 0, (size_t)W * 8, ctx->stream));
-        L.out.cnt = cnt;
+            if (specs[j].col == c) {
+                if (primary[specs[j].op] < 0) primary[specs[j].op] = j;
+                ++count[specs[j].op];
+            }
         auto prim = [&](int op) -> void * { return primary[op] >= 0 ? dvals[primary[op]] : nullptr; };
-        // sums feed both Sum and ArithmeticMean (divided by cnt in the epilogue); they land in the Sum output
-        // unless that one is rescaled in place by a Factor while a mean still needs the raw sums
-        const int ps = primary[BOWGPU_AGG_SUM], pm = primary[BOWGPU_AGG_MEAN];
-        int n_sum = 0, n_mean = 0;
-        for (int j = 0; j < nspecs; ++j)
-            if (specs[j].col == c) n_sum += specs[j].op == BOWGPU_AGG_SUM, n_mean += specs[j].op == BOWGPU_AGG_MEAN;
-        double *sum_dst = nullptr;
-        if (ps >= 0 && (specs[ps].nfactors == 0 || n_mean == 0))
-            sum_dst = (double *)dvals[ps];  // means only read it; a Factor rescales it in place when no mean needs it
-        else if (n_mean == 1 && n_sum == 0)
-            sum_dst = (double *)dvals[pm];  // divided in place
-        else if (n_mean > 0)
-            sum_dst = (double *)arena_take(ctx, wv);
-        L.out.sum = sum_dst;
-        col_sum[c] = sum_dst;
-        L.out.mn = (double *)prim(BOWGPU_AGG_MIN);
-        L.out.mx = (double *)prim(BOWGPU_AGG_MAX);
-        L.out.first = (uint64_t *)prim(BOWGPU_AGG_FIRST);
-        L.out.last = (uint64_t *)prim(BOWGPU_AGG_LAST);
-        L.ops = OPS_SUMCNT;
-        if (L.out.mn || L.out.mx) L.ops |= OPS_MINMAX;
-        if (L.out.first || L.out.last) L.ops |= OPS_FIRSTLAST;
-        cudaEvent_t e0, e1;
-        timing_main_pair(ctx, &e0, &e1);
-        CK(launch_segreduce_basic(L, ctx->sm_count, ctx->stream, e0, e1));
-        count_launch(ctx, 1, true);
-        count_launch(ctx, 1);
-        for (int j = 0; j < nspecs; ++j) {  // duplicates of an (op, column) pair
-            if (specs[j].col != c || !agg_is_basic(specs[j].op)) continue;
-            const int p = primary[specs[j].op];
-            if (specs[j].op == BOWGPU_AGG_MEAN) continue;  // every mean divides the shared sums itself
-            const void *srcv = specs[j].op == BOWGPU_AGG_COUNT ? (const void *)cnt : dvals[p];
-            if (specs[j].op == BOWGPU_AGG_SUM) srcv = sum_dst;
-            if (srcv == dvals[j]) continue;
-            CK(cudaMemcpyAsync(dvals[j], srcv, (size_t)W * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        // A base quantity (sum / integral) feeds its own op and a derived op that divides it in the epilogue
+        // (mean, weighted averages).  It lands in the base op's output unless a Factor rescales that one in
+        // place while a derived op still needs the raw values.
+        auto pick_dst = [&](int base_op, int derived_op) -> double * {
+            const int pb = primary[base_op], pd = primary[derived_op];
+            if (pb >= 0 && (specs[pb].nfactors == 0 || count[derived_op] == 0)) return (double *)dvals[pb];
+            if (count[derived_op] == 1 && count[base_op] == 0) return (double *)dvals[pd];  // divided in place
+            if (count[derived_op] > 0) return (double *)arena_take(ctx, wv);
+            return nullptr;
+        };
+        auto copy_dups = [&](int op, const void *src) -> int32_t {  // duplicates of an (op, column) pair
+            for (int j = 0; j < nspecs; ++j) {
+                if (specs[j].col != c || specs[j].op != op || !src || src == dvals[j]) continue;
+                CK(cudaMemcpyAsync(dvals[j], src, (size_t)W * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+            return BOWGPU_OK;
+        };
+        bool any_basic = false, any_int = false;
+        for (int o = 0; o < BOWGPU_AGG__COUNT; ++o)
+            if (count[o]) any_basic |= agg_is_basic(o), any_int |= agg_is_integral(o);
+        if (any_basic) {
+            SegLaunch L;
+            memset(&L, 0, sizeof L);
+            L.time = (const int64_t *)f->cols[r->time_col].values;
+            L.values = dc.values;
+            L.validity = dc.validity;
+            L.is_int = dc.dtype == BOWGPU_INT64;
+            L.g = g;
+            L.carry_head = (BasicCarry *)carry;
+            L.carry_tail = (BasicCarry *)carry + seg_num_tiles(g.n);
+            L.status = ctx->d_status;
+            // the valid-row count drives every validity bitmap: Count output if it can be used as is, else scratch
+            int64_t *cnt = nullptr;
+            if (primary[BOWGPU_AGG_COUNT] >= 0 && specs[primary[BOWGPU_AGG_COUNT]].nfactors == 0)
+                cnt = (int64_t *)dvals[primary[BOWGPU_AGG_COUNT]];
+            else
+                cnt = (int64_t *)arena_take(ctx, wv);
+            CK(cudaMemsetAsync(cnt, 0, (size_t)W * 8, ctx->stream));
+            L.out.cnt = cnt;
+            double *sum_dst = pick_dst(BOWGPU_AGG_SUM, BOWGPU_AGG_MEAN);
+            L.out.sum = sum_dst;
+            L.out.mn = (double *)prim(BOWGPU_AGG_MIN);
+            L.out.mx = (double *)prim(BOWGPU_AGG_MAX);
+            L.out.first = (uint64_t *)prim(BOWGPU_AGG_FIRST);
+            L.out.last = (uint64_t *)prim(BOWGPU_AGG_LAST);
+            L.ops = OPS_SUMCNT;
+            if (L.out.mn || L.out.mx) L.ops |= OPS_MINMAX;
+            if (L.out.first || L.out.last) L.ops |= OPS_FIRSTLAST;
+            cudaEvent_t e0, e1;
+            timing_main_pair(ctx, &e0, &e1);
+            CK(launch_segreduce_basic(L, ctx->sm_count, ctx->stream, e0, e1));
+            count_launch(ctx, 1, true);
+            count_launch(ctx, 1);
+            if ((rc = copy_dups(BOWGPU_AGG_COUNT, cnt))) return rc;
+            if ((rc = copy_dups(BOWGPU_AGG_SUM, sum_dst))) return rc;
+            for (int op : {BOWGPU_AGG_MIN, BOWGPU_AGG_MAX, BOWGPU_AGG_FIRST, BOWGPU_AGG_LAST})
+                if ((rc = copy_dups(op, prim(op)))) return rc;
+            for (int j = 0; j < nspecs; ++j)
+                if (specs[j].col == c && agg_is_basic(specs[j].op)) {
+                    spec_cnt[j] = cnt;
+                    if (specs[j].op == BOWGPU_AGG_MEAN) spec_src[j] = sum_dst;  // every mean divides the shared sums
+                }
+        }
+        if (any_int) {
+            IntLaunch L;
+            memset(&L, 0, sizeof L);
+            L.time = (const int64_t *)f->cols[r->time_col].values;
+            L.values = dc.values;
+            L.validity = dc.validity;
+            L.is_int = dc.dtype == BOWGPU_INT64;
+            L.g = g;
+            L.carry_head = carry;
+            L.carry_tail = carry + integral_carry_bytes(g.n) / 2;
+            L.status = ctx->d_status;
+            const bool want_step = count[BOWGPU_AGG_INTEGRAL_STEP] || count[BOWGPU_AGG_WAVG_STEP];
+            const bool want_trap = count[BOWGPU_AGG_INTEGRAL_TRAPEZOID] || count[BOWGPU_AGG_WAVG_LINEAR];
+            if (want_step) {
+                L.out.n_step = (int64_t *)arena_take(ctx, wv);
+                CK(cudaMemsetAsync(L.out.n_step, 0, (size_t)W * 8, ctx->stream));
+                L.out.step = pick_dst(BOWGPU_AGG_INTEGRAL_STEP, BOWGPU_AGG_WAVG_STEP);
+            }
+            if (want_trap) {
+                L.out.n_trap = (int64_t *)arena_take(ctx, wv);
+                CK(cudaMemsetAsync(L.out.n_trap, 0, (size_t)W * 8, ctx->stream));
+                L.out.trap = pick_dst(BOWGPU_AGG_INTEGRAL_TRAPEZOID, BOWGPU_AGG_WAVG_LINEAR);
+            }
+            cudaEvent_t e0, e1;
+            timing_main_pair(ctx, &e0, &e1);
+            CK(launch_segreduce_integral(L, ctx->sm_count, ctx->stream, e0, e1));
+            count_launch(ctx, 1, true);
+            count_launch(ctx, 1);
+            if ((rc = copy_dups(BOWGPU_AGG_INTEGRAL_STEP, L.out.step))) return rc;
+            if ((rc = copy_dups(BOWGPU_AGG_INTEGRAL_TRAPEZOID, L.out.trap))) return rc;
+            for (int j = 0; j < nspecs; ++j) {
+                if (specs[j].col != c) continue;
+                switch (specs[j].op) {
+                case BOWGPU_AGG_INTEGRAL_STEP: spec_cnt[j] = L.out.n_step; break;
+                case BOWGPU_AGG_INTEGRAL_TRAPEZOID: spec_cnt[j] = L.out.n_trap; break;
+                case BOWGPU_AGG_WAVG_STEP: spec_cnt[j] = L.out.n_step, spec_src[j] = L.out.step; break;
+                case BOWGPU_AGG_WAVG_LINEAR: spec_cnt[j] = L.out.n_trap, spec_src[j] = L.out.trap; break;
+                default: break;
+                }
+            }
         }
     }
     for (int j = 0; j < nspecs; ++j) {
@@ -914,9 +975,9 @@ extern "C" int32_t bowgpu_rolling_aggregate(bowgpu_rolling *r, const bowgpu_agg_
         memset(&e, 0, sizeof e);
         e.op = specs[j].op;
         e.out_is_int = outs[j].dtype == BOWGPU_INT64;
-        e.cnt = agg_is_basic(specs[j].op) ? col_cnt[specs[j].col] : nullptr;
+        e.cnt = spec_cnt[j];
         e.ok = nullptr;
-        e.sum_src = specs[j].op == BOWGPU_AGG_MEAN ? col_sum[specs[j].col] : nullptr;
+        e.sum_src = spec_src[j];
         e.values = dvals[j];
         e.validity = dbits[j];
         e.nfactors = specs[j].nfactors;

@@ -42,6 +42,10 @@ __global__ void epilogue_kernel(const EpiBatch B, const WindowGeom g) {
         } else if (sp.op == BOWGPU_AGG_MEAN) {
             bits = f64_as_bits(__ddiv_rn(sp.sum_src[k], (double)c));  // arithmeticmean.go:28
             have = true;
+        } else if (sp.op == BOWGPU_AGG_WAVG_STEP || sp.op == BOWGPU_AGG_WAVG_LINEAR) {
+            // integral / float64(w.LastValue - w.FirstValue), weightedmean.go:17,31
+            bits = f64_as_bits(__ddiv_rn(sp.sum_src[k], (double)(int64_t)g.div.d));
+            have = true;
         }
         if (valid && sp.nfactors > 0) {
             if (!have) bits = vals[k];

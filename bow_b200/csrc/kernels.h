@@ -64,6 +64,28 @@ size_t seg_carry_bytes(int64_t n);  // bytes for carry_head + carry_tail
 int launch_segreduce_basic(const SegLaunch &L, int sm_count, cudaStream_t stream, cudaEvent_t ev_main0,
                            cudaEvent_t ev_main1);
 
+// ---- integral family (IntegralStep / IntegralTrapezoid / WeightedAverage*) ------------------------
+struct IntegralOut {
+    int64_t *n_step;  // [W] zeroed by the caller: number of valid points (IntegralStep is valid iff > 0)
+    int64_t *n_trap;  // [W] zeroed by the caller: 1 iff the trapezoid integral is valid (>= 2 points)
+    double *step;     // [W] or null
+    double *trap;     // [W] or null
+};
+struct IntLaunch {
+    const int64_t *time;
+    const uint64_t *values;
+    const uint8_t *validity;
+    int32_t is_int;
+    WindowGeom g;
+    IntegralOut out;
+    void *carry_head;  // [ntiles] of integral_carry_bytes(n) / 2
+    void *carry_tail;
+    int32_t *status;
+};
+size_t integral_carry_bytes(int64_t n);
+int launch_segreduce_integral(const IntLaunch &L, int sm_count, cudaStream_t stream, cudaEvent_t ev_main0,
+                              cudaEvent_t ev_main1);
+
 // ---- bounds ------------------------------------------------------------------------------------
 struct BoundsLaunch {
     const int64_t *time;
@@ -82,7 +104,7 @@ struct EpilogueSpec {
     int32_t out_is_int;  // output dtype is int64
     const int64_t *cnt;  // valid-row count of the input column per window (null for WindowStart)
     const uint8_t *ok;   // optional per-window validity bytes overriding cnt > 0 (integral family)
-    const double *sum_src;  // ArithmeticMean: per-window sums (may alias values)
+    const double *sum_src;  // ArithmeticMean: per-window sums; WeightedAverage*: integrals (may alias values)
     void *values;        // [W]
     uint8_t *validity;   // [ceil(W/8)] bytes
     int32_t nfactors;

@@ -1,0 +1,215 @@
+// seg_basic — Count / Sum / ArithmeticMean / Min / Max / First / Last on the streaming segmented
+// reduction (segreduce.cuh).  Replaces the per-window closures of the reference
+// (rolling/aggregation/{count,sum,arithmeticmean,minmax,firstlast}.go).
+//
+// Window state (a monoid; combine(L, R) keeps the left operand on ties, which reproduces the
+// reference's sequential semantics bit-exactly for Count/Min/Max/First/Last):
+//   cnt   valid rows                                           count.go:8-20
+//   sum   sum of float64(v) over valid rows                    sum.go:8-25, arithmeticmean.go:8-30
+//   mn/mx min / max over the non-NaN valid values, earliest wins on ties (minmax.go:20, `v < m`)
+//   fi/li index of the first / last valid row                  firstlast.go:8-36
+// cnt / fi / li never cost anything per row: they are popcount / ffs / fls of the thread's validity
+// bits masked to the segment.  Min/Max of the reference start from the FIRST valid value and only
+// replace on a strict compare, so a leading NaN is sticky and later NaNs are ignored:
+// result = isnan(first) ? first : mn.  ArithmeticMean = sum / float64(cnt) is formed by the epilogue.
+#include <math_constants.h>
+
+#include "segreduce.cuh"
+
+namespace bowgpu {
+
+namespace {
+
+constexpr int64_t CLOSED_BIT = (int64_t)1 << 62;
+static_assert(SegG::T < 4096, "cnt / fi are packed in 12 bits each");
+
+// state of a run of rows; meta = cnt | fi << 12 (tile-relative first valid row), li = last valid row
+struct BState {
+    double sum, mn, mx;
+    uint32_t meta;
+    uint32_t li;
+};
+
+// Final per-window write (values only; validity bitmaps, the mean division and empty-window defaults
+// are produced by the epilogue from cnt).  first/last are raw value bits.
+template <bool IS_INT>
+__device__ __forceinline__ void write_window(const BasicOut &o, int64_t W, int64_t k, int64_t cnt, double sum,
+                                             double mn, double mx, uint64_t first, uint64_t last) {
+    if ((uint64_t)k >= (uint64_t)W || cnt == 0) return;
+    o.cnt[k] = cnt;
+    if (o.sum) o.sum[k] = sum;
+    if (o.mn || o.mx) {
+        const double f = bits_as_f64(first);
+        const bool sticky = !IS_INT && (f != f);  // first valid value is NaN (minmax.go:14-24)
+        if (o.mn) o.mn[k] = sticky ? f : mn;
+        if (o.mx) o.mx[k] = sticky ? f : mx;
+    }
+    if (o.first) o.first[k] = first;
+    if (o.last) o.last[k] = last;
+}
+
+template <uint32_t OPS, bool IS_INT>
+struct BasicPol {
+    using State = BState;
+    using Carry = BasicCarry;
+    using Out = BasicOut;
+    struct Inc {};
+    static constexpr bool NEXT_VALUE = false;
+
+    static __device__ __forceinline__ uint32_t cnt(const State &s) { return s.meta & 0xFFFu; }
+    static __device__ __forceinline__ uint32_t fi(const State &s) { return s.meta >> 12; }
+    static __device__ __forceinline__ Inc make_inc(bool, bool, uint64_t, int64_t) { return Inc(); }
+
+    static __device__ __forceinline__ State identity() {
+        State s;
+        s.sum = 0.0;
+        s.mn = CUDART_INF;
+        s.mx = -CUDART_INF;
+        s.meta = 0;
+        s.li = 0;
+        return s;
+    }
+    static __device__ __forceinline__ void accumulate(State &s, int64_t, uint64_t raw) {
+        const double v = IS_INT ? (double)(int64_t)raw : bits_as_f64(raw);  // GetFloat64, bowgetters.go:218-229
+        s.sum += v;
+        if (OPS & OPS_MINMAX) {
+            if (v < s.mn) s.mn = v;
+            if (v > s.mx) s.mx = v;
+        }
+    }
+    // cnt / fi / li of the rows selected by `mask` (bit j = row ti0 + j of the tile)
+    static __device__ __forceinline__ void set_meta(State &s, uint32_t mask, int ti0) {
+        const uint32_t c = __popc(mask);
+        const uint32_t f = mask ? (uint32_t)(ti0 + __ffs(mask) - 1) : 0u;
+        s.meta = c | (f << 12);
+        s.li = mask ? (uint32_t)(ti0 + 31 - __clz(mask)) : 0u;
+    }
+    static __device__ __forceinline__ State combine(const State &L, const State &R) {
+        State o;
+        o.sum = L.sum + R.sum;
+        if (OPS & OPS_MINMAX) {
+            o.mn = (R.mn < L.mn) ? R.mn : L.mn;
+            o.mx = (R.mx > L.mx) ? R.mx : L.mx;
+        }
+        const uint32_t lc = L.meta & 0xFFFu, rc = R.meta & 0xFFFu;
+        o.meta = (lc + rc) | ((lc ? L.meta : R.meta) & 0xFFF000u);
+        if (OPS & OPS_FIRSTLAST) o.li = rc ? R.li : L.li;
+        return o;
+    }
+    static __device__ __forceinline__ State shfl_up(const State &s, int d) {
+        State o;
+        o.sum = __shfl_up_sync(0xffffffffu, s.sum, d);
+        if (OPS & OPS_MINMAX) {
+            o.mn = __shfl_up_sync(0xffffffffu, s.mn, d);
+            o.mx = __shfl_up_sync(0xffffffffu, s.mx, d);
+        }
+        o.meta = __shfl_up_sync(0xffffffffu, s.meta, d);
+        if (OPS & OPS_FIRSTLAST) o.li = __shfl_up_sync(0xffffffffu, s.li, d);
+        return o;
+    }
+    static __device__ __forceinline__ void write(const Out &o, const WindowGeom &g, int64_t k, const State &s,
+                                                 const Inc &, const uint64_t *vsm) {
+        const uint32_t c = cnt(s);
+        const uint64_t fb = c ? vsm[fi(s)] : 0, lb = c ? vsm[s.li] : 0;
+        write_window<IS_INT>(o, g.W, k, c, s.sum, s.mn, s.mx, fb, lb);
+    }
+    static __device__ __forceinline__ Carry make_carry(const State &s, const Inc &, const uint64_t *vsm, int64_t key,
+                                                       bool closed) {
+        const uint32_t c = cnt(s);
+        Carry r;
+        r.key = key;
+        r.cnt = (int64_t)c | (closed ? CLOSED_BIT : 0);
+        r.sum = s.sum;
+        r.mn = s.mn;
+        r.mx = s.mx;
+        r.first = c ? vsm[fi(s)] : 0;
+        r.last = c ? vsm[s.li] : 0;
+        r._pad = 0;
+        return r;
+    }
+    static __device__ __forceinline__ void carry_set_key(Carry &c, int64_t key) { c.key = key; }
+    static __device__ __forceinline__ int64_t carry_key(const Carry &c) { return c.key; }
+    static __device__ __forceinline__ bool carry_closed(const Carry &c) { return (c.cnt & CLOSED_BIT) != 0; }
+    static __device__ __forceinline__ void carry_combine(Carry &a, const Carry &h) {
+        const int64_t hc = h.cnt & ~CLOSED_BIT;
+        a.sum = a.sum + h.sum;
+        a.mn = (h.mn < a.mn) ? h.mn : a.mn;
+        a.mx = (h.mx > a.mx) ? h.mx : a.mx;
+        a.first = a.cnt ? a.first : h.first;
+        a.last = hc ? h.last : a.last;
+        a.cnt += hc;
+    }
+    static __device__ __forceinline__ void write_carry(const Out &o, const WindowGeom &g, int64_t k, const Carry &a) {
+        write_window<IS_INT>(o, g.W, k, a.cnt, a.sum, a.mn, a.mx, a.first, a.last);
+    }
+    // Windows that begin AND end strictly inside one thread's rows (only when windows are shorter than
+    // R rows): rows (jfirst, jlast] of the thread are re-reduced window by window from shared memory in
+    // a rolled loop and written out directly.  Kept out of line so the unrolled fast path stays small.
+    static __device__ __noinline__ void middle(const Out *outp, int64_t W, int64_t s0, uint64_t d, double inv_rd,
+                                               const int64_t *trow, const uint64_t *vrow, uint32_t vbits, int jfirst,
+                                               int jlast, int /*nexist*/) {
+        const Out o = *outp;
+        State st = identity();
+        uint32_t seg = 0;  // valid rows of the current window
+        uint64_t kcur = div_slow((uint64_t)trow[jfirst + 1] - (uint64_t)s0, d, inv_rd);
+        uint64_t erel = (kcur + 1) * d;
+        for (int j = jfirst + 1; j <= jlast; ++j) {
+            if ((vbits >> j) & 1u) {
+                accumulate(st, 0, vrow[j]);
+                seg |= 1u << j;
+            }
+            const uint64_t xn = (uint64_t)trow[j + 1] - (uint64_t)s0;
+            if (j == jlast || xn >= erel) {
+                const uint64_t fb = seg ? vrow[__ffs(seg) - 1] : 0, lb = seg ? vrow[31 - __clz(seg)] : 0;
+                write_window<IS_INT>(o, W, (int64_t)kcur, __popc(seg), st.sum, st.mn, st.mx, fb, lb);
+                st = identity();
+                seg = 0;
+                if (xn - erel < d) {
+                    ++kcur;
+                    erel += d;
+                } else {
+                    kcur = div_slow(xn, d, inv_rd);
+                    erel = (kcur + 1) * d;
+                }
+            }
+        }
+    }
+};
+
+template <uint32_t OPS>
+int launch_ops(const SegLaunch &L, int sm, cudaStream_t s, cudaEvent_t e0, cudaEvent_t e1) {
+    const bool nulls = L.validity != nullptr;
+    auto fill = [&](auto &A) {
+        A.time = L.time;
+        A.values = L.values;
+        A.validity = L.validity;
+        A.g = L.g;
+        A.out = L.out;
+        A.carry_head = L.carry_head;
+        A.carry_tail = L.carry_tail;
+        A.status = L.status;
+    };
+    if (L.is_int) {
+        SegArgs<BasicPol<OPS, true>> A;
+        fill(A);
+        return nulls ? seg_launch<BasicPol<OPS, true>, true, 3>(A, sm, s, e0, e1)
+                     : seg_launch<BasicPol<OPS, true>, false, 3>(A, sm, s, e0, e1);
+    }
+    SegArgs<BasicPol<OPS, false>> A;
+    fill(A);
+    return nulls ? seg_launch<BasicPol<OPS, false>, true, 3>(A, sm, s, e0, e1)
+                 : seg_launch<BasicPol<OPS, false>, false, 3>(A, sm, s, e0, e1);
+}
+
+}  // namespace
+
+int64_t seg_num_tiles(int64_t n) { return (n + SegG::T - 1) / SegG::T; }
+size_t seg_carry_bytes(int64_t n) { return (size_t)seg_num_tiles(n) * 2 * sizeof(BasicCarry); }
+
+int launch_segreduce_basic(const SegLaunch &L, int sm_count, cudaStream_t stream, cudaEvent_t e0, cudaEvent_t e1) {
+    if (L.ops & OPS_FIRSTLAST) return launch_ops<OPS_SUMCNT | OPS_MINMAX | OPS_FIRSTLAST>(L, sm_count, stream, e0, e1);
+    if (L.ops & OPS_MINMAX) return launch_ops<OPS_SUMCNT | OPS_MINMAX>(L, sm_count, stream, e0, e1);
+    return launch_ops<OPS_SUMCNT>(L, sm_count, stream, e0, e1);
+}
+
+}  // namespace bowgpu

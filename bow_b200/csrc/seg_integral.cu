@@ -1,0 +1,238 @@
+// seg_integral — IntegralStep / IntegralTrapezoid (and, through the epilogue's division by the window
+// width, WeightedAverageStep / WeightedAverageLinear) on the streaming segmented reduction.
+// Replaces rolling/aggregation/integral.go:8-69 and weightedmean.go:8-34.
+//
+// A "point" is a row whose value is valid (the time column is non-null on the GPU path).  With
+// T = float64(t) converted BEFORE subtracting, exactly like the reference (integral.go:48-55):
+//   step       sum_j v_j * (T_{j+1} - T_j)  +  v_last * (float64(E_k) - T_last)         integral.go:40-69
+//   trapezoid  sum_j (v_j + v_{j+1}) / 2 * (T_{j+1} - T_j)  over rows_inc(k)             integral.go:8-38
+// State of a run of rows: {n, firstT, firstV, lastT, lastV, sumStep, sumTrap}; two adjacent runs
+// combine by adding the joint term between L's last and R's first point, so the state is a monoid
+// and the generic kernel can split windows at thread and tile boundaries.  The trapezoid needs
+// inclusive windows (integral.go:9): the row after a window's last row joins it when its time equals
+// the window end; the closing thread sees that row (Inc) and appends it at finalisation.
+// No FMA contraction (-fmad=false): Go on amd64 rounds the product and the sum separately.
+#include "segreduce.cuh"
+
+namespace bowgpu {
+
+namespace {
+
+struct IState {
+    double fT, fV, lT, lV, sS, sT;
+    uint32_t n;
+};
+
+struct alignas(16) ICarry {
+    int64_t key;       // window index, -1 = none
+    int64_t n;         // points; bit 62 = window closed inside the tile (head records)
+    double fT, fV, lT, lV, sS, sT;
+    double incV, incT;
+    int64_t inc_has;
+    int64_t _pad;
+};
+constexpr int64_t I_CLOSED_BIT = (int64_t)1 << 62;
+
+template <bool STEP, bool TRAP, bool IS_INT>
+struct IntegralPol {
+    using State = IState;
+    using Carry = ICarry;
+    using Out = IntegralOut;
+    struct Inc {
+        double v, T;
+        bool has;
+    };
+    static constexpr bool NEXT_VALUE = TRAP;
+
+    static __device__ __forceinline__ double val(uint64_t raw) {
+        return IS_INT ? (double)(int64_t)raw : bits_as_f64(raw);  // GetFloat64, bowgetters.go:218-229
+    }
+    static __device__ __forceinline__ Inc make_inc(bool at_end, bool valid_next, uint64_t raw_next, int64_t t_next) {
+        Inc i;
+        i.has = at_end && valid_next;
+        i.v = val(raw_next);
+        i.T = (double)t_next;
+        return i;
+    }
+    static __device__ __forceinline__ State identity() {
+        State s;
+        s.fT = s.fV = s.lT = s.lV = 0.0;
+        s.sS = s.sT = 0.0;
+        s.n = 0;
+        return s;
+    }
+    static __device__ __forceinline__ void accumulate(State &s, int64_t t, uint64_t raw) {
+        const double T = (double)t, v = val(raw);
+        if (s.n) {
+            const double dt = T - s.lT;
+            if (STEP) s.sS += s.lV * dt;              // integral.go:57
+            if (TRAP) s.sT += (s.lV + v) / 2 * dt;    // integral.go:28
+        } else {
+            s.fT = T;
+            s.fV = v;
+        }
+        s.lT = T;
+        s.lV = v;
+        s.n += 1;
+    }
+    static __device__ __forceinline__ void set_meta(State &, uint32_t, int) {}
+    static __device__ __forceinline__ State combine(const State &L, const State &R) {
+        State o;
+        const bool l = L.n != 0, r = R.n != 0;
+        const double dt = R.fT - L.lT;
+        if (STEP) {
+            const double j = (L.sS + L.lV * dt) + R.sS;
+            o.sS = l ? (r ? j : L.sS) : R.sS;
+        }
+        if (TRAP) {
+            const double j = (L.sT + (L.lV + R.fV) / 2 * dt) + R.sT;
+            o.sT = l ? (r ? j : L.sT) : R.sT;
+        }
+        o.fT = l ? L.fT : R.fT;
+        o.fV = l ? L.fV : R.fV;
+        o.lT = r ? R.lT : L.lT;
+        o.lV = r ? R.lV : L.lV;
+        o.n = L.n + R.n;
+        return o;
+    }
+    static __device__ __forceinline__ State shfl_up(const State &s, int d) {
+        State o;
+        o.fT = __shfl_up_sync(0xffffffffu, s.fT, d);
+        o.fV = __shfl_up_sync(0xffffffffu, s.fV, d);
+        o.lT = __shfl_up_sync(0xffffffffu, s.lT, d);
+        o.lV = __shfl_up_sync(0xffffffffu, s.lV, d);
+        if (STEP) o.sS = __shfl_up_sync(0xffffffffu, s.sS, d);
+        if (TRAP) o.sT = __shfl_up_sync(0xffffffffu, s.sT, d);
+        o.n = __shfl_up_sync(0xffffffffu, s.n, d);
+        return o;
+    }
+    static __device__ __forceinline__ void finish(const Out &o, int64_t W, int64_t s0, uint64_t d, int64_t k, int64_t n,
+                                                  double lT, double lV, double sS, double sT, bool inc_has,
+                                                  double incV, double incT) {
+        if ((uint64_t)k >= (uint64_t)W) return;
+        if (STEP && n > 0) {
+            const double E = (double)(int64_t)((uint64_t)s0 + ((uint64_t)k + 1) * d);  // float64(w.LastValue)
+            o.step[k] = sS + lV * (E - lT);                                             // integral.go:53-57
+            o.n_step[k] = n;
+        }
+        if (TRAP && n + (inc_has ? 1 : 0) >= 2) {  // integral.go:33-35: fewer than two points -> nil
+            double s = sT;
+            if (inc_has) s += (lV + incV) / 2 * (incT - lT);
+            o.trap[k] = s;
+            o.n_trap[k] = 1;
+        }
+    }
+    static __device__ __forceinline__ void write(const Out &o, const WindowGeom &g, int64_t k, const State &s,
+                                                 const Inc &inc, const uint64_t *) {
+        finish(o, g.W, g.s0, g.div.d, k, s.n, s.lT, s.lV, s.sS, s.sT, TRAP && inc.has, inc.v, inc.T);
+    }
+    static __device__ __forceinline__ Carry make_carry(const State &s, const Inc &inc, const uint64_t *, int64_t key,
+                                                       bool closed) {
+        Carry c;
+        c.key = key;
+        c.n = (int64_t)s.n | (closed ? I_CLOSED_BIT : 0);
+        c.fT = s.fT;
+        c.fV = s.fV;
+        c.lT = s.lT;
+        c.lV = s.lV;
+        c.sS = STEP ? s.sS : 0.0;
+        c.sT = TRAP ? s.sT : 0.0;
+        c.incV = inc.v;
+        c.incT = inc.T;
+        c.inc_has = TRAP && inc.has;
+        c._pad = 0;
+        return c;
+    }
+    static __device__ __forceinline__ void carry_set_key(Carry &c, int64_t key) { c.key = key; }
+    static __device__ __forceinline__ int64_t carry_key(const Carry &c) { return c.key; }
+    static __device__ __forceinline__ bool carry_closed(const Carry &c) { return (c.n & I_CLOSED_BIT) != 0; }
+    static __device__ __forceinline__ void carry_combine(Carry &a, const Carry &h) {
+        const int64_t hn = h.n & ~I_CLOSED_BIT;
+        if (hn) {
+            if (a.n) {
+                const double dt = h.fT - a.lT;
+                a.sS = (a.sS + a.lV * dt) + h.sS;
+                a.sT = (a.sT + (a.lV + h.fV) / 2 * dt) + h.sT;
+            } else {
+                a.sS = h.sS;
+                a.sT = h.sT;
+                a.fT = h.fT;
+                a.fV = h.fV;
+            }
+            a.lT = h.lT;
+            a.lV = h.lV;
+            a.n += hn;
+        }
+        a.inc_has = h.inc_has;
+        a.incV = h.incV;
+        a.incT = h.incT;
+    }
+    static __device__ __forceinline__ void write_carry(const Out &o, const WindowGeom &g, int64_t k, const Carry &a) {
+        finish(o, g.W, g.s0, g.div.d, k, a.n, a.lT, a.lV, a.sS, a.sT, a.inc_has != 0, a.incV, a.incT);
+    }
+    // windows strictly inside one thread's rows (see BasicPol::middle)
+    static __device__ __noinline__ void middle(const Out *outp, int64_t W, int64_t s0, uint64_t d, double inv_rd,
+                                               const int64_t *trow, const uint64_t *vrow, uint32_t vraw, int jfirst,
+                                               int jlast, int nexist) {
+        const Out o = *outp;
+        State st = identity();
+        uint64_t kcur = div_slow((uint64_t)trow[jfirst + 1] - (uint64_t)s0, d, inv_rd);
+        uint64_t erel = (kcur + 1) * d;
+        for (int j = jfirst + 1; j <= jlast; ++j) {
+            if ((vraw >> j) & 1u) accumulate(st, trow[j], vrow[j]);
+            const bool next_exists = j + 1 < nexist;
+            const uint64_t xn = (uint64_t)trow[j + 1] - (uint64_t)s0;
+            if (j == jlast || xn >= erel) {
+                const bool inc = TRAP && next_exists && xn == erel && ((vraw >> (j + 1)) & 1u);
+                finish(o, W, s0, d, (int64_t)kcur, st.n, st.lT, st.lV, st.sS, st.sT, inc, val(vrow[j + 1]),
+                       (double)trow[j + 1]);
+                st = identity();
+                if (xn - erel < d) {
+                    ++kcur;
+                    erel += d;
+                } else {
+                    kcur = div_slow(xn, d, inv_rd);
+                    erel = (kcur + 1) * d;
+                }
+            }
+        }
+    }
+};
+
+template <bool STEP, bool TRAP>
+int launch_mode(const IntLaunch &L, int sm, cudaStream_t s, cudaEvent_t e0, cudaEvent_t e1) {
+    const bool nulls = L.validity != nullptr;
+    auto fill = [&](auto &A) {
+        A.time = L.time;
+        A.values = L.values;
+        A.validity = L.validity;
+        A.g = L.g;
+        A.out = L.out;
+        A.carry_head = (ICarry *)L.carry_head;
+        A.carry_tail = (ICarry *)L.carry_tail;
+        A.status = L.status;
+    };
+    if (L.is_int) {
+        SegArgs<IntegralPol<STEP, TRAP, true>> A;
+        fill(A);
+        return nulls ? seg_launch<IntegralPol<STEP, TRAP, true>, true, 2>(A, sm, s, e0, e1)
+                     : seg_launch<IntegralPol<STEP, TRAP, true>, false, 2>(A, sm, s, e0, e1);
+    }
+    SegArgs<IntegralPol<STEP, TRAP, false>> A;
+    fill(A);
+    return nulls ? seg_launch<IntegralPol<STEP, TRAP, false>, true, 2>(A, sm, s, e0, e1)
+                 : seg_launch<IntegralPol<STEP, TRAP, false>, false, 2>(A, sm, s, e0, e1);
+}
+
+}  // namespace
+
+size_t integral_carry_bytes(int64_t n) { return (size_t)((n + SegG::T - 1) / SegG::T) * 2 * sizeof(ICarry); }
+
+int launch_segreduce_integral(const IntLaunch &L, int sm_count, cudaStream_t stream, cudaEvent_t e0, cudaEvent_t e1) {
+    const bool step = L.out.step != nullptr, trap = L.out.trap != nullptr;
+    if (step && trap) return launch_mode<true, true>(L, sm_count, stream, e0, e1);
+    if (trap) return launch_mode<false, true>(L, sm_count, stream, e0, e1);
+    return launch_mode<true, false>(L, sm_count, stream, e0, e1);
+}
+
+}  // namespace bowgpu

@@ -22,9 +22,12 @@ struct TileGeom {
     static constexpr int T = NT * R;                 // rows per tile
     static constexpr int TIME_ENTRIES = T + 4;       // rows r0-2 .. r0+T+1
     static constexpr int TIME_BYTES = TIME_ENTRIES * 8;
-    static constexpr int VAL_BYTES = T * 8;
+    static constexpr int VAL_ENTRIES = T + 2;        // rows r0 .. r0+T+1 (the row after the tile is the
+    static constexpr int VAL_BYTES = VAL_ENTRIES * 8;  // inclusive row of a window closing at the tile end)
     static constexpr int BITS_BYTES = T / 8;         // validity bytes of one tile
-    static constexpr int BITS_STRIDE = BITS_BYTES + 16;
+    static constexpr int BITS_COPY = BITS_BYTES + 16;  // + the bits of the rows after the tile
+    static constexpr int BITS_STRIDE = BITS_COPY + 16;
+    static constexpr int STAGE_BYTES = TIME_BYTES + VAL_BYTES + BITS_STRIDE;
     static_assert(R % 2 == 1, "R must be odd (bank-conflict-free thread-consecutive reads)");
     static_assert(T % 128 == 0, "tile validity bytes must be a multiple of 16");
     static_assert(R <= 31, "per-thread validity bits are extracted from two 32-bit words");
@@ -52,6 +55,7 @@ struct TileSrc {
 };
 
 // Called by ONE thread.  Stage layout: [time TIME_BYTES][values VAL_BYTES][bits BITS_STRIDE].
+// (TIME_BYTES, VAL_BYTES and BITS_COPY are multiples of 16, so every destination is 16-byte aligned.)
 template <class G, bool WITH_VALUES>
 __device__ __forceinline__ void issue_tile(const TileSrc &src, int64_t tile, uint8_t *stage, uint64_t *bar) {
     const int64_t r0 = tile * G::T;
@@ -60,14 +64,14 @@ __device__ __forceinline__ void issue_tile(const TileSrc &src, int64_t tile, uin
     if (hi > src.n) hi = src.n;
     uint8_t *tdst = stage + (r0 == 0 ? 16 : 0);
     const uint32_t tbytes = (uint32_t)(hi - lo) * 8u;
-    int64_t vhi = r0 + G::T;
+    int64_t vhi = r0 + G::VAL_ENTRIES;
     if (vhi > src.n) vhi = src.n;
     const uint32_t vbytes = (uint32_t)(vhi - r0) * 8u;
     uint32_t bbytes = 0;
     if (WITH_VALUES && src.validity) {
         int64_t total = ((src.n + 7) / 8 + 15) & ~(int64_t)15;  // device bitmaps are padded to 16B
         int64_t b0 = r0 / 8;
-        int64_t b1 = b0 + G::BITS_BYTES;
+        int64_t b1 = b0 + G::BITS_COPY;
         if (b1 > total) b1 = total;
         bbytes = (uint32_t)(b1 - b0);
     }

@@ -79,8 +79,6 @@ def run_both(ctx, cols, interval, specs, offset=0, inclusive=False, slice_offset
                          ids=[f"{c[0]}-{c[1]}-{c[2]}" for c in G.AGGREGATIONS])
 def test_golden_aggregations(ctx, agg, fixture, factor, vtype, expected, cite):
     from bow_b200 import native as N
-    if N.AGG[agg] >= 8:
-        pytest.skip("integral family: see test_gpu_integral.py")
     rows = G.FIXTURES[fixture]
     cols = H.np_cols_from_lists([[r[0] for r in rows], [r[1] for r in rows]], [L.INT64, L.FLOAT64])
     fr = N.Frame.from_numpy(ctx, cols)
@@ -127,6 +125,45 @@ def test_random_vs_oracle(ctx, kind, n):
         got, want, abs_sums = run_both(ctx, cols, interval, specs, offset=offset, inclusive=inclusive,
                                        slice_offset=int(rng.integers(0, 70)) if trial == 3 else 0)
         compare_aggs(BASIC, got, want, abs_sums, what=f"{kind} n={n} I={interval} off={offset} inc={inclusive}")
+
+
+INTEGRALS = ["IntegralStep", "IntegralTrapezoid", "WeightedAverageStep", "WeightedAverageLinear"]
+ICASES = [(k, n) for k in ("regular", "dense", "sparse", "bursty") for n in (1, 2, 17, 18, 300, 2176, 2177, 4353, 30011)]
+
+
+@pytest.mark.parametrize("kind,n", ICASES, ids=[f"{k}-{n}" for k, n in ICASES])
+def test_random_integrals_vs_oracle(ctx, kind, n):
+    """float64 integrals / weighted averages: |gpu - ref| <= 1e-12 * max(|ref|, integral of |v|)"""
+    from bow_b200 import native as N
+    rng = np.random.default_rng(hash((kind, n, "i")) & 0xFFFF)
+    for trial in range(4):
+        t = H.random_times(rng, n, kind)
+        dtype = np.int64 if trial == 1 else np.float64
+        v = H.random_values(rng, n, dtype, [0.0, 0.3, 0.1, 0.9][trial])
+        interval = int(rng.choice([1, 2, 5, 10, 60, 1000, 100000]))
+        offset = int(rng.integers(-2 * interval, 2 * interval))
+        inclusive = bool(rng.integers(0, 2))
+        cols = [(t, None), v]
+        specs = [("WindowStart", 0)] + [(a, 1) for a in INTEGRALS] + [("IntegralStep", 1, [0.5]), ("Count", 1)]
+        fr = N.Frame.from_numpy(ctx, cols, offset=int(rng.integers(0, 70)) if trial == 3 else 0)
+        r = N.Rolling(fr, 0, interval, offset=offset, inclusive=inclusive)
+        got = r.aggregate(specs)
+        want = R.RefRolling(R.Frame(cols), 0, interval, offset=offset, inclusive=inclusive).aggregate(specs)
+        av = (np.abs(v[0].astype(np.float64)), v[1])
+        scale = R.RefRolling(R.Frame([cols[0], av]), 0, interval, offset=offset, inclusive=inclusive).aggregate(
+            [("WindowStart", 0), ("IntegralStep", 1), ("IntegralTrapezoid", 1)])
+        sc = np.maximum(np.where(scale[1][1], np.abs(scale[1][0]), 0), np.where(scale[2][1], np.abs(scale[2][0]), 0))
+        what = f"{kind} n={n} I={interval} off={offset} inc={inclusive} trial={trial}"
+        for j, sp in enumerate(specs):
+            (gv, gm), (wv, wm) = got[j], want[j]
+            assert np.array_equal(gm, wm), f"{what} {sp}: validity differs at {np.flatnonzero(gm != wm)[:10]}"
+            if sp[0] in ("WindowStart", "Count"):
+                assert np.array_equal(gv, wv), (what, sp)
+                continue
+            tol = TOL * np.maximum(np.abs(wv), sc if sp[0].startswith("Integral") else sc / interval)
+            bad = np.flatnonzero(~(np.abs(gv - wv) <= tol) & (bits(gv) != bits(wv)))
+            assert bad.size == 0, f"{what} {sp}: {bad[:10]} got {gv[bad[:10]]} want {wv[bad[:10]]}"
+            assert not np.any(bits(gv)[~gm]), f"{what} {sp}: non-zero value in a null slot"
 
 
 @pytest.mark.parametrize("kind", ["regular", "dense", "sparse", "bursty"])
