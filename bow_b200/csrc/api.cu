@@ -999,5 +999,115 @@ extern "C" int32_t bowgpu_rolling_aggregate(bowgpu_rolling *r, const bowgpu_agg_
 extern "C" int32_t bowgpu_rolling_interpolate(bowgpu_rolling *r, const int32_t *ops, int32_t nops, bowgpu_frame **out_frame,
                                               int64_t *n_out) {
     if (!r || !ops || !out_frame || !n_out) return BOWGPU_EINVAL;
-    return fail(r->frame->ctx, BOWGPU_EUNSUPPORTED, "interpolate not built yet");
+    *out_frame = nullptr;
+    *n_out = 0;
+    bowgpu_frame *f = r->frame;
+    bowgpu_ctx *ctx = f->ctx;
+    Guard gd(ctx);
+    const int ncols = (int)f->cols.size();
+    // the reference appends [start row] ++ window by column POSITION (bowappend.go:28-47): the interpolations must
+    // name every column of the Bow in schema order (which also keeps the interval column, interpolation.go:49-51)
+    if (nops != ncols)
+        return fail(ctx, BOWGPU_EINVAL, "interpolations must name every column in schema order (%d given, %d columns)", nops, ncols);
+    if (ncols > INTERP_MAX_COLS) return fail(ctx, BOWGPU_EUNSUPPORTED, "interpolate supports at most %d columns", INTERP_MAX_COLS);
+    for (int j = 0; j < nops; ++j) {  // validateInterpolation, interpolation.go:71-96
+        if (ops[j] < 0 || ops[j] > BOWGPU_INTERP_NONE) return fail(ctx, BOWGPU_EUNSUPPORTED, "interpolation %d: unknown opcode %d", j, ops[j]);
+        if (ops[j] == BOWGPU_INTERP_WINDOW_START && f->cols[j].dtype != BOWGPU_INT64)
+            return fail(ctx, BOWGPU_ETYPE, "interpolation %d: WindowStart accepts types [int64], got type float64", j);
+    }
+    const WindowGeom g = make_geom(r, r->inclusive);
+    const int64_t W = g.W;
+    bowgpu_frame *of = new (std::nothrow) bowgpu_frame();
+    if (!of) return BOWGPU_ENOMEM;
+    of->ctx = ctx;
+    of->cols.resize(ncols);
+    for (int j = 0; j < ncols; ++j) of->cols[j].dtype = f->cols[j].dtype;
+    auto bail = [&](int32_t code) {
+        cudaStreamSynchronize(ctx->stream);
+        for (auto &c : of->cols) free_col(c);
+        delete of;
+        return code;
+    };
+    if (W == 0 || g.n == 0) {  // interpolation.go:59-61: empty result keeps the schema
+        *out_frame = of;
+        return BOWGPU_OK;
+    }
+    const size_t wv = align_up((size_t)(W + 1) * 8, 256), wb = align_up((size_t)W + 16, 256);
+    const size_t need = 8192 + 3 * wv + (size_t)ncols * (wv + wb) + scan_scratch_bytes(W) + 1024;
+    int32_t rc = arena_reserve(ctx, need);
+    if (rc) return bail(rc);
+    arena_reset(ctx);
+    InterpLaunch L;
+    memset(&L, 0, sizeof L);
+    L.time = (const int64_t *)f->cols[r->time_col].values;
+    int64_t *d_first = (int64_t *)arena_take(ctx, wv);
+    L.first = d_first;
+    L.off = (int64_t *)arena_take(ctx, wv);
+    L.wsrc = (int64_t *)arena_take(ctx, wv);
+    int64_t *scan_tmp = (int64_t *)arena_take(ctx, scan_scratch_bytes(W));
+    L.g = g;
+    L.inclusive = r->inclusive;
+    L.ncols = ncols;
+    if (r->has_prev) {
+        L.prev_time = (int64_t)r->prev[r->time_col].bits;
+        L.prev_time_valid = r->prev[r->time_col].valid;
+    }
+    for (int j = 0; j < ncols; ++j) {
+        InterpCol &c = L.cols[j];
+        c.values = f->cols[j].values;
+        c.validity = (const uint32_t *)f->cols[j].validity;
+        c.syn_val = (uint64_t *)arena_take(ctx, wv);
+        c.syn_ok = (uint8_t *)arena_take(ctx, wb);
+        c.op = ops[j];
+        c.is_int = f->cols[j].dtype == BOWGPU_INT64;
+        if (r->has_prev) {
+            c.prev_bits = r->prev[j].bits;
+            c.prev_valid = r->prev[j].valid;
+        }
+    }
+    timing_begin(ctx);
+    BoundsLaunch B;
+    B.time = L.time;
+    B.g = g;
+    B.first = d_first;
+    B.status = ctx->d_status;
+    int e = launch_bounds(B, ctx->sm_count, ctx->stream, nullptr, nullptr);
+    if (!e) e = launch_interp_windows(L, ctx->stream);
+    if (!e) e = launch_exclusive_scan(L.off, W, scan_tmp, ctx->stream);
+    count_launch(ctx, 5);
+    int64_t total = 0;
+    if (e || cudaMemcpyAsync(&total, L.off + W, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+        return bail(fail(ctx, BOWGPU_ECUDA, "interpolate (windows/scan): %s", cudaGetErrorString(cudaGetLastError())));
+    of->n = total;
+    for (int j = 0; j < ncols; ++j) {
+        const bool may_null = f->cols[j].validity != nullptr || ops[j] != BOWGPU_INTERP_WINDOW_START;
+        rc = alloc_col(ctx, of->cols[j], total, f->cols[j].dtype, may_null);
+        if (rc) return bail(rc);
+        L.cols[j].out_values = of->cols[j].values;
+        L.cols[j].out_validity = (uint32_t *)of->cols[j].validity;
+    }
+    cudaEvent_t e0, e1;
+    timing_main_pair(ctx, &e0, &e1);
+    e = launch_interp_gather(L, total, ctx->sm_count, ctx->stream, e0, e1);
+    count_launch(ctx, 1);
+    count_launch(ctx, 1, true);
+    timing_end(ctx);
+    if (e) return bail(fail(ctx, BOWGPU_ECUDA, "interpolate (gather): %s", cudaGetErrorString((cudaError_t)e)));
+    for (int j = 0; j < ncols; ++j) {  // bitmaps without nulls are dropped (the aggregation kernels run faster)
+        DevCol &c = of->cols[j];
+        if (!c.validity) continue;
+        rc = count_nulls(ctx, c, total);
+        if (rc) return bail(rc);
+        if (c.null_count == 0) {
+            cudaFree(c.validity);
+            c.validity = nullptr;
+            c.own_validity = false;
+        }
+    }
+    rc = check_status(ctx);
+    if (rc) return bail(rc);
+    *out_frame = of;
+    *n_out = total;
+    return BOWGPU_OK;
 }

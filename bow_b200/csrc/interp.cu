@@ -1,0 +1,328 @@
+// interp — Rolling.Interpolate on the device (reference rolling/interpolation.go:30-161 and the
+// closures of rolling/interpolation/{windowstart,linear,stepprevious,none}.go).
+//
+// Output Bow = for every window k: [one synthetic row at S_k iff the window has no row whose time
+// equals S_k] ++ the rows of the window (interpolation.go:118-161).  Three steps:
+//   1. interp_window_kernel (W threads): slice [lo, hi) of the window from the bounds array,
+//      "missing start" test through the reference's float64 round trip (interpolation.go:121-128),
+//      the synthetic row's value for every column (prev / next valid row found by word-wise scans of
+//      the validity bitmap), and the window's output row count;
+//   2. an exclusive scan of the counts (block-level scan + partial sums) -> output offset per window;
+//   3. interp_gather_kernel: row tiles of the OUTPUT frame; each CTA loads the offsets of the windows
+//      overlapping its tile into shared memory, every thread binary-searches its row's window there and
+//      copies all columns; validity words are built with ballot, so the bit-granular shift caused by
+//      inserted rows costs nothing.  Balanced by rows, independent of window sizes.
+#include "../../include/bowgpu.h"
+#include "kernels.h"
+
+namespace bowgpu {
+
+namespace {
+
+// ---- word-wise validity scans (GetPrev* / GetNext* of the reference, bowgetters.go:65-107,282-311) ------
+__device__ __forceinline__ int64_t prev_valid(const uint32_t *bm, int64_t i) {  // last valid row <= i, or -1
+    if (i < 0) return -1;
+    if (!bm) return i;
+    int64_t w = i >> 5;
+    uint32_t m = bm[w] & (0xFFFFFFFFu >> (31 - (int)(i & 31)));
+    while (true) {
+        if (m) return w * 32 + 31 - __clz(m);
+        if (--w < 0) return -1;
+        m = bm[w];
+    }
+}
+__device__ __forceinline__ int64_t next_valid(const uint32_t *bm, int64_t i, int64_t n) {  // first valid row >= i
+    if (i >= n) return -1;
+    if (!bm) return i;
+    const int64_t nw = (n + 31) >> 5;
+    int64_t w = i >> 5;
+    uint32_t m = bm[w] & (0xFFFFFFFFu << (int)(i & 31));
+    while (true) {
+        if (m) {
+            const int64_t r = w * 32 + __ffs(m) - 1;
+            return r < n ? r : -1;
+        }
+        if (++w >= nw) return -1;
+        m = bm[w];
+    }
+}
+
+__global__ void interp_window_kernel(const InterpLaunch P) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const WindowGeom &g = P.g;
+    if (k >= g.W) return;
+    const int64_t *t = P.time;
+    const uint64_t d = g.div.d;
+    const int64_t Sk = (int64_t)((uint64_t)g.s0 + (uint64_t)k * d);
+    int64_t lo = P.first[k];
+    const int64_t b = P.first[k + 1];
+    bool inc = false;  // Window.IsInclusive, rolling.go:201-209
+    if (P.inclusive && b < g.n && b >= g.early_rows) inc = ((uint64_t)t[b] - (uint64_t)g.s0) == ((uint64_t)k + 1) * d;
+    int64_t hi = b + (inc ? 1 : 0);
+    if (k == 0 && g.early_rows > 0 && !g.early_keep) lo = hi = 0;  // rows before s0 dropped with an empty window 0
+    const int64_t first_index = lo;
+    // interpolation.go:119-128: the comparison goes through float64
+    const int64_t fcv = hi > lo ? f64_to_i64_go((double)t[lo]) : -1;
+    const int missing = fcv != Sk;
+    P.off[k] = (int64_t)missing + (hi - lo);
+    P.wsrc[k] = (lo - missing) * 2 + missing;  // fixed up to "source row - output row" after the scan
+    if (!missing) return;
+    for (int j = 0; j < P.ncols; ++j) {
+        const InterpCol &c = P.cols[j];
+        uint64_t bits = 0;
+        bool valid = false;
+        switch (c.op) {
+        case BOWGPU_INTERP_WINDOW_START:  // interpolation/windowstart.go:8-14
+            bits = (uint64_t)Sk;
+            valid = true;
+            break;
+        case BOWGPU_INTERP_NONE:  // interpolation/none.go:8-14
+            break;
+        case BOWGPU_INTERP_STEP_PREVIOUS: {  // interpolation/stepprevious.go:8-26
+            const int64_t p = prev_valid(c.validity, first_index - 1);
+            if (p >= 0) {
+                bits = c.values[p];
+                valid = true;
+            } else if (c.prev_valid) {
+                bits = c.prev_bits;
+                valid = true;
+            }
+            break;
+        }
+        case BOWGPU_INTERP_LINEAR: {  // interpolation/linear.go:8-38
+            double t0, v0;
+            const int64_t p = prev_valid(c.validity, first_index - 1);
+            if (p >= 0) {
+                t0 = (double)t[p];
+                v0 = c.is_int ? (double)(int64_t)c.values[p] : bits_as_f64(c.values[p]);
+            } else if (c.prev_valid && P.prev_time_valid) {
+                t0 = (double)P.prev_time;
+                v0 = c.is_int ? (double)(int64_t)c.prev_bits : bits_as_f64(c.prev_bits);
+            } else {
+                break;
+            }
+            const int64_t nx = next_valid(c.validity, first_index, g.n);
+            if (nx < 0) break;
+            const double t2 = (double)t[nx];
+            const double v2 = c.is_int ? (double)(int64_t)c.values[nx] : bits_as_f64(c.values[nx]);
+            const double coef = __ddiv_rn(__dsub_rn((double)Sk, t0), __dsub_rn(t2, t0));  // linear.go:34
+            const double res = __dadd_rn(__dmul_rn(__dsub_rn(v2, v0), coef), v0);          // linear.go:35
+            bits = c.is_int ? (uint64_t)f64_to_i64_go(res) : f64_as_bits(res);  // SetOrDrop into the column type
+            valid = true;
+            break;
+        }
+        }
+        c.syn_val[k] = valid ? bits : 0;
+        c.syn_ok[k] = valid;
+    }
+}
+
+// ---- exclusive scan of int64 counts, in place; data[n] receives the total ---------------------------------
+constexpr int SCAN_NT = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_NT * SCAN_ITEMS;
+
+__device__ __forceinline__ int64_t block_exclusive_scan(int64_t v, int64_t *sh /*[32+1]*/, int64_t &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int64_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int64_t u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) sh[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int64_t w = lane < (int)(blockDim.x >> 5) ? sh[lane] : 0;
+        int64_t wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t u = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += u;
+        }
+        sh[lane] = wi - w;
+        if (lane == 31) sh[32] = wi;
+    }
+    __syncthreads();
+    const int64_t res = sh[warp] + incl - v;
+    total = sh[32];
+    __syncthreads();
+    return res;
+}
+
+__global__ void scan_block_sums(const int64_t *data, int64_t n, int64_t *bsum) {
+    __shared__ int64_t sh[33];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    int64_t s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i)
+        if (base + i < n) s += data[base + i];
+    int64_t total;
+    block_exclusive_scan(s, sh, total);
+    if (threadIdx.x == 0) bsum[blockIdx.x] = total;
+}
+
+__global__ void scan_partials(int64_t *bsum, int64_t nb) {  // one block
+    __shared__ int64_t sh[33];
+    int64_t carry = 0;
+    for (int64_t base = 0; base < nb; base += blockDim.x) {
+        const int64_t i = base + threadIdx.x;
+        const int64_t v = i < nb ? bsum[i] : 0;
+        int64_t total;
+        const int64_t ex = block_exclusive_scan(v, sh, total);
+        if (i < nb) bsum[i] = carry + ex;
+        carry += total;
+    }
+}
+
+__global__ void scan_apply(int64_t *data, int64_t n, const int64_t *bsum) {
+    __shared__ int64_t sh[33];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    int64_t v[SCAN_ITEMS];
+    int64_t s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        v[i] = base + i < n ? data[base + i] : 0;
+        s += v[i];
+    }
+    int64_t total;
+    int64_t run = block_exclusive_scan(s, sh, total) + bsum[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        if (base + i < n) data[base + i] = run;
+        run += v[i];
+        if (base + i == n - 1) data[n] = run;
+    }
+}
+
+// after the scan: wsrc[k] = ((source row of the window's first copied row - its output row) << 1) | missing
+__global__ void interp_fix_wsrc(const int64_t *off, int64_t *wsrc, int64_t W) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= W) return;
+    const int64_t v = wsrc[k];
+    const int64_t missing = v & 1;
+    wsrc[k] = ((v >> 1) - off[k]) * 2 + missing;
+}
+
+// ---- gather -----------------------------------------------------------------------------------------------
+constexpr int GA_NT = 256, GA_ROWS = 8, GA_TILE = GA_NT * GA_ROWS;  // output rows per CTA iteration
+constexpr int GA_CAP = GA_TILE + 4;                                   // windows overlapping one tile
+
+__device__ __forceinline__ int64_t upper_bound_minus1(const int64_t *off, int64_t lo, int64_t hi, int64_t o) {
+    // last k in [lo, hi) with off[k] <= o   (off[lo] <= o is guaranteed by the caller)
+    while (hi - lo > 1) {
+        const int64_t mid = lo + ((hi - lo) >> 1);
+        if (off[mid] <= o)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(GA_NT) interp_gather_kernel(const InterpLaunch P, const int64_t n_out,
+                                                               const int64_t ntiles) {
+    __shared__ int64_t s_off[GA_CAP];
+    __shared__ int64_t s_src[GA_CAP];
+    __shared__ int64_t s_k[2];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int64_t W = P.g.W;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t o0 = tile * GA_TILE;
+        const int64_t o1 = o0 + GA_TILE < n_out ? o0 + GA_TILE : n_out;
+        if (tid < 2) s_k[tid] = upper_bound_minus1(P.off, 0, W, tid == 0 ? o0 : o1 - 1);
+        __syncthreads();
+        const int64_t k_lo = s_k[0], k_hi = s_k[1];
+        // m <= GA_TILE + 2: every window but one (an empty window starting at -1, interpolation.go:119,128)
+        // emits at least one row; clamp anyway so shared memory can never be overrun
+        int m = (int)((k_hi - k_lo + 1) < (int64_t)GA_CAP ? (k_hi - k_lo + 1) : (int64_t)GA_CAP);
+        for (int i = tid; i < m; i += GA_NT) {
+            s_off[i] = P.off[k_lo + i];
+            s_src[i] = P.wsrc[k_lo + i];
+        }
+        __syncthreads();
+        int64_t src[GA_ROWS];  // >= 0: input row; -1 - k: synthetic row of window k; INT64_MIN: past the end
+#pragma unroll
+        for (int i = 0; i < GA_ROWS; ++i) {
+            const int64_t o = o0 + tid + (int64_t)i * GA_NT;
+            src[i] = INT64_MIN;
+            if (o < n_out) {
+                int lo = 0, hi = m;
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_off[mid] <= o)
+                        lo = mid;
+                    else
+                        hi = mid;
+                }
+                const int64_t v = s_src[lo];
+                src[i] = ((v & 1) && o == s_off[lo]) ? -1 - (k_lo + lo) : o + (v >> 1);
+            }
+        }
+        for (int j = 0; j < P.ncols; ++j) {
+            const InterpCol &c = P.cols[j];
+            uint64_t val[GA_ROWS];
+            bool ok[GA_ROWS];
+#pragma unroll
+            for (int i = 0; i < GA_ROWS; ++i) {
+                const int64_t s = src[i];
+                val[i] = 0;
+                ok[i] = false;
+                if (s >= 0) {
+                    val[i] = c.values[s];
+                    ok[i] = c.validity ? ((c.validity[s >> 5] >> (s & 31)) & 1u) : true;
+                } else if (s != INT64_MIN) {
+                    const int64_t k = -1 - s;
+                    val[i] = c.syn_val[k];
+                    ok[i] = c.syn_ok[k] != 0;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < GA_ROWS; ++i) {
+                const int64_t o = o0 + tid + (int64_t)i * GA_NT;
+                if (o < n_out) c.out_values[o] = val[i];
+                if (c.out_validity) {
+                    const uint32_t ball = __ballot_sync(0xffffffffu, ok[i]);
+                    if (lane == 0 && o < n_out) c.out_validity[o >> 5] = ball;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+int launch_interp_windows(const InterpLaunch &L, cudaStream_t stream) {
+    if (L.g.W <= 0) return 0;
+    const int nt = 128;
+    interp_window_kernel<<<(unsigned)((L.g.W + nt - 1) / nt), nt, 0, stream>>>(L);
+    return (int)cudaGetLastError();
+}
+
+size_t scan_scratch_bytes(int64_t n) { return (size_t)((n + SCAN_TILE - 1) / SCAN_TILE + 1) * 8; }
+
+int launch_exclusive_scan(int64_t *data, int64_t n, int64_t *scratch, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    const int64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+    scan_block_sums<<<(unsigned)nb, SCAN_NT, 0, stream>>>(data, n, scratch);
+    scan_partials<<<1, 1024, 0, stream>>>(scratch, nb);
+    scan_apply<<<(unsigned)nb, SCAN_NT, 0, stream>>>(data, n, scratch);
+    return (int)cudaGetLastError();
+}
+
+int launch_interp_gather(const InterpLaunch &L, int64_t n_out, int sm_count, cudaStream_t stream, cudaEvent_t e0,
+                         cudaEvent_t e1) {
+    if (L.g.W > 0) {
+        const int nt = 256;
+        interp_fix_wsrc<<<(unsigned)((L.g.W + nt - 1) / nt), nt, 0, stream>>>(L.off, L.wsrc, L.g.W);
+    }
+    if (n_out <= 0) return (int)cudaGetLastError();
+    const int64_t ntiles = (n_out + GA_TILE - 1) / GA_TILE;
+    int64_t grid = (int64_t)sm_count * 4;
+    if (grid > ntiles) grid = ntiles;
+    if (e0) cudaEventRecord(e0, stream);
+    interp_gather_kernel<<<(unsigned)grid, GA_NT, 0, stream>>>(L, n_out, ntiles);
+    if (e1) cudaEventRecord(e1, stream);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace bowgpu

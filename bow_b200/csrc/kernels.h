@@ -98,6 +98,41 @@ int launch_bounds(const BoundsLaunch &L, int sm_count, cudaStream_t stream, cuda
 int launch_inclusive_bitmap(const int64_t *time, const int64_t *first, WindowGeom g, uint8_t *bitmap,
                             cudaStream_t stream);
 
+// ---- interpolate (interp.cu) ------------------------------------------------------------------------
+constexpr int INTERP_MAX_COLS = 32;
+struct InterpCol {
+    const uint64_t *values;    // input column
+    const uint32_t *validity;  // input validity (bit offset 0) or null
+    uint64_t *syn_val;         // [W] value of the synthetic window-start row (scratch)
+    uint8_t *syn_ok;           // [W] its validity
+    uint64_t *out_values;      // [n_out]
+    uint32_t *out_validity;    // [ceil(n_out/32)] words or null
+    uint64_t prev_bits;        // Options.PrevRow cell of this column
+    int32_t prev_valid;
+    int32_t op;                // BOWGPU_INTERP_*
+    int32_t is_int;
+    int32_t _pad;
+};
+struct InterpLaunch {
+    const int64_t *time;
+    const int64_t *first;  // [W+1] from the bounds kernel
+    int64_t *off;          // [W+1] output rows per window, scanned in place to output offsets
+    int64_t *wsrc;         // [W]
+    WindowGeom g;
+    int64_t prev_time;     // Options.PrevRow time cell
+    int32_t prev_time_valid;
+    int32_t inclusive;
+    int32_t ncols;
+    int32_t _pad;
+    InterpCol cols[INTERP_MAX_COLS];
+};
+int launch_interp_windows(const InterpLaunch &L, cudaStream_t stream);
+size_t scan_scratch_bytes(int64_t n);
+// exclusive scan in place; data[n] receives the total
+int launch_exclusive_scan(int64_t *data, int64_t n, int64_t *scratch, cudaStream_t stream);
+int launch_interp_gather(const InterpLaunch &L, int64_t n_out, int sm_count, cudaStream_t stream, cudaEvent_t e0,
+                         cudaEvent_t e1);
+
 // ---- per-window epilogue (validity bitmaps, defaults of empty windows, WindowStart, Factor) -----
 struct EpilogueSpec {
     int32_t op;          // BOWGPU_AGG_*

@@ -1,0 +1,132 @@
+"""Parity of Rolling.Interpolate on the GPU (through the C ABI) against the oracle: row placement,
+values and validity of every output row.  Bit-exact (WindowStart / StepPrevious / None / copied rows;
+Linear evaluates the reference's five float64 operations in the same order without FMA, so it is
+bit-exact too; the stated tolerance for Linear is 1e-12 relative)."""
+import numpy as np
+import pytest
+
+from oracle import literal as L
+from oracle import refc as R
+from tests import helpers as H
+from tests.golden import reference_vectors as G
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from bow_b200 import native as N
+    c = N.Ctx(0)
+    yield c
+    c.close()
+
+
+def bits(a):
+    a = np.asarray(a)
+    return a.view(np.int64) if a.dtype == np.float64 else a
+
+
+def assert_frames_equal(got, want, what=""):
+    assert len(got) == len(want)
+    for j, ((gv, gm), (wv, wm)) in enumerate(zip(got, want)):
+        assert len(gv) == len(wv), (what, j, len(gv), len(wv))
+        assert gv.dtype == wv.dtype, (what, j)
+        assert np.array_equal(gm, wm), f"{what} col {j}: validity differs at {np.flatnonzero(gm != wm)[:10]}"
+        bad = np.flatnonzero((bits(gv) != bits(wv)) & gm)
+        if gv.dtype == np.float64:
+            bad = bad[~(np.isnan(gv[bad]) & np.isnan(wv[bad]))]
+        assert bad.size == 0, f"{what} col {j}: rows {bad[:10]} got {gv[bad[:10]]} want {wv[bad[:10]]}"
+
+
+@pytest.mark.parametrize("name,kind,rows,offset,expected,cite", G.INTERPOLATIONS, ids=[c[0] for c in G.INTERPOLATIONS])
+def test_golden_interpolations(ctx, name, kind, rows, offset, expected, cite):
+    from bow_b200 import native as N
+    cols = H.np_cols_from_lists([[r[0] for r in rows], [r[1] for r in rows]], [L.INT64, L.FLOAT64])
+    fr = N.Frame.from_numpy(ctx, cols)
+    r = N.Rolling(fr, 0, 2, offset=offset)
+    out = H.lists_from_np(r.interpolate(["WindowStart", "None_" if kind == "None" else kind]).download())
+    H.assert_cols_equal(out, [[r[0] for r in expected], [r[1] for r in expected]], cite)
+
+
+@pytest.mark.parametrize("name,times,offset,expected", G.INTERP_WINDOWSTART, ids=[c[0] for c in G.INTERP_WINDOWSTART])
+def test_golden_interp_windowstart(ctx, name, times, offset, expected):
+    from bow_b200 import native as N
+    fr = N.Frame.from_numpy(ctx, H.np_cols_from_lists([times], [L.INT64]))
+    r = N.Rolling(fr, 0, 2, offset=offset)
+    H.assert_cols_equal(H.lists_from_np(r.interpolate(["WindowStart"]).download()), [expected])
+
+
+ICASES = [(k, n) for k in ("regular", "dense", "sparse", "bursty") for n in (1, 2, 31, 33, 300, 2047, 2049, 4100, 30011)]
+
+
+@pytest.mark.parametrize("kind,n", ICASES, ids=[f"{k}-{n}" for k, n in ICASES])
+def test_random_interpolate_vs_oracle(ctx, kind, n):
+    from bow_b200 import native as N
+    rng = np.random.default_rng(hash((kind, n, "interp")) & 0xFFFF)
+    for trial in range(5):
+        t = H.random_times(rng, n, kind)
+        a = H.random_values(rng, n, np.float64, [0.0, 0.3, 0.1, 0.9, 0.5][trial])
+        b = H.random_values(rng, n, np.int64, [0.2, 0.0, 0.6, 0.0, 0.97][trial])
+        c = H.random_values(rng, n, np.float64, 0.4)
+        cols = [a, (t, None), b, c]           # interval column in the middle
+        ops = ["Linear", "WindowStart", ["StepPrevious", "Linear"][trial % 2], ["None_", "StepPrevious"][trial % 2]]
+        interval = int(rng.choice([1, 2, 5, 10, 60, 1000]))
+        offset = int(rng.integers(-2 * interval, 2 * interval))
+        inclusive = trial == 3
+        prev = None
+        if trial in (1, 4):
+            prev = [(np.array([1.5]), np.array([trial == 1])), (np.array([int(t[0]) - 3], dtype=np.int64), None),
+                    (np.array([7], dtype=np.int64), None), (np.array([-2.0]), np.array([True]))]
+        so = int(rng.integers(0, 70)) if trial == 2 else 0
+        fr = N.Frame.from_numpy(ctx, cols, offset=so)
+        r = N.Rolling(fr, 1, interval, offset=offset, inclusive=inclusive, prev_row=prev)
+        got = r.interpolate(ops).download()
+        ref = R.RefRolling(R.Frame(cols), 1, interval, offset=offset, inclusive=inclusive,
+                           prev_row=R.Frame(prev) if prev else None)
+        want = ref.interpolate(ops)
+        assert_frames_equal(got, want, f"{kind} n={n} I={interval} off={offset} inc={inclusive} trial={trial}")
+
+
+def test_interpolate_then_aggregate(ctx):
+    """the reference's usual chain: Interpolate(WindowStart, Linear) then WeightedAverageLinear / IntegralTrapezoid"""
+    from bow_b200 import native as N
+    rng = np.random.default_rng(11)
+    n = 40000
+    t = np.cumsum(rng.integers(1, 9, size=n)).astype(np.int64) + 1000
+    v = H.random_values(rng, n, np.float64, 0.1)
+    w = H.random_values(rng, n, np.int64, 0.0)
+    cols = [(t, None), v, w]
+    fr = N.Frame.from_numpy(ctx, cols)
+    r = N.Rolling(fr, 0, 250, offset=70)
+    fi = r.interpolate(["WindowStart", "Linear", "Linear"])
+    r2 = N.Rolling(fi, 0, 250, offset=70)
+    specs = [("WindowStart", 0), ("WeightedAverageLinear", 1), ("IntegralTrapezoid", 1), ("WeightedAverageStep", 2),
+             ("Count", 1), ("ArithmeticMean", 2)]
+    got = r2.aggregate(specs)
+    ref = R.RefRolling(R.Frame(cols), 0, 250, offset=70)
+    icols = ref.interpolate(["WindowStart", "Linear", "Linear"])
+    icols = [(vv, None if mm.all() else mm) for vv, mm in icols]
+    assert_frames_equal(fi.download(), [(vv, np.ones(len(vv), bool) if mm is None else mm) for vv, mm in icols], "interp")
+    want = R.RefRolling(R.Frame(icols), 0, 250, offset=70).aggregate(specs)
+    for j, sp in enumerate(specs):
+        (gv, gm), (wv, wm) = got[j], want[j]
+        assert np.array_equal(gm, wm), sp
+        if gv.dtype == np.int64:
+            assert np.array_equal(gv, wv), sp
+        else:
+            assert np.allclose(gv, wv, rtol=1e-12, atol=1e-9 if sp[0].startswith("Integral") else 1e-12), sp
+
+
+def test_interpolate_errors_and_empty(ctx):
+    from bow_b200 import native as N
+    t = np.array([1, 2, 3], dtype=np.int64)
+    v = np.array([1.0, 2.0, 3.0])
+    fr = N.Frame.from_numpy(ctx, [(t, None), (v, None)])
+    r = N.Rolling(fr, 0, 2)
+    with pytest.raises(N.BowGpuError, match="ETYPE"):
+        r.interpolate(["WindowStart", "WindowStart"])
+    with pytest.raises(N.BowGpuError, match="EINVAL"):
+        r.interpolate(["WindowStart"])
+    fe = N.Frame.from_numpy(ctx, [(np.zeros(0, dtype=np.int64), None), (np.zeros(0), None)])
+    out = N.Rolling(fe, 0, 2).interpolate(["WindowStart", "Linear"])
+    assert out.num_rows == 0 and out.num_cols == 2
