@@ -1,0 +1,191 @@
+"""Minimal host-side `bow.Bow` for the interval-rolling path: a thin wrapper over an Arrow record
+batch, exactly like the reference's `type bow struct{ arrow.Record }` (reference bow.go:96-98).
+
+Only what the rolling path and its tests touch is mirrored (constructors from column / row based
+data, schema accessors, zero-copy slicing, Equal).  Everything else of the reference's Bow surface
+(joins, fills, parquet ...) is out of scope.  Only Int64 and Float64 columns can be
+sent to the GPU; Boolean / String columns may exist in a Bow but cannot take part in a rolling call.
+"""
+from __future__ import annotations
+
+import enum
+from typing import Any, List, Optional, Sequence
+
+import numpy as np
+import pyarrow as pa
+
+
+class BowError(Exception):
+    """Carries the reference's error strings (Go `error` values)."""
+
+
+class Type(enum.IntEnum):  # bowtypes.go:17-32
+    Unknown = 0
+    Float64 = 1
+    Int64 = 2
+    Boolean = 3
+    String = 4
+    InputDependent = 5
+    IteratorDependent = 6
+
+    def __str__(self) -> str:  # Type.String(), used by "%v" in the reference's error messages
+        return {0: "undefined", 1: "float64", 2: "int64", 3: "bool", 4: "utf8"}.get(int(self), self.name)
+
+
+Unknown, Float64, Int64, Boolean, String = Type.Unknown, Type.Float64, Type.Int64, Type.Boolean, Type.String
+InputDependent, IteratorDependent = Type.InputDependent, Type.IteratorDependent
+
+_TO_ARROW = {Type.Float64: pa.float64(), Type.Int64: pa.int64(), Type.Boolean: pa.bool_(), Type.String: pa.string()}
+
+
+def _from_arrow(t: pa.DataType) -> Type:
+    for k, v in _TO_ARROW.items():
+        if v == t:
+            return k
+    return Type.Unknown
+
+
+class Series:
+    """bow.Series (bowseries.go:14-25): a named Arrow array."""
+
+    def __init__(self, name: str, array: pa.Array):
+        self.Name, self.Array = name, array
+
+
+def NewSeries(name: str, typ: Type, data: Sequence, valid: Optional[Sequence[bool]] = None) -> Series:
+    """bowseries.go:27-30"""
+    mask = None if valid is None else ~np.asarray(valid, dtype=bool)
+    arr = pa.array(list(data) if not isinstance(data, np.ndarray) else data, type=_TO_ARROW[typ],
+                   mask=mask, from_pandas=False)
+    return Series(name, arr)
+
+
+def NewSeriesFromNumpy(name: str, values: np.ndarray, valid: Optional[np.ndarray] = None) -> Series:
+    """Zero-copy wrap of a numpy int64 / float64 buffer (+ optional bool validity), the analogue of
+    bow.NewSeriesFromBuffer (bowseries.go:32-34)."""
+    values = np.ascontiguousarray(values)
+    assert values.dtype in (np.int64, np.float64)
+    bufs = [None, pa.py_buffer(values)]
+    nulls = 0
+    if valid is not None:
+        valid = np.asarray(valid, dtype=bool)
+        nulls = int(len(valid) - np.count_nonzero(valid))
+        if nulls:
+            bufs[0] = pa.py_buffer(np.packbits(valid, bitorder="little"))
+    typ = pa.int64() if values.dtype == np.int64 else pa.float64()
+    return Series(name, pa.Array.from_buffers(typ, len(values), bufs, null_count=nulls))
+
+
+class Bow:
+    def __init__(self, record: pa.RecordBatch):
+        self.Record = record
+
+    # -- schema -------------------------------------------------------------------------------------
+    def NumRows(self) -> int:
+        return self.Record.num_rows
+
+    def NumCols(self) -> int:
+        return self.Record.num_columns
+
+    def ColumnName(self, i: int) -> str:
+        return self.Record.schema.field(i).name
+
+    def ColumnType(self, i: int) -> Type:
+        return _from_arrow(self.Record.schema.field(i).type)
+
+    def ColumnIndex(self, name: str) -> int:  # bowgetters.go:318-331
+        idx = [i for i, f in enumerate(self.Record.schema) if f.name == name]
+        if not idx:
+            raise BowError(f"no column '{name}'")
+        if len(idx) > 1:
+            raise BowError(f"several columns '{name}'")
+        return idx[0]
+
+    def Column(self, i: int) -> pa.Array:
+        return self.Record.column(i)
+
+    def Metadata(self) -> dict:
+        return dict(self.Record.schema.metadata or {})
+
+    # -- cells / slices -------------------------------------------------------------------------------
+    def GetValue(self, col: int, row: int) -> Any:  # bowgetters.go:46-63
+        return self.Record.column(col)[row].as_py()
+
+    def NewSlice(self, i: int, j: int) -> "Bow":  # bow.go:279-283 (zero copy)
+        return Bow(self.Record.slice(i, j - i))
+
+    def NewEmptySlice(self) -> "Bow":
+        return Bow(self.Record.slice(0, 0))
+
+    def ToColBased(self) -> List[list]:
+        return [self.Record.column(i).to_pylist() for i in range(self.NumCols())]
+
+    # -- comparator of the reference's tests (bow.go:227-275) --------------------------------------------
+    def Equal(self, other: "Bow") -> bool:
+        a, b = self.Record, other.Record
+        if a.schema.names != b.schema.names or [f.type for f in a.schema] != [f.type for f in b.schema]:
+            return False
+        if (a.schema.metadata or {}) != (b.schema.metadata or {}):
+            return False
+
+        def rows(r):  # rows whose every cell is null are skipped (bow.go:257-262)
+            cols = [r.column(i).to_pylist() for i in range(r.num_columns)]
+            out = []
+            for i in range(r.num_rows):
+                row = {r.schema.field(j).name: cols[j][i] for j in range(r.num_columns) if cols[j][i] is not None}
+                if row:
+                    out.append(row)
+            return out
+
+        ra, rb = rows(a), rows(b)
+        if len(ra) != len(rb):
+            return False
+        for x, y in zip(ra, rb):
+            if x.keys() != y.keys():
+                return False
+            for k in x:
+                u, v = x[k], y[k]
+                if isinstance(u, float) and isinstance(v, float) and u != u and v != v:
+                    continue
+                if u != v or type(u) is not type(v):
+                    return False
+        return True
+
+    def __str__(self) -> str:
+        return self.Record.to_pandas().to_string() if self.NumRows() else f"<empty Bow {self.Record.schema.names}>"
+
+
+def NewBow(*series: Series) -> Bow:
+    """bow.go:109-116: fresh schema, no metadata, every field nullable (bowrecord.go:36-40)"""
+    names = [s.Name for s in series]
+    arrays = [s.Array for s in series]
+    n = {len(a) for a in arrays}
+    if len(n) > 1:
+        raise BowError("bow.NewBow: series have different lengths")
+    return Bow(pa.RecordBatch.from_arrays(arrays, names=names))
+
+
+def NewBowFromColBasedInterfaces(colNames: Sequence[str], colTypes: Sequence[Type], colBasedData: Sequence[Sequence]) -> Bow:
+    """bow.go:125-148"""
+    if len(colNames) != len(colTypes) or len(colNames) != len(colBasedData):
+        raise BowError("bow.NewBowFromColBasedInterfaces: mismatch between colNames, colTypes and colBasedData lengths")
+    series = []
+    for name, typ, data in zip(colNames, colTypes, colBasedData):
+        conv = []
+        for v in data:
+            if v is None:
+                conv.append(None)
+            elif typ == Type.Float64:
+                conv.append(float(v))
+            elif typ == Type.Int64:
+                conv.append(int(v))
+            else:
+                conv.append(v)
+        series.append(Series(name, pa.array(conv, type=_TO_ARROW[typ])))
+    return NewBow(*series)
+
+
+def NewBowFromRowBasedInterfaces(colNames: Sequence[str], colTypes: Sequence[Type], rows: Sequence[Sequence]) -> Bow:
+    """bow.go:150-170"""
+    cols = [[r[j] for r in rows] for j in range(len(colNames))]
+    return NewBowFromColBasedInterfaces(colNames, colTypes, cols)

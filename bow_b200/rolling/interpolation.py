@@ -1,0 +1,25 @@
+"""rolling/interpolation: the built-in ColInterpolation constructors (reference rolling/interpolation/*.go).
+`None` is spelled `None_` (Python keyword).  The north-star's `StepNext` does not exist upstream
+ and is not provided: its parity would be unpinned."""
+from __future__ import annotations
+
+from .. import bow as B
+from .. import native as N
+from . import ColInterpolation
+
+
+def WindowStart(colName: str) -> ColInterpolation:     # windowstart.go:8-14
+    return ColInterpolation(colName, [B.Int64], None, kernel_op=N.INTERP["WindowStart"])
+
+
+def Linear(colName: str) -> ColInterpolation:          # linear.go:8-38
+    return ColInterpolation(colName, [B.Int64, B.Float64], None, kernel_op=N.INTERP["Linear"])
+
+
+def StepPrevious(colName: str) -> ColInterpolation:    # stepprevious.go:8-26
+    return ColInterpolation(colName, [B.Int64, B.Float64, B.Boolean, B.String], None,
+                            kernel_op=N.INTERP["StepPrevious"])
+
+
+def None_(colName: str) -> ColInterpolation:           # none.go:8-14
+    return ColInterpolation(colName, [B.Int64, B.Float64, B.Boolean, B.String], None, kernel_op=N.INTERP["None_"])
