@@ -250,3 +250,31 @@ def test_errors(ctx):
     r4 = N.Rolling(fr4, 0, 10)
     assert r4.num_windows == 0
     assert r4.aggregate([("WindowStart", 0), ("Sum", 1)])[0][0].size == 0
+
+
+@pytest.mark.parametrize("g", [2, 5])
+def test_sharded_matches_oracle(ctx, g):
+    """range-partitioned execution (bowgpu_rolling_create_shard): every shard runs on this GPU, the
+    concatenation must equal the unsharded oracle"""
+    from bow_b200 import parallel as PP
+    from bow_b200 import runtime
+    runtime.set_default_ctx(ctx)
+    rng = np.random.default_rng(21 + g)
+    specs = [("WindowStart", 0)] + [(a, 1) for a in BASIC[1:]] + [(a, 1) for a in INTEGRALS]
+    for kind, n, interval in (("regular", 50000, 37), ("bursty", 40000, 500), ("sparse", 9000, 3)):
+        t = H.random_times(rng, n, kind)
+        t = t - int(t[0]) + 7
+        v = H.random_values(rng, n, np.float64, 0.25)
+        cols = [(t, None), v]
+        inclusive = bool(rng.integers(0, 2))
+        shards, s0 = PP.plan_for_columns(t, interval, 3, g)
+        per = [PP.aggregate_shard(cols, s, 0, interval, s0, inclusive, specs) for s in shards]
+        got = PP.concat_outputs(per)
+        want = R.RefRolling(R.Frame(cols), 0, interval, offset=3, inclusive=inclusive).aggregate(specs)
+        for sp, (gv, gm), (wv, wm) in zip(specs, got, want):
+            assert np.array_equal(gm, wm), (kind, sp)
+            if sp[0] in EXACT:
+                assert np.array_equal(bits(gv), bits(wv)), (kind, sp)
+            else:
+                assert np.allclose(gv, wv, rtol=1e-11, atol=1e-9), (kind, sp)
+    runtime.set_default_ctx(None)

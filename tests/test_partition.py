@@ -1,0 +1,143 @@
+"""Host-side sharding logic of the multi-GPU path (bow_b200.partition / bow_b200.parallel) on CPU:
+planner invariants, and a world_size-2 gloo run in which every rank aggregates its shard and rank 0
+concatenates — with the ORACLE injected as the per-shard executor (there is no GPU here; the executor is a
+test double, the planner / halo / lattice pinning / gather logic is the code under test)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from bow_b200 import parallel as PP
+from bow_b200 import partition as P
+from oracle import refc as R
+from tests import helpers as H
+
+SPECS = [("WindowStart", 0), ("Count", 1), ("Sum", 1), ("ArithmeticMean", 1), ("Min", 1), ("Max", 1), ("First", 1),
+         ("Last", 1), ("IntegralStep", 1), ("IntegralTrapezoid", 1), ("WeightedAverageLinear", 1)]
+
+
+def oracle_executor(cols, time_col, interval, s0, num_windows, inclusive, specs):
+    """Shard executor backed by the oracle: runs it on the shard's rows and re-indexes its windows onto the
+    pinned lattice (s0, num_windows); windows without rows get the empty-window defaults."""
+    outs = []
+    n = len(cols[0][0])
+    ref_out, k_off, wl = None, 0, 0
+    if n:
+        t = cols[time_col][0]
+        assert int(t[0]) >= s0
+        ref = R.RefRolling(R.Frame(cols), time_col, interval, offset=s0 % interval, inclusive=inclusive)
+        assert (ref.first_window_start - s0) % interval == 0
+        k_off = (ref.first_window_start - s0) // interval
+        ref_out = ref.aggregate(specs)
+        wl = ref.num_windows
+    for j, sp in enumerate(specs):
+        op = sp[0]
+        dt = np.int64 if op in ("WindowStart", "Count") or (op in ("First", "Last") and cols[sp[1]][0].dtype == np.int64) \
+            else np.float64
+        v = np.zeros(num_windows, dtype=dt)
+        m = np.zeros(num_windows, dtype=bool)
+        if op == "WindowStart":
+            v[:] = s0 + np.arange(num_windows, dtype=np.int64) * interval
+            m[:] = True
+        elif op in ("Count", "Sum"):
+            m[:] = True
+        if ref_out is not None:
+            take = max(0, min(wl, num_windows - k_off))
+            v[k_off:k_off + take] = ref_out[j][0][:take]
+            m[k_off:k_off + take] = ref_out[j][1][:take]
+        outs.append((v, m))
+    return outs
+
+
+def check_plan(shards, n, W):
+    assert shards[0].k_lo == 0 and shards[0].row_lo == 0
+    assert shards[-1].k_hi == W and shards[-1].row_hi == n
+    for a, b in zip(shards, shards[1:]):
+        assert a.k_hi == b.k_lo and a.row_hi == b.row_lo          # disjoint, contiguous
+        assert a.k_hi % 64 == 0 or a.k_hi in (0, W)               # bitmaps concatenate byte aligned
+        assert a.row_hi <= a.halo_hi <= a.row_hi + 1
+
+
+@pytest.mark.parametrize("kind", ["regular", "dense", "sparse", "bursty"])
+@pytest.mark.parametrize("g", [1, 2, 3, 8])
+def test_plan_and_concat_matches_unsharded(kind, g):
+    rng = np.random.default_rng(hash((kind, g)) & 0xFFFF)
+    for n, interval in ((0, 5), (1, 5), (50, 3), (5000, 7), (20000, 2), (20000, 400)):
+        t = H.random_times(rng, n, kind)
+        if n:
+            t = t - int(t[0]) + 1000      # non-negative times (negative ones need the single-shard early-row path)
+        v = H.random_values(rng, n, np.float64, 0.2)
+        cols = [(t, None), v]
+        offset = int(rng.integers(-interval, interval))
+        inclusive = bool(rng.integers(0, 2))
+        shards, s0 = PP.plan_for_columns(t, interval, offset, g)
+        ref = R.RefRolling(R.Frame(cols), 0, interval, offset=offset, inclusive=inclusive)
+        W = ref.num_windows
+        check_plan(shards, n, W)
+        assert sum(s.num_windows for s in shards) == W
+        if n == 0:
+            continue
+        assert s0 == ref.first_window_start
+        per = [PP.aggregate_shard(cols, s, 0, interval, s0, inclusive, SPECS, executor=oracle_executor) for s in shards]
+        got = PP.concat_outputs(per)
+        want = ref.aggregate(SPECS)
+        for sp, (gv, gm), (wv, wm) in zip(SPECS, got, want):
+            assert np.array_equal(gm, wm), (kind, g, n, interval, sp)
+            assert np.array_equal(gv[gm].view(np.int64), wv[wm].view(np.int64)), (kind, g, n, interval, sp)
+
+
+def test_regular_lower_bound():
+    lb = P.regular_lower_bound(1000, 10, 50)
+    t = 1000 + np.arange(50) * 10
+    for x in (0, 999, 1000, 1001, 1005, 1010, 1489, 1490, 1491, 99999):
+        assert lb(x) == int(np.searchsorted(t, x, side="left"))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(5)          # every rank regenerates the same global series
+        n, interval, offset = 30000, 11, 4
+        t = (np.cumsum(rng.integers(0, 6, size=n)) + 100).astype(np.int64)
+        v = (rng.normal(size=n), rng.random(n) > 0.15)
+        cols = [(t, None), v]
+        shards, s0 = PP.plan_for_columns(t, interval, offset, world)
+        local = PP.slice_cols(cols, shards[rank].row_lo, shards[rank].halo_hi)     # a rank only holds its rows
+        out = PP.aggregate_shard(local, shards[rank], 0, interval, s0, True, SPECS, executor=oracle_executor)
+        full = PP.gather_outputs(out, dst=0)
+        if rank == 0:
+            want = R.RefRolling(R.Frame(cols), 0, interval, offset=offset, inclusive=True).aggregate(SPECS)
+            ok = all(np.array_equal(gm, wm) and np.array_equal(gv[gm].view(np.int64), wv[wm].view(np.int64))
+                     for (gv, gm), (wv, wm) in zip(full, want))
+            ret.put(("ok" if ok else "mismatch", len(full[0][0]), len(want[0][0])))
+        else:
+            assert full is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gather():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    status, wg, ww = ret.get(timeout=10)
+    assert status == "ok" and wg == ww
