@@ -75,6 +75,7 @@ struct bowgpu_rolling {
     int64_t t_after_early = 0;
     bool has_after_early = false;
     bool has_prev = false;
+    bool shard = false;  // range-partitioned shard: rows before s0 are the left halo (never part of a window)
     std::vector<PrevCell> prev;
 };
 
@@ -259,11 +260,11 @@ WindowGeom make_geom(const bowgpu_rolling *r, bool inclusive_eff) {
     // rows before s0 stay in window 0 iff that window holds a row in [S0, E0) — or exactly at E0 when the
     // iteration is inclusive (rolling.go:194-211: they are only part of the slice if lastRowIndex is set)
     g.early_keep = 0;
-    if (r->early_rows > 0 && r->has_after_early) {
+    g.shard = r->shard;
+    if (!r->shard && r->early_rows > 0 && r->has_after_early) {
         const uint64_t rel = (uint64_t)r->t_after_early - (uint64_t)r->s0;
         g.early_keep = rel < (uint64_t)r->interval || (inclusive_eff && rel == (uint64_t)r->interval);
     }
-    g._pad = 0;
     return g;
 }
 
@@ -621,6 +622,26 @@ extern "C" int32_t bowgpu_frame_generate(bowgpu_ctx *ctx, const bowgpu_gen_spec 
 // ================================================================================================
 // rolling
 // ================================================================================================
+// rows with t < r->s0 at the head of the frame (and the time of the first row after them)
+static int32_t find_early_rows(bowgpu_ctx *ctx, bowgpu_rolling *r) {
+    const DevCol &tc = r->frame->cols[r->time_col];
+    const int64_t n = r->frame->n;
+    CK(launch_lower_bound((const int64_t *)tc.values, n, r->s0, ctx->d_scalars, ctx->stream));
+    int64_t p = 0;
+    CK(cudaMemcpyAsync(&p, ctx->d_scalars, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    r->early_rows = p;
+    r->has_after_early = false;
+    if (p < n) {
+        int64_t tp = 0;
+        CK(cudaMemcpyAsync(&tp, tc.values + p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        r->t_after_early = tp;
+        r->has_after_early = true;
+    }
+    return BOWGPU_OK;
+}
+
 extern "C" int32_t bowgpu_rolling_create(bowgpu_frame *frame, int32_t time_col, int64_t interval, int64_t offset,
                                          int32_t inclusive, const bowgpu_col *prev_row, bowgpu_rolling **out) {
     if (!frame || !out) return BOWGPU_EINVAL;
@@ -684,20 +705,8 @@ extern "C" int32_t bowgpu_rolling_create(bowgpu_frame *frame, int32_t time_col, 
         // countWindows, rolling.go:143-154
         r->W = s0 > r->t_last ? 0 : (int64_t)(((uint64_t)r->t_last - (uint64_t)s0) / (uint64_t)interval) + 1;
         if (r->t_first < s0) {  // negative timestamps: leading rows before the first window start
-            int e = launch_lower_bound((const int64_t *)tc.values, n, s0, ctx->d_scalars, ctx->stream);
-            int64_t p = 0;
-            if (e || cudaMemcpyAsync(&p, ctx->d_scalars, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
-                cudaStreamSynchronize(ctx->stream) != cudaSuccess)
-                return bail(fail(ctx, BOWGPU_ECUDA, "lower_bound: %s", cudaGetErrorString(cudaGetLastError())));
-            r->early_rows = p;
-            if (p < n) {
-                int64_t tp = 0;
-                if (cudaMemcpyAsync(&tp, tc.values + p, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
-                    cudaStreamSynchronize(ctx->stream) != cudaSuccess)
-                    return bail(fail(ctx, BOWGPU_ECUDA, "reading time: %s", cudaGetErrorString(cudaGetLastError())));
-                r->t_after_early = tp;
-                r->has_after_early = true;
-            }
+            int32_t rc = find_early_rows(ctx, r);
+            if (rc) return bail(rc);
         }
     }
     *out = r;
@@ -711,16 +720,19 @@ extern "C" int32_t bowgpu_rolling_create_shard(bowgpu_frame *frame, int32_t time
     bowgpu_rolling *r = nullptr;
     int32_t rc = bowgpu_rolling_create(frame, time_col, interval, 0, inclusive, prev_row, &r);
     if (rc) return rc;
-    if (frame->n > 0 && r->t_first < s0) {
-        delete r;
-        return fail(frame->ctx, BOWGPU_EINVAL, "shard starts before its first window (t[0]=%lld < s0=%lld)",
-                    (long long)r->t_first, (long long)s0);
-    }
     r->s0 = s0;
     r->W = num_windows;
     r->offset = 0;
+    r->shard = true;
     r->early_rows = 0;
     r->has_after_early = false;
+    if (frame->n > 0 && r->t_first < s0) {  // left halo: rows before the shard's first window
+        rc = find_early_rows(frame->ctx, r);
+        if (rc) {
+            delete r;
+            return rc;
+        }
+    }
     *out = r;
     return BOWGPU_OK;
 }

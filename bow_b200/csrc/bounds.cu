@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(BND_NT, 4) bounds_kernel(const BoundsLaunch P,
             uint64_t erel = (kcur + 1) * d;
             const uint64_t Wu = (uint64_t)g.W;
             if (r0 + ti0 == 0)  // owner of row 0 (kcur > 0 only for a shard with leading empty windows)
-                for (uint64_t k = 0; k <= kcur && k <= Wu; ++k) P.first[k] = 0;
+                for (uint64_t k = 0; k <= kcur && k <= Wu; ++k) P.first[k] = g.shard ? g.early_rows : 0;
 #pragma unroll
             for (int j = 0; j < R; ++j) {
                 if (ti0 + j + 1 < nrem) {

@@ -18,50 +18,54 @@ struct EpiBatch {
     EpilogueSpec s[EPI_MAX];
 };
 
-__global__ void epilogue_kernel(const EpiBatch B, const WindowGeom g) {
-    const EpilogueSpec &sp = B.s[blockIdx.y];
+// One thread per window, looping over the specs of the batch: the per-window counts shared by the
+// aggregations of one input column are fetched from DRAM once (repeats hit L1).
+__global__ void __launch_bounds__(256) epilogue_kernel(const EpiBatch B, const int nspecs, const WindowGeom g) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = k < g.W;
-    bool valid = false;
-    if (in) {
-        const int64_t c = sp.cnt ? sp.cnt[k] : 0;
-        uint64_t *vals = reinterpret_cast<uint64_t *>(sp.values);
-        const bool always = sp.op == BOWGPU_AGG_WINDOW_START || sp.op == BOWGPU_AGG_COUNT || sp.op == BOWGPU_AGG_SUM;
-        valid = always || (sp.ok ? sp.ok[k] != 0 : c > 0);
-        bool have = false;  // value already computed in a register
-        uint64_t bits = 0;
-        if (sp.op == BOWGPU_AGG_WINDOW_START) {
-            bits = (uint64_t)g.s0 + (uint64_t)k * g.div.d;
-            have = true;
-        } else if (sp.op == BOWGPU_AGG_COUNT) {
-            bits = (uint64_t)c;
-            have = true;
-        } else if (sp.ok ? sp.ok[k] == 0 : c == 0) {
-            bits = 0;  // null slot, or Sum of an empty / all-null window = 0.0
-            have = true;
-        } else if (sp.op == BOWGPU_AGG_MEAN) {
-            bits = f64_as_bits(__ddiv_rn(sp.sum_src[k], (double)c));  // arithmeticmean.go:28
-            have = true;
-        } else if (sp.op == BOWGPU_AGG_WAVG_STEP || sp.op == BOWGPU_AGG_WAVG_LINEAR) {
-            // integral / float64(w.LastValue - w.FirstValue), weightedmean.go:17,31
-            bits = f64_as_bits(__ddiv_rn(sp.sum_src[k], (double)(int64_t)g.div.d));
-            have = true;
-        }
-        if (valid && sp.nfactors > 0) {
-            if (!have) bits = vals[k];
-            for (int i = 0; i < sp.nfactors; ++i) {
-                if (sp.out_is_int)
-                    bits = (uint64_t)f64_to_i64_go(__dmul_rn((double)(int64_t)bits, sp.factors[i]));
-                else
-                    bits = f64_as_bits(__dmul_rn(bits_as_f64(bits), sp.factors[i]));
-            }
-            have = true;
-        }
-        if (have) vals[k] = bits;
-    }
-    const uint32_t ball = __ballot_sync(0xffffffffu, valid);
     const int lane = threadIdx.x & 31;
-    if ((lane & 7) == 0 && in) sp.validity[k >> 3] = (uint8_t)(ball >> lane);
+    for (int si = 0; si < nspecs; ++si) {
+        const EpilogueSpec &sp = B.s[si];
+        bool valid = false;
+        if (in) {
+            const int64_t c = sp.cnt ? __ldg(sp.cnt + k) : 0;
+            uint64_t *vals = reinterpret_cast<uint64_t *>(sp.values);
+            const bool always = sp.op == BOWGPU_AGG_WINDOW_START || sp.op == BOWGPU_AGG_COUNT || sp.op == BOWGPU_AGG_SUM;
+            valid = always || (sp.ok ? sp.ok[k] != 0 : c > 0);
+            bool have = false;  // value already computed in a register
+            uint64_t bits = 0;
+            if (sp.op == BOWGPU_AGG_WINDOW_START) {
+                bits = (uint64_t)g.s0 + (uint64_t)k * g.div.d;
+                have = true;
+            } else if (sp.op == BOWGPU_AGG_COUNT) {
+                bits = (uint64_t)c;
+                have = true;
+            } else if (sp.ok ? sp.ok[k] == 0 : c == 0) {
+                bits = 0;  // null slot, or Sum of an empty / all-null window = 0.0
+                have = true;
+            } else if (sp.op == BOWGPU_AGG_MEAN) {
+                bits = f64_as_bits(__ddiv_rn(sp.sum_src[k], (double)c));  // arithmeticmean.go:28
+                have = true;
+            } else if (sp.op == BOWGPU_AGG_WAVG_STEP || sp.op == BOWGPU_AGG_WAVG_LINEAR) {
+                // integral / float64(w.LastValue - w.FirstValue), weightedmean.go:17,31
+                bits = f64_as_bits(__ddiv_rn(sp.sum_src[k], (double)(int64_t)g.div.d));
+                have = true;
+            }
+            if (valid && sp.nfactors > 0) {
+                if (!have) bits = vals[k];
+                for (int i = 0; i < sp.nfactors; ++i) {
+                    if (sp.out_is_int)
+                        bits = (uint64_t)f64_to_i64_go(__dmul_rn((double)(int64_t)bits, sp.factors[i]));
+                    else
+                        bits = f64_as_bits(__dmul_rn(bits_as_f64(bits), sp.factors[i]));
+                }
+                have = true;
+            }
+            if (have) vals[k] = bits;
+        }
+        const uint32_t ball = __ballot_sync(0xffffffffu, valid);
+        if ((lane & 7) == 0 && in) sp.validity[k >> 3] = (uint8_t)(ball >> lane);
+    }
 }
 
 }  // namespace
@@ -73,8 +77,7 @@ int launch_epilogue(const EpilogueSpec *specs, int nspecs, WindowGeom g, cudaStr
         EpiBatch B;
         const int m = nspecs - b < EPI_MAX ? nspecs - b : EPI_MAX;
         for (int i = 0; i < m; ++i) B.s[i] = specs[b + i];
-        dim3 grid((unsigned)((g.W + nt - 1) / nt), (unsigned)m);
-        epilogue_kernel<<<grid, nt, 0, stream>>>(B, g);
+        epilogue_kernel<<<(unsigned)((g.W + nt - 1) / nt), nt, 0, stream>>>(B, m, g);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
     }

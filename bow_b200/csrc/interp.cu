@@ -59,7 +59,7 @@ __global__ void interp_window_kernel(const InterpLaunch P) {
     bool inc = false;  // Window.IsInclusive, rolling.go:201-209
     if (P.inclusive && b < g.n && b >= g.early_rows) inc = ((uint64_t)t[b] - (uint64_t)g.s0) == ((uint64_t)k + 1) * d;
     int64_t hi = b + (inc ? 1 : 0);
-    if (k == 0 && g.early_rows > 0 && !g.early_keep) lo = hi = 0;  // rows before s0 dropped with an empty window 0
+    if (k == 0 && g.early_rows > 0 && !g.early_keep && !g.shard) lo = hi = 0;  // rows before s0 dropped with an empty window 0
     const int64_t first_index = lo;
     // interpolation.go:119-128: the comparison goes through float64
     const int64_t fcv = hi > lo ? f64_to_i64_go((double)t[lo]) : -1;

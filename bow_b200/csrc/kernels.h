@@ -9,7 +9,9 @@ namespace bowgpu {
 
 // Window geometry shared by every kernel (SURVEY 8 notation):
 //   S_k = s0 + k*I, window of row i: k(i) = floor((t[i]-s0)/I); rows [0, early_rows) have t < s0
-//   (only possible for negative timestamps, rolling.go:96-99) and belong to window 0 iff early_keep.
+//   (negative timestamps, rolling.go:96-99) and belong to window 0 iff early_keep.  On a range-partitioned
+//   shard (`shard` set) the early rows are the LEFT HALO: they belong to no window (early_keep = 0,
+//   first[0] = early_rows) and only serve the prev-valid searches of Rolling.Interpolate.
 struct WindowGeom {
     int64_t n;           // rows
     int64_t s0;          // first window start (rolling.go:96-99)
@@ -17,7 +19,7 @@ struct WindowGeom {
     DivU64 div;          // interval
     int64_t early_rows;
     int32_t early_keep;
-    int32_t _pad;
+    int32_t shard;
 };
 
 // status word bits written by the kernels

@@ -192,13 +192,13 @@ int launch_ops(const SegLaunch &L, int sm, cudaStream_t s, cudaEvent_t e0, cudaE
     if (L.is_int) {
         SegArgs<BasicPol<OPS, true>> A;
         fill(A);
-        return nulls ? seg_launch<BasicPol<OPS, true>, true, 3>(A, sm, s, e0, e1)
-                     : seg_launch<BasicPol<OPS, true>, false, 3>(A, sm, s, e0, e1);
+        return nulls ? seg_launch<BasicPol<OPS, true>, true, SEG_CFG_CTAS>(A, sm, s, e0, e1)
+                     : seg_launch<BasicPol<OPS, true>, false, SEG_CFG_CTAS>(A, sm, s, e0, e1);
     }
     SegArgs<BasicPol<OPS, false>> A;
     fill(A);
-    return nulls ? seg_launch<BasicPol<OPS, false>, true, 3>(A, sm, s, e0, e1)
-                 : seg_launch<BasicPol<OPS, false>, false, 3>(A, sm, s, e0, e1);
+    return nulls ? seg_launch<BasicPol<OPS, false>, true, SEG_CFG_CTAS>(A, sm, s, e0, e1)
+                 : seg_launch<BasicPol<OPS, false>, false, SEG_CFG_CTAS>(A, sm, s, e0, e1);
 }
 
 }  // namespace

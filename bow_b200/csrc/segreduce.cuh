@@ -35,8 +35,18 @@
 
 namespace bowgpu {
 
-constexpr int SEG_NT = 128;
-constexpr int SEG_R = 17;
+// tile shape and residency (compile-time; -DSEG_CFG_* only for tuning sweeps, scripts/tune_seg.sh)
+#ifndef SEG_CFG_NT
+#define SEG_CFG_NT 128
+#endif
+#ifndef SEG_CFG_R
+#define SEG_CFG_R 17
+#endif
+#ifndef SEG_CFG_CTAS
+#define SEG_CFG_CTAS 3
+#endif
+constexpr int SEG_NT = SEG_CFG_NT;
+constexpr int SEG_R = SEG_CFG_R;
 constexpr int SEG_MAX_STAGES = 8;
 using SegG = TileGeom<SEG_NT, SEG_R>;
 constexpr int SEG_NW = SEG_NT / 32;

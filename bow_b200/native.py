@@ -13,7 +13,7 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbowgpu.so")
+LIB_PATH = os.environ.get("BOWGPU_LIB") or os.path.join(HERE, "libbowgpu.so")  # BOWGPU_LIB: tuning builds only
 
 FLOAT64, INT64 = 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1

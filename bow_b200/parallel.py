@@ -79,3 +79,96 @@ def gather_outputs(local: Outputs, dst: int = 0) -> Optional[Outputs]:
     if rank != dst:
         return None
     return concat_outputs(gathered)
+
+
+# ---- Rolling.Interpolate across shards ------------------------------------------------------------------------
+InterpExecutor = Callable[[Sequence[NpCol], int, int, int, int, bool, Sequence, Optional[Sequence[NpCol]]], List[NpCol]]
+
+
+def halo_searches(cols: Sequence[NpCol], interp_cols: Sequence[int]):
+    """prev_valid_row / next_valid_row callables of `partition.plan_interpolate` for host-resident columns."""
+    n = len(cols[0][0])
+
+    def prev_valid_row(row: int) -> int:
+        lo = row
+        for j in interp_cols:
+            m = cols[j][1]
+            if m is None:
+                lo = min(lo, max(row - 1, 0))
+                continue
+            idx = np.flatnonzero(m[:row])
+            lo = min(lo, int(idx[-1]) if len(idx) else 0)
+        return lo
+
+    def next_valid_row(row: int) -> int:
+        hi = row
+        for j in interp_cols:
+            m = cols[j][1]
+            if m is None:
+                hi = max(hi, min(row + 1, n))
+                continue
+            idx = np.flatnonzero(m[row:])
+            hi = max(hi, row + int(idx[0]) + 1 if len(idx) else n)
+        return hi
+
+    return prev_valid_row, next_valid_row
+
+
+def plan_interpolate_for_columns(cols: Sequence[NpCol], time_col: int, interval: int, offset: int, n_shards: int,
+                                 ops: Sequence) -> Tuple[List[P.Shard], int]:
+    time = cols[time_col][0]
+    n = len(time)
+    if n == 0:
+        return P.plan(0, 0, 0, interval, offset, n_shards, lambda x: 0), 0
+    need = [j for j, o in enumerate(ops) if str(o) in ("Linear", "StepPrevious", "1", "2")]
+    pv, nv = halo_searches(cols, need)
+    off = P.normalise_offset(interval, offset)
+    s0 = P.first_window_start(int(time[0]), interval, off)
+    shards = P.plan_interpolate(n, int(time[0]), int(time[-1]), interval, offset, n_shards,
+                                lambda x: int(np.searchsorted(time, x, side="left")), pv, nv)
+    return shards, s0
+
+
+def gpu_interpolate_executor(cols: Sequence[NpCol], time_col: int, interval: int, s0: int, num_windows: int,
+                             inclusive: bool, ops: Sequence, prev_row: Optional[Sequence[NpCol]]) -> List[NpCol]:
+    """Interpolates windows [0, num_windows) of the lattice starting at s0 on this process' GPU; rows of `cols`
+    before s0 are the left halo."""
+    from . import native as N
+    from .runtime import default_ctx
+    fr = N.Frame.from_numpy(default_ctx(), cols)
+    r = N.Rolling(fr, time_col, interval, inclusive=inclusive, prev_row=prev_row, shard=(s0, num_windows))
+    try:
+        out = r.interpolate(ops)
+        try:
+            return out.download()
+        finally:
+            out.close()
+    finally:
+        r.close()
+        fr.close()
+
+
+def interpolate_shard(cols: Sequence[NpCol], shard: P.Shard, time_col: int, interval: int, s0_global: int,
+                      inclusive: bool, ops: Sequence, prev_row: Optional[Sequence[NpCol]] = None,
+                      executor: InterpExecutor = gpu_interpolate_executor) -> Tuple[List[NpCol], int]:
+    """-> (interpolated rows of windows [k_lo, k_hi + extra_windows), number of those rows that belong to the
+    shard's OWN windows).  The global interpolated frame is the concatenation of every shard's first `own` rows;
+    the remaining rows (start row of the next shard's first window onwards) only serve a following inclusive
+    Aggregate on this shard."""
+    ncols = len(cols)
+    if shard.num_windows == 0:
+        return [(np.zeros(0, dtype=v.dtype), np.zeros(0, dtype=bool)) for v, _ in cols], 0
+    nloc = shard.halo_hi - shard.first_row
+    local = cols if len(cols[0][0]) == nloc else slice_cols(cols, shard.first_row, shard.halo_hi)
+    s0 = s0_global + shard.k_lo * interval
+    out = executor(local, time_col, interval, s0, shard.num_windows + shard.extra_windows, inclusive, ops, prev_row)
+    assert len(out) == ncols
+    t_out = out[time_col][0]
+    own = int(np.searchsorted(t_out, s0 + shard.num_windows * interval, side="left")) if shard.extra_windows else len(t_out)
+    return out, own
+
+
+def concat_frames(per_shard: Sequence[Tuple[List[NpCol], int]]) -> List[NpCol]:
+    ncols = len(per_shard[0][0])
+    return [(np.concatenate([o[j][0][:own] for o, own in per_shard]),
+             np.concatenate([o[j][1][:own] for o, own in per_shard])) for j in range(ncols)]

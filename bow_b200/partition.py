@@ -25,6 +25,8 @@ class Shard:
     row_lo: int    # first row owned (= lower bound of S_{k_lo}; 0 for the first shard)
     row_hi: int    # one past the last row owned (= lower bound of S_{k_hi}; n for the last shard)
     halo_hi: int   # rows [row_hi, halo_hi) are shipped too (inclusive row of the last window)
+    frame_lo: int = -1   # first row shipped: rows [frame_lo, row_lo) are the LEFT halo (Interpolate only)
+    extra_windows: int = 0   # Interpolate only: 1 if the start row of window k_hi is produced here as well
 
     @property
     def num_windows(self) -> int:
@@ -33,6 +35,14 @@ class Shard:
     @property
     def num_rows(self) -> int:
         return self.row_hi - self.row_lo
+
+    @property
+    def first_row(self) -> int:
+        return self.row_lo if self.frame_lo < 0 else self.frame_lo
+
+    @property
+    def lead_rows(self) -> int:
+        return self.row_lo - self.first_row
 
 
 def go_div(a: int, b: int) -> int:
@@ -102,3 +112,40 @@ def regular_lower_bound(t0: int, step: int, n_rows: int) -> Callable[[int], int]
             return 0
         return min(n_rows, -((t0 - x) // step))
     return lb
+
+
+def plan_interpolate(n_rows: int, t_first: int, t_last: int, interval: int, offset: int, n_shards: int,
+                     lower_bound: Callable[[int], int], prev_valid_row: Callable[[int], int],
+                     next_valid_row: Callable[[int], int], align: int = 64) -> List[Shard]:
+    """Shards for Rolling.Interpolate (and the Aggregate that follows it on the interpolated frame).
+
+    On top of `plan`, shard g ships
+      * a LEFT halo back to `prev_valid_row(row_lo)`: the smallest, over the interpolated columns, of the last
+        row before row_lo holding a valid value (0 if a column has none) - what interpolation.Linear /
+        StepPrevious look up for the shard's first windows (reference linear.go:14-18, stepprevious.go:12-20;
+        for the first shard this role is played by Options.PrevRow);
+      * one extra WINDOW on the right (the one-window halo of the north star): the start row of window k_hi,
+        real or synthetic, is the inclusive row of the shard's last window when an inclusive aggregation
+        (IntegralTrapezoid / WeightedAverageLinear) follows, so it is interpolated here too;
+      * a RIGHT halo up to `next_valid_row(r)`: one past the largest, over the interpolated columns, of the
+        first row at or after r holding a valid value (n_rows if none), r = first row of the last window
+        interpolated here (linear.go:20-27 looks beyond the window).
+    """
+    base = plan(n_rows, t_first, t_last, interval, offset, n_shards, lower_bound, align)
+    if n_rows == 0:
+        return base
+    off = normalise_offset(interval, offset)
+    s0 = first_window_start(t_first, interval, off)
+    W = num_windows(t_first, t_last, interval, off)
+    out = []
+    for sh in base:
+        if sh.num_windows == 0:
+            out.append(Shard(sh.rank, sh.k_lo, sh.k_hi, sh.row_lo, sh.row_hi, sh.row_hi, sh.row_lo, 0))
+            continue
+        extra = 1 if sh.k_hi < W else 0
+        k_last = sh.k_hi - 1 + extra                       # last window interpolated on this shard
+        end_rows = lower_bound(s0 + (k_last + 1) * interval) if k_last + 1 < W else n_rows
+        halo_hi = min(n_rows, max(end_rows + 1, next_valid_row(lower_bound(s0 + k_last * interval))))
+        frame_lo = 0 if sh.row_lo == 0 else max(0, min(sh.row_lo - 1, prev_valid_row(sh.row_lo)))
+        out.append(Shard(sh.rank, sh.k_lo, sh.k_hi, sh.row_lo, sh.row_hi, halo_hi, frame_lo, extra))
+    return out

@@ -130,3 +130,55 @@ def test_interpolate_errors_and_empty(ctx):
     fe = N.Frame.from_numpy(ctx, [(np.zeros(0, dtype=np.int64), None), (np.zeros(0), None)])
     out = N.Rolling(fe, 0, 2).interpolate(["WindowStart", "Linear"])
     assert out.num_rows == 0 and out.num_cols == 2
+
+
+@pytest.mark.parametrize("g", [2, 3, 7])
+def test_sharded_interpolate_matches_oracle(ctx, g):
+    """range-partitioned Interpolate (left halo = rows before the shard's first window, right halo = one window +
+    next valid rows): the concatenation of the shards' own rows must equal the unsharded oracle, and the chained
+    per-shard Aggregate with inclusive aggregations must equal the unsharded chain"""
+    from bow_b200 import native as N
+    from bow_b200 import parallel as PP
+    rng = np.random.default_rng(100 + g)
+    ops = ["WindowStart", "Linear", "StepPrevious", "Linear"]
+    specs = [("WindowStart", 0), ("WeightedAverageLinear", 1), ("IntegralTrapezoid", 3), ("Last", 2), ("Count", 1),
+             ("IntegralStep", 1)]
+    for kind, n, interval in (("regular", 30000, 40), ("sparse", 9000, 11), ("bursty", 50000, 700), ("regular", 300, 5)):
+        t = H.random_times(rng, n, kind)
+        t = t - int(t[0]) + 5000
+        cols = [(t, None), H.random_values(rng, n, np.float64, 0.4), H.random_values(rng, n, np.int64, 0.93),
+                H.random_values(rng, n, np.int64, 0.0)]
+        offset = int(rng.integers(-interval, interval))
+        prev = [(np.array([4990], dtype=np.int64), None), (np.array([0.25]), None), (np.array([3], dtype=np.int64), None),
+                (np.array([-8], dtype=np.int64), None)]
+        shards, s0 = PP.plan_interpolate_for_columns(cols, 0, interval, offset, g, ops)
+        ref = R.RefRolling(R.Frame(cols), 0, interval, offset=offset, prev_row=R.Frame(prev))
+        want = ref.interpolate(ops)
+        per = [PP.interpolate_shard(cols, s, 0, interval, s0, False, ops, prev) for s in shards]
+        got = PP.concat_frames(per)
+        assert_frames_equal(got, want, f"sharded interp {kind} g={g}")
+        # chained on the device, shard by shard
+        icols = [(vv, None if mm.all() else mm) for vv, mm in want]
+        want_agg = R.RefRolling(R.Frame(icols), 0, interval, offset=offset).aggregate(specs)
+        outs = []
+        for s in shards:
+            if s.num_windows == 0:
+                continue
+            local = PP.slice_cols(cols, s.first_row, s.halo_hi)
+            fr = N.Frame.from_numpy(ctx, local)
+            s0g = s0 + s.k_lo * interval
+            r = N.Rolling(fr, 0, interval, prev_row=prev, shard=(s0g, s.num_windows + s.extra_windows))
+            fi = r.interpolate(ops)
+            r2 = N.Rolling(fi, 0, interval, shard=(s0g, s.num_windows))
+            outs.append(r2.aggregate(specs))
+            for o in (r2, fi, r, fr):
+                o.close()
+        got_agg = PP.concat_outputs(outs)
+        for j, sp in enumerate(specs):
+            (gv, gm), (wv, wm) = got_agg[j], want_agg[j]
+            assert np.array_equal(gm, wm), (kind, g, sp)
+            if gv.dtype == np.int64:
+                assert np.array_equal(gv[gm], wv[wm]), (kind, g, sp)
+            else:
+                scale = np.maximum(np.abs(wv[wm]), 1.0)
+                assert np.all(np.abs(gv[gm] - wv[wm]) <= 1e-12 * scale * max(1, interval)), (kind, g, sp)

@@ -141,3 +141,57 @@ def test_two_rank_gloo_gather():
         assert p.exitcode == 0
     status, wg, ww = ret.get(timeout=10)
     assert status == "ok" and wg == ww
+
+
+# ---- Rolling.Interpolate across shards -------------------------------------------------------------------------
+OPS = ["WindowStart", "Linear", "StepPrevious"]
+
+
+def oracle_interp_executor(cols, time_col, interval, s0, num_windows, inclusive, ops, prev_row):
+    """Shard executor backed by the oracle.  The oracle has no pinned-lattice mode, so it interpolates the
+    shard's rows INCLUDING the left halo (same lattice: offset = s0 mod interval) and the rows of the windows
+    [s0, s0 + num_windows*interval) are cut out by time afterwards; windows of the lattice that lie after the
+    last local row are empty and produce their start rows from the halo, like the kernel does."""
+    t = cols[time_col][0]
+    end = s0 + num_windows * interval
+    # one sentinel row at the end of the lattice makes the oracle emit the trailing empty windows; it is cut away
+    ext = []
+    for j, (v, m) in enumerate(cols):
+        sv = np.array([end if j == time_col else 0], dtype=v.dtype)
+        sm = np.array([j == time_col], dtype=bool)
+        mm = np.ones(len(v), dtype=bool) if m is None else m
+        ext.append((np.concatenate([v, sv]), np.concatenate([mm, sm])))
+    need_sentinel = len(t) == 0 or int(t[-1]) < end
+    use = ext if need_sentinel else [(v, np.ones(len(v), dtype=bool) if m is None else m) for v, m in cols]
+    pr = R.Frame(prev_row) if prev_row is not None else None
+    ref = R.RefRolling(R.Frame(use), time_col, interval, offset=s0 % interval, inclusive=inclusive, prev_row=pr)
+    out = ref.interpolate(ops)
+    to = out[time_col][0]
+    lo, hi = int(np.searchsorted(to, s0, side="left")), int(np.searchsorted(to, end, side="left"))
+    return [(v[lo:hi], m[lo:hi]) for v, m in out]
+
+
+@pytest.mark.parametrize("kind", ["regular", "sparse", "bursty"])
+@pytest.mark.parametrize("g", [1, 2, 5])
+def test_sharded_interpolate_matches_unsharded(kind, g):
+    rng = np.random.default_rng(hash((kind, g, "i")) & 0xFFFF)
+    for n, interval in ((1, 5), (40, 3), (6000, 7), (20000, 300)):
+        t = H.random_times(rng, n, kind)
+        t = t - int(t[0]) + 1000
+        cols = [(t, None), H.random_values(rng, n, np.float64, 0.5), H.random_values(rng, n, np.int64, 0.9)]
+        offset = int(rng.integers(-interval, interval))
+        prev = [(np.array([990], dtype=np.int64), None), (np.array([1.5]), None), (np.array([7], dtype=np.int64), None)]
+        shards, s0 = PP.plan_interpolate_for_columns(cols, 0, interval, offset, g, OPS)
+        ref = R.RefRolling(R.Frame(cols), 0, interval, offset=offset, prev_row=R.Frame(prev))
+        want = ref.interpolate(OPS)
+        per = [PP.interpolate_shard(cols, s, 0, interval, s0, False, OPS, prev, executor=oracle_interp_executor)
+               for s in shards]
+        got = PP.concat_frames(per)
+        for j in range(3):
+            assert np.array_equal(got[j][1], want[j][1]), (kind, g, n, interval, j)
+            assert np.array_equal(got[j][0][got[j][1]].view(np.int64), want[j][0][want[j][1]].view(np.int64)), \
+                (kind, g, n, interval, j)
+        # the rows a shard keeps beyond its own windows start with the next shard's first row
+        for (o, own), nxt in zip(per, per[1:]):
+            if len(o[0][0]) > own and nxt[1] > 0:
+                assert o[0][0][own] == nxt[0][0][0][0]
