@@ -586,16 +586,41 @@ extern "C" int32_t bowgpu_frame_generate(bowgpu_ctx *ctx, const bowgpu_gen_spec 
     if (!ctx || !spec || !out || spec->nrows < 0 || spec->ncols < 0 || spec->ncols > 31) return BOWGPU_EINVAL;
     *out = nullptr;
     Guard gd(ctx);
-    if (spec->kind != BOWGPU_GEN_REGULAR) return fail(ctx, BOWGPU_EUNSUPPORTED, "generator kind %d", spec->kind);
+    if (spec->kind != BOWGPU_GEN_REGULAR && spec->kind != BOWGPU_GEN_BURSTY)
+        return fail(ctx, BOWGPU_EUNSUPPORTED, "generator kind %d", spec->kind);
+    if (spec->kind == BOWGPU_GEN_BURSTY && (spec->step <= 0 || spec->row0 < 0))
+        return fail(ctx, BOWGPU_EINVAL, "bursty generator: step (window interval) must be positive");
     bowgpu_frame *f = new (std::nothrow) bowgpu_frame();
     if (!f) return BOWGPU_ENOMEM;
     f->ctx = ctx;
     f->n = spec->nrows;
     f->cols.resize(spec->ncols + 1);
     int32_t rc = alloc_col(ctx, f->cols[0], f->n, BOWGPU_INT64, false);
-    if (rc == BOWGPU_OK) {
+    if (rc == BOWGPU_OK && spec->kind == BOWGPU_GEN_REGULAR) {
         int e = launch_gen_regular((int64_t *)f->cols[0].values, f->n, spec->row0, spec->t0, spec->step, ctx->stream);
         if (e) rc = fail(ctx, BOWGPU_ECUDA, "gen_time: %s", cudaGetErrorString((cudaError_t)e));
+    }
+    if (rc == BOWGPU_OK && spec->kind == BOWGPU_GEN_BURSTY && f->n > 0) {
+        // enough windows of the pattern to cover global rows [0, row0 + nrows): the mean window holds ~7.7e3 rows
+        const int64_t nw = (spec->row0 + spec->nrows) / 2000 + 4096;
+        rc = arena_reserve(ctx, (size_t)(nw + 1) * 8 + scan_scratch_bytes(nw) + 1024);
+        if (rc == BOWGPU_OK) {
+            arena_reset(ctx);
+            int64_t *off = (int64_t *)arena_take(ctx, (size_t)(nw + 1) * 8);
+            int64_t *tmp = (int64_t *)arena_take(ctx, scan_scratch_bytes(nw));
+            int e = launch_gen_bursty_counts(off, nw, spec->seed, ctx->stream);
+            if (!e) e = launch_exclusive_scan(off, nw, tmp, ctx->stream);
+            int64_t total = 0;
+            if (!e) e = (int)cudaMemcpyAsync(&total, off + nw, 8, cudaMemcpyDeviceToHost, ctx->stream);
+            if (!e) e = (int)cudaStreamSynchronize(ctx->stream);
+            if (!e && total < spec->row0 + spec->nrows)
+                rc = fail(ctx, BOWGPU_EINVAL, "bursty generator: pattern covers %lld rows, %lld requested", (long long)total,
+                          (long long)(spec->row0 + spec->nrows));
+            if (!e && rc == BOWGPU_OK)
+                e = launch_gen_bursty_time((int64_t *)f->cols[0].values, f->n, spec->row0, spec->t0, spec->step, spec->seed,
+                                           off, nw, ctx->stream);
+            if (e) rc = fail(ctx, BOWGPU_ECUDA, "gen_bursty: %s", cudaGetErrorString((cudaError_t)e));
+        }
     }
     for (int c = 0; c < spec->ncols && rc == BOWGPU_OK; ++c) {
         DevCol &dc = f->cols[c + 1];

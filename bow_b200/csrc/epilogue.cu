@@ -24,14 +24,33 @@ __global__ void __launch_bounds__(256) epilogue_kernel(const EpiBatch B, const i
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = k < g.W;
     const int lane = threadIdx.x & 31;
-    for (int si = 0; si < nspecs; ++si) {
+    // phase 1: every global read of this window, all in flight together (the pass is latency bound otherwise)
+    int64_t cv[EPI_MAX];
+    double sv[EPI_MAX];
+    uint8_t okv[EPI_MAX];
+#pragma unroll
+    for (int si = 0; si < EPI_MAX; ++si) {
+        cv[si] = 0;
+        sv[si] = 0.0;
+        okv[si] = 0;
+        if (si < nspecs && in) {
+            const EpilogueSpec &sp = B.s[si];
+            if (sp.cnt) cv[si] = sp.cnt[k];
+            if (sp.sum_src) sv[si] = sp.sum_src[k];
+            if (sp.ok) okv[si] = sp.ok[k];
+        }
+    }
+#pragma unroll
+    for (int si = 0; si < EPI_MAX; ++si) {
+        if (si >= nspecs) break;
         const EpilogueSpec &sp = B.s[si];
         bool valid = false;
         if (in) {
-            const int64_t c = sp.cnt ? __ldg(sp.cnt + k) : 0;
+            const int64_t c = cv[si];
+            const bool okk = sp.ok ? okv[si] != 0 : c > 0;
             uint64_t *vals = reinterpret_cast<uint64_t *>(sp.values);
             const bool always = sp.op == BOWGPU_AGG_WINDOW_START || sp.op == BOWGPU_AGG_COUNT || sp.op == BOWGPU_AGG_SUM;
-            valid = always || (sp.ok ? sp.ok[k] != 0 : c > 0);
+            valid = always || okk;
             bool have = false;  // value already computed in a register
             uint64_t bits = 0;
             if (sp.op == BOWGPU_AGG_WINDOW_START) {
@@ -40,15 +59,15 @@ __global__ void __launch_bounds__(256) epilogue_kernel(const EpiBatch B, const i
             } else if (sp.op == BOWGPU_AGG_COUNT) {
                 bits = (uint64_t)c;
                 have = true;
-            } else if (sp.ok ? sp.ok[k] == 0 : c == 0) {
+            } else if (!okk) {
                 bits = 0;  // null slot, or Sum of an empty / all-null window = 0.0
                 have = true;
             } else if (sp.op == BOWGPU_AGG_MEAN) {
-                bits = f64_as_bits(__ddiv_rn(sp.sum_src[k], (double)c));  // arithmeticmean.go:28
+                bits = f64_as_bits(__ddiv_rn(sv[si], (double)c));  // arithmeticmean.go:28
                 have = true;
             } else if (sp.op == BOWGPU_AGG_WAVG_STEP || sp.op == BOWGPU_AGG_WAVG_LINEAR) {
                 // integral / float64(w.LastValue - w.FirstValue), weightedmean.go:17,31
-                bits = f64_as_bits(__ddiv_rn(sp.sum_src[k], (double)(int64_t)g.div.d));
+                bits = f64_as_bits(__ddiv_rn(sv[si], (double)(int64_t)g.div.d));
                 have = true;
             }
             if (valid && sp.nfactors > 0) {

@@ -46,7 +46,58 @@ __global__ void gen_values(uint64_t *v, uint32_t *validity, int64_t n, int64_t r
     }
 }
 
+// ---- BURSTY (BASELINE configs[3]: window sizes 0 .. ~1e6 rows, load-balance stress) -------------------------
+// Window k of the lattice S_k = t0 + k*I holds c_k rows, c_k drawn from u(seed, 0, k):
+//   50 %: 0 rows;  45 %: 1 + (u >> 8) % 100 rows;  5 %: (1000 + (u >> 8) % 1000) << ((u >> 32) % 10) rows
+// (integer-only so that the numpy mirror is bit-exact).  Row j of the window sits at
+//   S_k + floor(j * I / c_k)            when bit 40 of u is clear (the window has a row exactly at S_k)
+//   S_k + floor((2j + 1) * I / (2 c_k)) otherwise (no row at S_k: Interpolate must insert one).
+__host__ __device__ __forceinline__ int64_t bursty_count(uint64_t u) {
+    const uint64_t r = u % 100;
+    if (r < 50) return 0;
+    if (r < 95) return 1 + (int64_t)((u >> 8) % 100);
+    return (int64_t)((1000 + (u >> 8) % 1000) << ((u >> 32) % 10));
+}
+
+__global__ void gen_bursty_counts(int64_t *cnt, int64_t nw, uint64_t seed) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nw; k += (int64_t)gridDim.x * blockDim.x)
+        cnt[k] = bursty_count(synth_u(seed, 0, (uint64_t)k));
+}
+
+// off = exclusive scan of the counts (off[nw] = total rows); row gi lies in the window k with off[k] <= gi < off[k+1]
+__global__ void gen_time_bursty(int64_t *t, int64_t n, int64_t row0, int64_t t0, int64_t interval, uint64_t seed,
+                                const int64_t *off, int64_t nw) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t gi = row0 + i;
+        int64_t lo = 0, hi = nw;  // largest k with off[k] <= gi
+        while (hi - lo > 1) {
+            const int64_t mid = lo + ((hi - lo) >> 1);
+            if (off[mid] <= gi)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const int64_t k = lo, c = off[k + 1] - off[k], j = gi - off[k];
+        const bool shifted = (synth_u(seed, 0, (uint64_t)k) >> 40) & 1u;
+        const int64_t dt = shifted ? ((2 * j + 1) * interval) / (2 * c) : (j * interval) / c;
+        t[i] = t0 + k * interval + dt;
+    }
+}
+
 }  // namespace
+
+int launch_gen_bursty_counts(int64_t *cnt, int64_t nw, uint64_t seed, cudaStream_t stream) {
+    if (nw == 0) return 0;
+    gen_bursty_counts<<<592, 256, 0, stream>>>(cnt, nw, seed);
+    return (int)cudaGetLastError();
+}
+
+int launch_gen_bursty_time(int64_t *time, int64_t n, int64_t row0, int64_t t0, int64_t interval, uint64_t seed,
+                           const int64_t *off, int64_t nw, cudaStream_t stream) {
+    if (n == 0) return 0;
+    gen_time_bursty<<<1184, 256, 0, stream>>>(time, n, row0, t0, interval, seed, off, nw);
+    return (int)cudaGetLastError();
+}
 
 int launch_gen_regular(int64_t *time, int64_t n, int64_t row0, int64_t t0, int64_t step, cudaStream_t stream) {
     if (n == 0) return 0;

@@ -161,6 +161,10 @@ int launch_lower_bound(const int64_t *time, int64_t n, int64_t x, int64_t *out, 
 
 // ---- synthetic generators (generate.cu) ----------------------------------------------------------
 int launch_gen_regular(int64_t *time, int64_t n, int64_t row0, int64_t t0, int64_t step, cudaStream_t stream);
+// BURSTY: per-window row counts (to be scanned in place with launch_exclusive_scan) and the time column
+int launch_gen_bursty_counts(int64_t *cnt, int64_t nw, uint64_t seed, cudaStream_t stream);
+int launch_gen_bursty_time(int64_t *time, int64_t n, int64_t row0, int64_t t0, int64_t interval, uint64_t seed,
+                           const int64_t *off, int64_t nw, cudaStream_t stream);
 int launch_gen_values(uint64_t *v, uint8_t *validity, int64_t n, int64_t row0, uint64_t seed, uint64_t col, int is_int,
                       uint32_t null_mod, cudaStream_t stream);
 
