@@ -32,6 +32,9 @@ struct bowgpu_ctx {
     // scratch arena (grow only, bump allocated per call)
     uint8_t *arena = nullptr;
     size_t arena_cap = 0, arena_top = 0;
+    // stream-ordered pool for column buffers: freed blocks stay cached (release threshold = max), so the
+    // Interpolate -> Aggregate chain does not pay cudaMalloc / cudaFree of multi-GB columns on every call
+    cudaMemPool_t pool = nullptr;
     // pinned staging for pageable host memory
     uint8_t *pinned[2] = {nullptr, nullptr};
     cudaEvent_t pinned_ev[2] = {nullptr, nullptr};
@@ -109,6 +112,13 @@ int32_t fail(bowgpu_ctx *c, int32_t code, const char *fmt, ...) {
     } while (0)
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+cudaError_t pool_alloc(bowgpu_ctx *ctx, void **p, size_t bytes) {
+    return cudaMallocFromPoolAsync(p, bytes, ctx->pool, ctx->stream);
+}
+void pool_free(bowgpu_ctx *ctx, void *p) {
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
 int64_t bitmap_bytes_padded(int64_t n) { return (int64_t)align_up((size_t)((n + 7) / 8), 16) + 16; }
 
 // ---- scratch arena ---------------------------------------------------------------------------------
@@ -322,6 +332,17 @@ extern "C" int32_t bowgpu_ctx_create(int32_t device, void *stream, bowgpu_ctx **
         if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(BOWGPU_ECUDA);
         ctx->own_stream = true;
     }
+    {
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof props);
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        if (cudaMemPoolCreate(&ctx->pool, &props) != cudaSuccess) return bail(BOWGPU_ECUDA);
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     if (cudaMalloc(&ctx->d_status, 256) != cudaSuccess) return bail(BOWGPU_ENOMEM);
     ctx->d_scalars = (int64_t *)((char *)ctx->d_status + 64);
     cudaMemsetAsync(ctx->d_status, 0, 256, ctx->stream);
@@ -344,6 +365,7 @@ extern "C" void bowgpu_ctx_destroy(bowgpu_ctx *ctx) {
         if (ctx->ev_total[i]) cudaEventDestroy(ctx->ev_total[i]);
     }
     for (auto e : ctx->ev_main) cudaEventDestroy(e);
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -385,14 +407,22 @@ extern "C" int32_t bowgpu_ctx_last_timing(bowgpu_ctx *ctx, bowgpu_timing *out) {
 
 extern "C" int32_t bowgpu_ctx_sm_count(const bowgpu_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
 
+extern "C" int32_t bowgpu_ctx_trim(bowgpu_ctx *ctx) {
+    if (!ctx) return BOWGPU_EINVAL;
+    Guard gd(ctx);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemPoolTrimTo(ctx->pool, 0));
+    return BOWGPU_OK;
+}
+
 // ================================================================================================
 // frames
 // ================================================================================================
 namespace {
 
-void free_col(DevCol &c) {
-    if (c.own_values && c.values) cudaFree(c.values);
-    if (c.own_validity && c.validity) cudaFree(c.validity);
+void free_col(bowgpu_ctx *ctx, DevCol &c) {
+    if (c.own_values && c.values) pool_free(ctx, c.values);
+    if (c.own_validity && c.validity) pool_free(ctx, c.validity);
     c = DevCol();
 }
 
@@ -400,11 +430,11 @@ void free_col(DevCol &c) {
 int32_t alloc_col(bowgpu_ctx *ctx, DevCol &c, int64_t n, int32_t dtype, bool with_validity) {
     c.dtype = dtype;
     size_t vb = align_up((size_t)n * 8, 16) + 32;
-    CK(cudaMalloc((void **)&c.values, vb));
+    CK(pool_alloc(ctx, (void **)&c.values, vb));
     c.own_values = true;
     if (with_validity) {
         size_t bb = (size_t)bitmap_bytes_padded(n);
-        CK(cudaMalloc((void **)&c.validity, bb));
+        CK(pool_alloc(ctx, (void **)&c.validity, bb));
         c.own_validity = true;
         CK(cudaMemsetAsync(c.validity, 0, bb, ctx->stream));
     }
@@ -454,7 +484,7 @@ extern "C" int32_t bowgpu_frame_create(bowgpu_ctx *ctx, const bowgpu_col *cols, 
             c.dtype = s.dtype;
             if (want_validity) {
                 size_t bb = (size_t)bitmap_bytes_padded(n);
-                cudaError_t e = cudaMalloc((void **)&c.validity, bb);
+                cudaError_t e = pool_alloc(ctx, (void **)&c.validity, bb);
                 if (e != cudaSuccess) {
                     rc = fail(ctx, BOWGPU_ENOMEM, "cudaMalloc(%zu): %s", bb, cudaGetErrorString(e));
                     break;
@@ -496,7 +526,7 @@ extern "C" int32_t bowgpu_frame_create(bowgpu_ctx *ctx, const bowgpu_col *cols, 
                 if (s.null_count < 0) rc = count_nulls(ctx, c, n);
                 if (rc == BOWGPU_OK && c.null_count == 0) {  // bitmap without nulls: drop it (faster kernels)
                     cudaStreamSynchronize(ctx->stream);
-                    if (c.own_validity) cudaFree(c.validity);
+                    if (c.own_validity) pool_free(ctx, c.validity);
                     c.validity = nullptr;
                     c.own_validity = false;
                 }
@@ -509,7 +539,7 @@ extern "C" int32_t bowgpu_frame_create(bowgpu_ctx *ctx, const bowgpu_col *cols, 
     }
     if (rc != BOWGPU_OK) {
         cudaStreamSynchronize(ctx->stream);
-        for (auto &c : f->cols) free_col(c);
+        for (auto &c : f->cols) free_col(ctx, c);
         delete f;
         return rc;
     }
@@ -519,9 +549,12 @@ extern "C" int32_t bowgpu_frame_create(bowgpu_ctx *ctx, const bowgpu_col *cols, 
 
 extern "C" void bowgpu_frame_destroy(bowgpu_frame *f) {
     if (!f) return;
-    Guard gd(f->ctx);
-    cudaStreamSynchronize(f->ctx->stream);
-    for (auto &c : f->cols) free_col(c);
+    bowgpu_ctx *ctx = f->ctx;
+    Guard gd(ctx);
+    bool borrowed = false;  // zero-copy columns belong to the caller: it may release them right after this call
+    for (auto &c : f->cols) borrowed |= c.values && !c.own_values;
+    if (borrowed) cudaStreamSynchronize(ctx->stream);
+    for (auto &c : f->cols) free_col(ctx, c);  // stream ordered: kernels still using the columns finish first
     delete f;
 }
 
@@ -636,7 +669,7 @@ extern "C" int32_t bowgpu_frame_generate(bowgpu_ctx *ctx, const bowgpu_gen_spec 
     if (rc == BOWGPU_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
         rc = fail(ctx, BOWGPU_ECUDA, "generate: %s", cudaGetErrorString(cudaGetLastError()));
     if (rc != BOWGPU_OK) {
-        for (auto &c : f->cols) free_col(c);
+        for (auto &c : f->cols) free_col(ctx, c);
         delete f;
         return rc;
     }
@@ -1061,7 +1094,7 @@ extern "C" int32_t bowgpu_rolling_interpolate(bowgpu_rolling *r, const int32_t *
     for (int j = 0; j < ncols; ++j) of->cols[j].dtype = f->cols[j].dtype;
     auto bail = [&](int32_t code) {
         cudaStreamSynchronize(ctx->stream);
-        for (auto &c : of->cols) free_col(c);
+        for (auto &c : of->cols) free_col(ctx, c);
         delete of;
         return code;
     };
@@ -1126,20 +1159,35 @@ extern "C" int32_t bowgpu_rolling_interpolate(bowgpu_rolling *r, const int32_t *
     }
     cudaEvent_t e0, e1;
     timing_main_pair(ctx, &e0, &e1);
-    e = launch_interp_gather(L, total, ctx->sm_count, ctx->stream, e0, e1);
-    count_launch(ctx, 1);
+    // the tile -> window table lives in its own pool block: the arena may not grow while its buffers are in use
+    int64_t *tile_k = nullptr;
+    if (total > 0 && pool_alloc(ctx, (void **)&tile_k, (size_t)(interp_gather_tiles(total) + 1) * 8) != cudaSuccess)
+        return bail(fail(ctx, BOWGPU_ENOMEM, "interpolate: tile table"));
+    e = launch_interp_gather(L, total, tile_k, ctx->stream, e0, e1);
+    pool_free(ctx, tile_k);
+    count_launch(ctx, 2);
     count_launch(ctx, 1, true);
     timing_end(ctx);
     if (e) return bail(fail(ctx, BOWGPU_ECUDA, "interpolate (gather): %s", cudaGetErrorString((cudaError_t)e)));
-    for (int j = 0; j < ncols; ++j) {  // bitmaps without nulls are dropped (the aggregation kernels run faster)
-        DevCol &c = of->cols[j];
-        if (!c.validity) continue;
-        rc = count_nulls(ctx, c, total);
-        if (rc) return bail(rc);
-        if (c.null_count == 0) {
-            cudaFree(c.validity);
-            c.validity = nullptr;
-            c.own_validity = false;
+    {  // bitmaps without nulls are dropped (the aggregation kernels run faster): one popcount per column, one copy
+        unsigned long long *d_cnt = nullptr, h_cnt[INTERP_MAX_COLS];
+        if (pool_alloc(ctx, (void **)&d_cnt, sizeof h_cnt) != cudaSuccess) return bail(fail(ctx, BOWGPU_ENOMEM, "interpolate: counters"));
+        cudaMemsetAsync(d_cnt, 0, sizeof h_cnt, ctx->stream);
+        for (int j = 0; j < ncols; ++j)
+            if (of->cols[j].validity) launch_bitmap_popcount(of->cols[j].validity, total, d_cnt + j, ctx->stream);
+        cudaError_t ce = cudaMemcpyAsync(h_cnt, d_cnt, sizeof h_cnt, cudaMemcpyDeviceToHost, ctx->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+        pool_free(ctx, d_cnt);
+        if (ce != cudaSuccess) return bail(fail(ctx, BOWGPU_ECUDA, "interpolate (null counts): %s", cudaGetErrorString(ce)));
+        for (int j = 0; j < ncols; ++j) {
+            DevCol &c = of->cols[j];
+            if (!c.validity) continue;
+            c.null_count = total - (int64_t)h_cnt[j];
+            if (c.null_count == 0) {
+                pool_free(ctx, c.validity);
+                c.validity = nullptr;
+                c.own_validity = false;
+            }
         }
     }
     rc = check_status(ctx);

@@ -22,7 +22,37 @@ constexpr int BND_STAGE_BYTES = BndG::TIME_BYTES;
 constexpr int BND_HEADER_BYTES = 128;
 constexpr int BND_STAGES = 4;
 
-__global__ void __launch_bounds__(BND_NT, 4) bounds_kernel(const BoundsLaunch P, const int64_t ntiles) {
+// Rolled, out-of-line walk over the rows of ONE thread that holds at least one window start (or row 0, the
+// last row, or rows before s0).  Kept out of the unrolled fast path: most threads of most tiles see no window
+// start at all (long windows), and the fast path must stay small enough to live in the instruction cache.
+__device__ __noinline__ void bounds_walk(const BoundsLaunch &P, const int64_t *trow /* my first row in smem */,
+                                          int64_t row0 /* its global index */, int nmine /* rows I own */,
+                                          bool has_next /* the row after my last one exists */) {
+    const WindowGeom &g = P.g;
+    const uint64_t d = g.div.d, Wu = (uint64_t)g.W;
+    auto xrel = [&](int j) -> uint64_t {  // rows before s0 (left halo / negative timestamps) collapse onto window 0
+        return row0 + j < g.early_rows ? 0 : (uint64_t)trow[j] - (uint64_t)g.s0;
+    };
+    uint64_t kcur = div_u64(xrel(0), g.div);
+    uint64_t erel = (kcur + 1) * d;
+    if (row0 == 0)  // owner of row 0 (kcur > 0 only for a shard with leading empty windows)
+        for (uint64_t k = 0; k <= kcur && k <= Wu; ++k) P.first[k] = g.shard ? g.early_rows : 0;
+    const int nsteps = has_next ? nmine : nmine - 1;
+    for (int j = 0; j < nsteps; ++j) {
+        const uint64_t xn = xrel(j + 1);
+        if (xn >= erel) {  // row j+1 starts window knew; windows kcur+1..knew begin there
+            const uint64_t knew = xn - erel < d ? kcur + 1 : div_u64(xn, g.div);
+            const int64_t row = row0 + j + 1;
+            for (uint64_t k = kcur + 1; k <= knew && k <= Wu; ++k) P.first[k] = row;
+            kcur = knew;
+            erel = (kcur + 1) * d;
+        }
+    }
+    if (!has_next)  // owner of the last row: trailing (empty) windows end at n
+        for (uint64_t k = kcur + 1; k <= Wu; ++k) P.first[k] = g.n;
+}
+
+__global__ void __launch_bounds__(BND_NT, 4) bounds_kernel(const __grid_constant__ BoundsLaunch P, const int64_t ntiles) {
     using G = BndG;
     constexpr int R = G::R;
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -30,7 +60,6 @@ __global__ void __launch_bounds__(BND_NT, 4) bounds_kernel(const BoundsLaunch P,
     uint8_t *stages = smem_raw + BND_HEADER_BYTES;
     const int tid = threadIdx.x;
     const WindowGeom &g = P.g;
-    const uint64_t d = g.div.d;
     TileSrc src{P.time, nullptr, nullptr, g.n};
 
     if (tid == 0) {
@@ -53,44 +82,36 @@ __global__ void __launch_bounds__(BND_NT, 4) bounds_kernel(const BoundsLaunch P,
         const int64_t r0 = tile * G::T;
         const int64_t nrem = g.n - r0;
         const int ti0 = tid * R;
-        const bool early_tile = r0 < g.early_rows;
-        auto xrel = [&](int64_t x, int64_t ti) -> uint64_t {
-            if (early_tile && r0 + ti < g.early_rows) return 0;
-            return (uint64_t)x - (uint64_t)g.s0;
-        };
         if (ti0 < nrem) {
+            const bool whole = ti0 + R < nrem;  // my R rows and the row after them exist
+            const int nmine = whole ? R : (int)(nrem - ti0);
             int64_t x[R + 1];
 #pragma unroll
-            for (int j = 0; j <= R; ++j) x[j] = tsm[ti0 + 2 + j];
-            if (r0 + ti0 > 0) bad |= x[0] < tsm[ti0 + 1];
+            for (int j = 0; j <= R; ++j) x[j] = tsm[ti0 + G::HALO + j];
+            if (r0 + ti0 > 0) bad |= x[0] < tsm[ti0 + G::HALO - 1];
 #pragma unroll
             for (int j = 1; j < R; ++j)
-                if (ti0 + j < nrem) bad |= x[j] < x[j - 1];
-            uint64_t kcur = div_u64(xrel(x[0], ti0), g.div);
-            uint64_t erel = (kcur + 1) * d;
-            const uint64_t Wu = (uint64_t)g.W;
-            if (r0 + ti0 == 0)  // owner of row 0 (kcur > 0 only for a shard with leading empty windows)
-                for (uint64_t k = 0; k <= kcur && k <= Wu; ++k) P.first[k] = g.shard ? g.early_rows : 0;
+                if (whole || j < nmine) bad |= x[j] < x[j - 1];
+            // Sorted rows: a window starts inside (x[0], x[R]] iff x[R] lies at or beyond the end of x[0]'s window.
+            // The common cases - no start, or exactly one start of the very next window - are handled branch-free
+            // here; empty windows in between, several starts, tile / column edges and halo rows take the walk.
+            bool walk = !whole || r0 + ti0 == 0 || r0 + ti0 < g.early_rows;
+            if (!walk) {
+                const uint64_t rel0 = (uint64_t)x[0] - (uint64_t)g.s0;
+                const uint64_t kf = div_u64(rel0, g.div);
+                const uint64_t erel = (kf + 1) * g.div.d;
+                const uint64_t relR = (uint64_t)x[R] - (uint64_t)g.s0;
+                if (relR >= erel) {
+                    walk = relR - erel >= g.div.d;  // x[R] is beyond window kf+1: more than one start (or empty windows)
+                    if (!walk) {
+                        int before = 0;  // rows among x[1..R] that still belong to window kf (monotone predicate)
 #pragma unroll
-            for (int j = 0; j < R; ++j) {
-                if (ti0 + j + 1 < nrem) {
-                    const uint64_t xn = xrel(x[j + 1], ti0 + j + 1);
-                    if (xn >= erel) {  // row j+1 starts window knew; windows kcur+1..knew begin there
-                        uint64_t knew;
-                        if (xn - erel < d) {
-                            knew = kcur + 1;
-                        } else {
-                            knew = div_u64(xn, g.div);
-                        }
-                        const int64_t row = r0 + ti0 + j + 1;
-                        for (uint64_t k = kcur + 1; k <= knew && k <= Wu; ++k) P.first[k] = row;
-                        kcur = knew;
-                        erel = (kcur + 1) * d;
+                        for (int j = 1; j <= R; ++j) before += (uint64_t)x[j] - (uint64_t)g.s0 < erel;
+                        if (kf + 1 <= (uint64_t)g.W) P.first[kf + 1] = r0 + ti0 + before + 1;
                     }
-                } else if (ti0 + j + 1 == nrem) {  // owner of the last row: trailing (empty) windows end at n
-                    for (uint64_t k = kcur + 1; k <= Wu; ++k) P.first[k] = g.n;
                 }
             }
+            if (walk) bounds_walk(P, tsm + ti0 + G::HALO, r0 + ti0, nmine, whole);
         }
         __syncthreads();
         if (tid == 0) {

@@ -46,6 +46,16 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  : "memory");
 }
 
+// global -> shared 2-D tiled TMA copy (cp.async.bulk.tensor, SASS UTMALDG): box of the tensor map at element
+// coordinates (c0 = innermost, c1); the whole box (out-of-bounds parts zero filled) counts towards complete_tx
+__device__ __forceinline__ void tma_box_2d(void *dst_smem, const void *tmap, int32_t c0, int32_t c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+
 // ---- exact floor(x / d) for uint64 x and a launch-constant divisor d -------------------------
 // Two rounds of a round-toward-zero double estimate (never above the true quotient) followed by a
 // short correction loop.  inv_rd must be the double just below 1.0/d (host: nextafter(1.0/d, 0)).

@@ -20,16 +20,18 @@ struct EpiBatch {
 
 // One thread per window, looping over the specs of the batch: the per-window counts shared by the
 // aggregations of one input column are fetched from DRAM once (repeats hit L1).
-__global__ void __launch_bounds__(256) epilogue_kernel(const EpiBatch B, const int nspecs, const WindowGeom g) {
+template <int NS>
+__global__ void __launch_bounds__(256) epilogue_kernel(const __grid_constant__ EpiBatch B, const int nspecs,
+                                                       const WindowGeom g) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = k < g.W;
     const int lane = threadIdx.x & 31;
     // phase 1: every global read of this window, all in flight together (the pass is latency bound otherwise)
-    int64_t cv[EPI_MAX];
-    double sv[EPI_MAX];
-    uint8_t okv[EPI_MAX];
+    int64_t cv[NS];
+    double sv[NS];
+    uint8_t okv[NS];
 #pragma unroll
-    for (int si = 0; si < EPI_MAX; ++si) {
+    for (int si = 0; si < NS; ++si) {
         cv[si] = 0;
         sv[si] = 0.0;
         okv[si] = 0;
@@ -41,7 +43,7 @@ __global__ void __launch_bounds__(256) epilogue_kernel(const EpiBatch B, const i
         }
     }
 #pragma unroll
-    for (int si = 0; si < EPI_MAX; ++si) {
+    for (int si = 0; si < NS; ++si) {
         if (si >= nspecs) break;
         const EpilogueSpec &sp = B.s[si];
         bool valid = false;
@@ -96,7 +98,13 @@ int launch_epilogue(const EpilogueSpec *specs, int nspecs, WindowGeom g, cudaStr
         EpiBatch B;
         const int m = nspecs - b < EPI_MAX ? nspecs - b : EPI_MAX;
         for (int i = 0; i < m; ++i) B.s[i] = specs[b + i];
-        epilogue_kernel<<<(unsigned)((g.W + nt - 1) / nt), nt, 0, stream>>>(B, m, g);
+        const unsigned grid = (unsigned)((g.W + nt - 1) / nt);
+        if (m <= 4)
+            epilogue_kernel<4><<<grid, nt, 0, stream>>>(B, m, g);
+        else if (m <= 8)
+            epilogue_kernel<8><<<grid, nt, 0, stream>>>(B, m, g);
+        else
+            epilogue_kernel<EPI_MAX><<<grid, nt, 0, stream>>>(B, m, g);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
     }

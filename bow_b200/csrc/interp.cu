@@ -203,11 +203,20 @@ __global__ void interp_fix_wsrc(const int64_t *off, int64_t *wsrc, int64_t W) {
 }
 
 // ---- gather -----------------------------------------------------------------------------------------------
-constexpr int GA_NT = 256, GA_ROWS = 8, GA_TILE = GA_NT * GA_ROWS;  // output rows per CTA iteration
+constexpr int GA_NT = 256, GA_ROWS = 8, GA_TILE = GA_NT * GA_ROWS;  // output rows per CTA
 constexpr int GA_CAP = GA_TILE + 4;                                   // windows overlapping one tile
 
-__device__ __forceinline__ int64_t upper_bound_minus1(const int64_t *off, int64_t lo, int64_t hi, int64_t o) {
-    // last k in [lo, hi) with off[k] <= o   (off[lo] <= o is guaranteed by the caller)
+// tile_k[t] = last window k with off[k] <= t * GA_TILE  (t < ntiles); tile_k[ntiles] = W - 1.
+// One thread per tile: the searches run in parallel here instead of serialising at the head of every gather CTA.
+__global__ void interp_tile_windows(const int64_t *off, int64_t W, int64_t ntiles, int64_t *tile_k) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > ntiles) return;
+    if (t == ntiles) {
+        tile_k[t] = W - 1;
+        return;
+    }
+    const int64_t o = t * GA_TILE;
+    int64_t lo = 0, hi = W;  // off[0] = 0 <= o
     while (hi - lo > 1) {
         const int64_t mid = lo + ((hi - lo) >> 1);
         if (off[mid] <= o)
@@ -215,77 +224,88 @@ __device__ __forceinline__ int64_t upper_bound_minus1(const int64_t *off, int64_
         else
             hi = mid;
     }
-    return lo;
+    tile_k[t] = lo;
 }
 
-__global__ void __launch_bounds__(GA_NT) interp_gather_kernel(const InterpLaunch P, const int64_t n_out,
-                                                               const int64_t ntiles) {
+// One CTA per tile of GA_TILE output rows.  Row o of the output comes from input row o + shift(window of o), or is
+// the synthetic start row of its window.  Loads of a column (GA_ROWS per thread, coalesced across the warp) are all
+// issued before the first store, 4 CTAs per SM keep ~64 KB per SM in flight.
+__global__ void __launch_bounds__(GA_NT, 4)
+    interp_gather_kernel(const __grid_constant__ InterpLaunch P, const int64_t n_out, const int64_t *__restrict__ tile_k) {
     __shared__ int64_t s_off[GA_CAP];
     __shared__ int64_t s_src[GA_CAP];
-    __shared__ int64_t s_k[2];
     const int tid = threadIdx.x, lane = tid & 31;
-    const int64_t W = P.g.W;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t o0 = tile * GA_TILE;
-        const int64_t o1 = o0 + GA_TILE < n_out ? o0 + GA_TILE : n_out;
-        if (tid < 2) s_k[tid] = upper_bound_minus1(P.off, 0, W, tid == 0 ? o0 : o1 - 1);
-        __syncthreads();
-        const int64_t k_lo = s_k[0], k_hi = s_k[1];
-        // m <= GA_TILE + 2: every window but one (an empty window starting at -1, interpolation.go:119,128)
-        // emits at least one row; clamp anyway so shared memory can never be overrun
-        int m = (int)((k_hi - k_lo + 1) < (int64_t)GA_CAP ? (k_hi - k_lo + 1) : (int64_t)GA_CAP);
-        for (int i = tid; i < m; i += GA_NT) {
-            s_off[i] = P.off[k_lo + i];
-            s_src[i] = P.wsrc[k_lo + i];
+    const int64_t tile = blockIdx.x;
+    const int64_t o0 = tile * GA_TILE;
+    const int64_t k_lo = tile_k[tile], k_hi = tile_k[tile + 1];
+    // m <= GA_TILE + 2: every window but one (an empty window starting at -1, interpolation.go:119,128)
+    // emits at least one row; clamp anyway so shared memory can never be overrun
+    const int m = (int)((k_hi - k_lo + 1) < (int64_t)GA_CAP ? (k_hi - k_lo + 1) : (int64_t)GA_CAP);
+    for (int i = tid; i < m; i += GA_NT) {
+        s_off[i] = P.off[k_lo + i];
+        s_src[i] = P.wsrc[k_lo + i];
+    }
+    __syncthreads();
+    int64_t src[GA_ROWS];  // >= 0: input row; -1 - k: synthetic row of window k; INT64_MIN: past the end
+    bool any_syn = false;
+#pragma unroll
+    for (int i = 0; i < GA_ROWS; ++i) {
+        const int64_t o = o0 + tid + (int64_t)i * GA_NT;
+        src[i] = INT64_MIN;
+        if (o < n_out) {
+            int lo = 0, hi = m;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_off[mid] <= o)
+                    lo = mid;
+                else
+                    hi = mid;
+            }
+            const int64_t v = s_src[lo];
+            const bool syn = (v & 1) && o == s_off[lo];
+            src[i] = syn ? -1 - (k_lo + lo) : o + (v >> 1);
+            any_syn |= syn;
         }
-        __syncthreads();
-        int64_t src[GA_ROWS];  // >= 0: input row; -1 - k: synthetic row of window k; INT64_MIN: past the end
+    }
+    const bool full = o0 + GA_TILE <= n_out;
+    const int ncols = P.ncols;
+    for (int j = 0; j < ncols; ++j) {
+        const uint64_t *__restrict__ vin = P.cols[j].values;
+        const uint32_t *__restrict__ bin = P.cols[j].validity;
+        uint64_t *__restrict__ vout = P.cols[j].out_values;
+        uint32_t *__restrict__ bout = P.cols[j].out_validity;
+        uint64_t val[GA_ROWS];
+        uint32_t okm = 0;
+#pragma unroll
+        for (int i = 0; i < GA_ROWS; ++i) {
+            const int64_t sr = src[i];
+            val[i] = 0;
+            if (sr >= 0) {
+                val[i] = vin[sr];
+                const uint32_t w = bin ? bin[sr >> 5] : 0xFFFFFFFFu;
+                okm |= ((w >> (sr & 31)) & 1u) << i;
+            }
+        }
+        if (any_syn) {  // at most one row per window; out of the streaming path
+#pragma unroll
+            for (int i = 0; i < GA_ROWS; ++i) {
+                const int64_t sr = src[i];
+                if (sr < 0 && sr != INT64_MIN) {
+                    const int64_t k = -1 - sr;
+                    val[i] = P.cols[j].syn_val[k];
+                    okm |= (uint32_t)(P.cols[j].syn_ok[k] != 0) << i;
+                }
+            }
+        }
 #pragma unroll
         for (int i = 0; i < GA_ROWS; ++i) {
             const int64_t o = o0 + tid + (int64_t)i * GA_NT;
-            src[i] = INT64_MIN;
-            if (o < n_out) {
-                int lo = 0, hi = m;
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (s_off[mid] <= o)
-                        lo = mid;
-                    else
-                        hi = mid;
-                }
-                const int64_t v = s_src[lo];
-                src[i] = ((v & 1) && o == s_off[lo]) ? -1 - (k_lo + lo) : o + (v >> 1);
+            if (full || o < n_out) vout[o] = val[i];
+            if (bout) {
+                const uint32_t ball = __ballot_sync(0xffffffffu, (okm >> i) & 1u);
+                if (lane == 0 && (full || o < n_out)) bout[o >> 5] = ball;
             }
         }
-        for (int j = 0; j < P.ncols; ++j) {
-            const InterpCol &c = P.cols[j];
-            uint64_t val[GA_ROWS];
-            bool ok[GA_ROWS];
-#pragma unroll
-            for (int i = 0; i < GA_ROWS; ++i) {
-                const int64_t s = src[i];
-                val[i] = 0;
-                ok[i] = false;
-                if (s >= 0) {
-                    val[i] = c.values[s];
-                    ok[i] = c.validity ? ((c.validity[s >> 5] >> (s & 31)) & 1u) : true;
-                } else if (s != INT64_MIN) {
-                    const int64_t k = -1 - s;
-                    val[i] = c.syn_val[k];
-                    ok[i] = c.syn_ok[k] != 0;
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < GA_ROWS; ++i) {
-                const int64_t o = o0 + tid + (int64_t)i * GA_NT;
-                if (o < n_out) c.out_values[o] = val[i];
-                if (c.out_validity) {
-                    const uint32_t ball = __ballot_sync(0xffffffffu, ok[i]);
-                    if (lane == 0 && o < n_out) c.out_validity[o >> 5] = ball;
-                }
-            }
-        }
-        __syncthreads();
     }
 }
 
@@ -309,20 +329,21 @@ int launch_exclusive_scan(int64_t *data, int64_t n, int64_t *scratch, cudaStream
     return (int)cudaGetLastError();
 }
 
-int launch_interp_gather(const InterpLaunch &L, int64_t n_out, int sm_count, cudaStream_t stream, cudaEvent_t e0,
+int launch_interp_gather(const InterpLaunch &L, int64_t n_out, int64_t *tile_k, cudaStream_t stream, cudaEvent_t e0,
                          cudaEvent_t e1) {
     if (L.g.W > 0) {
         const int nt = 256;
         interp_fix_wsrc<<<(unsigned)((L.g.W + nt - 1) / nt), nt, 0, stream>>>(L.off, L.wsrc, L.g.W);
     }
     if (n_out <= 0) return (int)cudaGetLastError();
-    const int64_t ntiles = (n_out + GA_TILE - 1) / GA_TILE;
-    int64_t grid = (int64_t)sm_count * 4;
-    if (grid > ntiles) grid = ntiles;
+    const int64_t ntiles = interp_gather_tiles(n_out);
+    interp_tile_windows<<<(unsigned)((ntiles + 1 + 255) / 256), 256, 0, stream>>>(L.off, L.g.W, ntiles, tile_k);
     if (e0) cudaEventRecord(e0, stream);
-    interp_gather_kernel<<<(unsigned)grid, GA_NT, 0, stream>>>(L, n_out, ntiles);
+    interp_gather_kernel<<<(unsigned)ntiles, GA_NT, 0, stream>>>(L, n_out, tile_k);
     if (e1) cudaEventRecord(e1, stream);
     return (int)cudaGetLastError();
 }
+
+int64_t interp_gather_tiles(int64_t n_out) { return (n_out + GA_TILE - 1) / GA_TILE; }
 
 }  // namespace bowgpu

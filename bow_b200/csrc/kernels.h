@@ -32,7 +32,7 @@ struct alignas(16) BasicCarry {
     double sum;
     double mn, mx;
     uint64_t first, last;  // raw bits of first / last valid value
-    uint64_t _pad;
+    int64_t edge_t;        // head records: time of the tile's first row; tail records: of its last row
 };
 
 struct BasicOut {  // per-window outputs of one input column (any pointer may be null)
@@ -132,7 +132,9 @@ int launch_interp_windows(const InterpLaunch &L, cudaStream_t stream);
 size_t scan_scratch_bytes(int64_t n);
 // exclusive scan in place; data[n] receives the total
 int launch_exclusive_scan(int64_t *data, int64_t n, int64_t *scratch, cudaStream_t stream);
-int launch_interp_gather(const InterpLaunch &L, int64_t n_out, int sm_count, cudaStream_t stream, cudaEvent_t e0,
+int64_t interp_gather_tiles(int64_t n_out);
+// tile_k: scratch of interp_gather_tiles(n_out) + 1 int64
+int launch_interp_gather(const InterpLaunch &L, int64_t n_out, int64_t *tile_k, cudaStream_t stream, cudaEvent_t e0,
                          cudaEvent_t e1);
 
 // ---- per-window epilogue (validity bitmaps, defaults of empty windows, WindowStart, Factor) -----

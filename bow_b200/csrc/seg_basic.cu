@@ -21,13 +21,12 @@ namespace bowgpu {
 namespace {
 
 constexpr int64_t CLOSED_BIT = (int64_t)1 << 62;
-static_assert(SegG::T < 4096, "cnt / fi are packed in 12 bits each");
 
-// state of a run of rows; meta = cnt | fi << 12 (tile-relative first valid row), li = last valid row
+// state of a run of rows
 struct BState {
     double sum, mn, mx;
-    uint32_t meta;
-    uint32_t li;
+    uint64_t first, last;  // raw bits of the first / last valid value (maintained only when the ops need them)
+    uint32_t cnt;          // valid rows
 };
 
 // Final per-window write (values only; validity bitmaps, the mean division and empty-window defaults
@@ -55,9 +54,10 @@ struct BasicPol {
     using Out = BasicOut;
     struct Inc {};
     static constexpr bool NEXT_VALUE = false;
+    // Min/Max of a float column start from the FIRST valid value (a leading NaN is sticky): keep its bits
+    static constexpr bool NEED_FIRST = (OPS & OPS_FIRSTLAST) || ((OPS & OPS_MINMAX) && !IS_INT);
+    static constexpr bool NEED_LAST = (OPS & OPS_FIRSTLAST) != 0;
 
-    static __device__ __forceinline__ uint32_t cnt(const State &s) { return s.meta & 0xFFFu; }
-    static __device__ __forceinline__ uint32_t fi(const State &s) { return s.meta >> 12; }
     static __device__ __forceinline__ Inc make_inc(bool, bool, uint64_t, int64_t) { return Inc(); }
 
     static __device__ __forceinline__ State identity() {
@@ -65,8 +65,8 @@ struct BasicPol {
         s.sum = 0.0;
         s.mn = CUDART_INF;
         s.mx = -CUDART_INF;
-        s.meta = 0;
-        s.li = 0;
+        s.first = s.last = 0;
+        s.cnt = 0;
         return s;
     }
     static __device__ __forceinline__ void accumulate(State &s, int64_t, uint64_t raw) {
@@ -77,12 +77,14 @@ struct BasicPol {
             if (v > s.mx) s.mx = v;
         }
     }
-    // cnt / fi / li of the rows selected by `mask` (bit j = row ti0 + j of the tile)
-    static __device__ __forceinline__ void set_meta(State &s, uint32_t mask, int ti0) {
-        const uint32_t c = __popc(mask);
-        const uint32_t f = mask ? (uint32_t)(ti0 + __ffs(mask) - 1) : 0u;
-        s.meta = c | (f << 12);
-        s.li = mask ? (uint32_t)(ti0 + 31 - __clz(mask)) : 0u;
+    // cnt / first / last cost nothing per row: popcount / ffs / fls of the validity bits of the rows of one phase
+    // that joined the run (bit j of mask = row j of the thread's phase, vrow = its values in shared memory)
+    static __device__ __forceinline__ void note(State &s, uint32_t mask, const uint64_t *vrow) {
+        if (mask) {
+            if (NEED_FIRST && s.cnt == 0) s.first = vrow[__ffs(mask) - 1];
+            if (NEED_LAST) s.last = vrow[31 - __clz(mask)];
+            s.cnt += __popc(mask);
+        }
     }
     static __device__ __forceinline__ State combine(const State &L, const State &R) {
         State o;
@@ -91,9 +93,9 @@ struct BasicPol {
             o.mn = (R.mn < L.mn) ? R.mn : L.mn;
             o.mx = (R.mx > L.mx) ? R.mx : L.mx;
         }
-        const uint32_t lc = L.meta & 0xFFFu, rc = R.meta & 0xFFFu;
-        o.meta = (lc + rc) | ((lc ? L.meta : R.meta) & 0xFFF000u);
-        if (OPS & OPS_FIRSTLAST) o.li = rc ? R.li : L.li;
+        if (NEED_FIRST) o.first = L.cnt ? L.first : R.first;
+        if (NEED_LAST) o.last = R.cnt ? R.last : L.last;
+        o.cnt = L.cnt + R.cnt;
         return o;
     }
     static __device__ __forceinline__ State shfl_up(const State &s, int d) {
@@ -103,76 +105,45 @@ struct BasicPol {
             o.mn = __shfl_up_sync(0xffffffffu, s.mn, d);
             o.mx = __shfl_up_sync(0xffffffffu, s.mx, d);
         }
-        o.meta = __shfl_up_sync(0xffffffffu, s.meta, d);
-        if (OPS & OPS_FIRSTLAST) o.li = __shfl_up_sync(0xffffffffu, s.li, d);
+        if (NEED_FIRST) o.first = __shfl_up_sync(0xffffffffu, (unsigned long long)s.first, d);
+        if (NEED_LAST) o.last = __shfl_up_sync(0xffffffffu, (unsigned long long)s.last, d);
+        o.cnt = __shfl_up_sync(0xffffffffu, s.cnt, d);
         return o;
     }
     static __device__ __forceinline__ void write(const Out &o, const WindowGeom &g, int64_t k, const State &s,
-                                                 const Inc &, const uint64_t *vsm) {
-        const uint32_t c = cnt(s);
-        const uint64_t fb = c ? vsm[fi(s)] : 0, lb = c ? vsm[s.li] : 0;
-        write_window<IS_INT>(o, g.W, k, c, s.sum, s.mn, s.mx, fb, lb);
+                                                 const Inc &) {
+        write_window<IS_INT>(o, g.W, k, s.cnt, s.sum, s.mn, s.mx, s.first, s.last);
     }
-    static __device__ __forceinline__ Carry make_carry(const State &s, const Inc &, const uint64_t *vsm, int64_t key,
-                                                       bool closed) {
-        const uint32_t c = cnt(s);
+    static __device__ __forceinline__ Carry make_carry(const State &s, const Inc &, int64_t key, bool closed) {
         Carry r;
         r.key = key;
-        r.cnt = (int64_t)c | (closed ? CLOSED_BIT : 0);
+        r.cnt = (int64_t)s.cnt | (closed ? CLOSED_BIT : 0);
         r.sum = s.sum;
         r.mn = s.mn;
         r.mx = s.mx;
-        r.first = c ? vsm[fi(s)] : 0;
-        r.last = c ? vsm[s.li] : 0;
-        r._pad = 0;
+        r.first = s.first;
+        r.last = s.last;
+        r.edge_t = 0;
         return r;
     }
     static __device__ __forceinline__ void carry_set_key(Carry &c, int64_t key) { c.key = key; }
+    static __device__ __forceinline__ void carry_set_edge(Carry &c, int64_t t, uint64_t, bool) { c.edge_t = t; }
+    static __device__ __forceinline__ int64_t carry_edge_t(const Carry &c) { return c.edge_t; }
     static __device__ __forceinline__ int64_t carry_key(const Carry &c) { return c.key; }
     static __device__ __forceinline__ bool carry_closed(const Carry &c) { return (c.cnt & CLOSED_BIT) != 0; }
+    static __device__ __forceinline__ void carry_inc_from_edge(Carry &, const Carry &, int64_t) {}
+    static __device__ __forceinline__ void carry_clear_inc(Carry &) {}
     static __device__ __forceinline__ void carry_combine(Carry &a, const Carry &h) {
-        const int64_t hc = h.cnt & ~CLOSED_BIT;
+        const int64_t ac = a.cnt & ~CLOSED_BIT, hc = h.cnt & ~CLOSED_BIT;
         a.sum = a.sum + h.sum;
         a.mn = (h.mn < a.mn) ? h.mn : a.mn;
         a.mx = (h.mx > a.mx) ? h.mx : a.mx;
-        a.first = a.cnt ? a.first : h.first;
+        a.first = ac ? a.first : h.first;
         a.last = hc ? h.last : a.last;
-        a.cnt += hc;
+        a.cnt = ac + hc;
     }
     static __device__ __forceinline__ void write_carry(const Out &o, const WindowGeom &g, int64_t k, const Carry &a) {
-        write_window<IS_INT>(o, g.W, k, a.cnt, a.sum, a.mn, a.mx, a.first, a.last);
-    }
-    // Windows that begin AND end strictly inside one thread's rows (only when windows are shorter than
-    // R rows): rows (jfirst, jlast] of the thread are re-reduced window by window from shared memory in
-    // a rolled loop and written out directly.  Kept out of line so the unrolled fast path stays small.
-    static __device__ __noinline__ void middle(const Out *outp, int64_t W, int64_t s0, uint64_t d, double inv_rd,
-                                               const int64_t *trow, const uint64_t *vrow, uint32_t vbits, int jfirst,
-                                               int jlast, int /*nexist*/) {
-        const Out o = *outp;
-        State st = identity();
-        uint32_t seg = 0;  // valid rows of the current window
-        uint64_t kcur = div_slow((uint64_t)trow[jfirst + 1] - (uint64_t)s0, d, inv_rd);
-        uint64_t erel = (kcur + 1) * d;
-        for (int j = jfirst + 1; j <= jlast; ++j) {
-            if ((vbits >> j) & 1u) {
-                accumulate(st, 0, vrow[j]);
-                seg |= 1u << j;
-            }
-            const uint64_t xn = (uint64_t)trow[j + 1] - (uint64_t)s0;
-            if (j == jlast || xn >= erel) {
-                const uint64_t fb = seg ? vrow[__ffs(seg) - 1] : 0, lb = seg ? vrow[31 - __clz(seg)] : 0;
-                write_window<IS_INT>(o, W, (int64_t)kcur, __popc(seg), st.sum, st.mn, st.mx, fb, lb);
-                st = identity();
-                seg = 0;
-                if (xn - erel < d) {
-                    ++kcur;
-                    erel += d;
-                } else {
-                    kcur = div_slow(xn, d, inv_rd);
-                    erel = (kcur + 1) * d;
-                }
-            }
-        }
+        write_window<IS_INT>(o, g.W, k, a.cnt & ~CLOSED_BIT, a.sum, a.mn, a.mx, a.first, a.last);
     }
 };
 
@@ -203,7 +174,7 @@ int launch_ops(const SegLaunch &L, int sm, cudaStream_t s, cudaEvent_t e0, cudaE
 
 }  // namespace
 
-int64_t seg_num_tiles(int64_t n) { return (n + SegG::T - 1) / SegG::T; }
+int64_t seg_num_tiles(int64_t n) { return (n + SEG_T - 1) / SEG_T; }
 size_t seg_carry_bytes(int64_t n) { return (size_t)seg_num_tiles(n) * 2 * sizeof(BasicCarry); }
 
 int launch_segreduce_basic(const SegLaunch &L, int sm_count, cudaStream_t stream, cudaEvent_t e0, cudaEvent_t e1) {

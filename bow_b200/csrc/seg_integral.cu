@@ -29,8 +29,12 @@ struct alignas(16) ICarry {
     double fT, fV, lT, lV, sS, sT;
     double incV, incT;
     int64_t inc_has;
-    int64_t _pad;
+    int64_t edge_t;       // head records: first row of the tile (time, raw value bits, validity);
+    uint64_t edge_raw;    // tail records: edge_t = time of the tile's last row
+    int64_t edge_valid;
+    int64_t _pad[2];
 };
+static_assert(sizeof(ICarry) == 128, "carry record layout");
 constexpr int64_t I_CLOSED_BIT = (int64_t)1 << 62;
 
 template <bool STEP, bool TRAP, bool IS_INT>
@@ -75,7 +79,7 @@ struct IntegralPol {
         s.lV = v;
         s.n += 1;
     }
-    static __device__ __forceinline__ void set_meta(State &, uint32_t, int) {}
+    static __device__ __forceinline__ void note(State &, uint32_t, const uint64_t *) {}
     static __device__ __forceinline__ State combine(const State &L, const State &R) {
         State o;
         const bool l = L.n != 0, r = R.n != 0;
@@ -123,11 +127,10 @@ struct IntegralPol {
         }
     }
     static __device__ __forceinline__ void write(const Out &o, const WindowGeom &g, int64_t k, const State &s,
-                                                 const Inc &inc, const uint64_t *) {
+                                                 const Inc &inc) {
         finish(o, g.W, g.s0, g.div.d, k, s.n, s.lT, s.lV, s.sS, s.sT, TRAP && inc.has, inc.v, inc.T);
     }
-    static __device__ __forceinline__ Carry make_carry(const State &s, const Inc &inc, const uint64_t *, int64_t key,
-                                                       bool closed) {
+    static __device__ __forceinline__ Carry make_carry(const State &s, const Inc &inc, int64_t key, bool closed) {
         Carry c;
         c.key = key;
         c.n = (int64_t)s.n | (closed ? I_CLOSED_BIT : 0);
@@ -140,9 +143,25 @@ struct IntegralPol {
         c.incV = inc.v;
         c.incT = inc.T;
         c.inc_has = TRAP && inc.has;
-        c._pad = 0;
+        c.edge_t = 0;
+        c.edge_raw = 0;
+        c.edge_valid = 0;
+        c._pad[0] = c._pad[1] = 0;
         return c;
     }
+    static __device__ __forceinline__ void carry_set_edge(Carry &c, int64_t t, uint64_t raw, bool valid) {
+        c.edge_t = t;
+        c.edge_raw = raw;
+        c.edge_valid = valid;
+    }
+    static __device__ __forceinline__ int64_t carry_edge_t(const Carry &c) { return c.edge_t; }
+    // a window that ends exactly at a tile boundary: its inclusive row, if any, is the next tile's first row
+    static __device__ __forceinline__ void carry_inc_from_edge(Carry &a, const Carry &h, int64_t E) {
+        a.inc_has = TRAP && h.edge_t == E && h.edge_valid;
+        a.incV = val(h.edge_raw);
+        a.incT = (double)h.edge_t;
+    }
+    static __device__ __forceinline__ void carry_clear_inc(Carry &a) { a.inc_has = 0; }
     static __device__ __forceinline__ void carry_set_key(Carry &c, int64_t key) { c.key = key; }
     static __device__ __forceinline__ int64_t carry_key(const Carry &c) { return c.key; }
     static __device__ __forceinline__ bool carry_closed(const Carry &c) { return (c.n & I_CLOSED_BIT) != 0; }
@@ -168,34 +187,7 @@ struct IntegralPol {
         a.incT = h.incT;
     }
     static __device__ __forceinline__ void write_carry(const Out &o, const WindowGeom &g, int64_t k, const Carry &a) {
-        finish(o, g.W, g.s0, g.div.d, k, a.n, a.lT, a.lV, a.sS, a.sT, a.inc_has != 0, a.incV, a.incT);
-    }
-    // windows strictly inside one thread's rows (see BasicPol::middle)
-    static __device__ __noinline__ void middle(const Out *outp, int64_t W, int64_t s0, uint64_t d, double inv_rd,
-                                               const int64_t *trow, const uint64_t *vrow, uint32_t vraw, int jfirst,
-                                               int jlast, int nexist) {
-        const Out o = *outp;
-        State st = identity();
-        uint64_t kcur = div_slow((uint64_t)trow[jfirst + 1] - (uint64_t)s0, d, inv_rd);
-        uint64_t erel = (kcur + 1) * d;
-        for (int j = jfirst + 1; j <= jlast; ++j) {
-            if ((vraw >> j) & 1u) accumulate(st, trow[j], vrow[j]);
-            const bool next_exists = j + 1 < nexist;
-            const uint64_t xn = (uint64_t)trow[j + 1] - (uint64_t)s0;
-            if (j == jlast || xn >= erel) {
-                const bool inc = TRAP && next_exists && xn == erel && ((vraw >> (j + 1)) & 1u);
-                finish(o, W, s0, d, (int64_t)kcur, st.n, st.lT, st.lV, st.sS, st.sT, inc, val(vrow[j + 1]),
-                       (double)trow[j + 1]);
-                st = identity();
-                if (xn - erel < d) {
-                    ++kcur;
-                    erel += d;
-                } else {
-                    kcur = div_slow(xn, d, inv_rd);
-                    erel = (kcur + 1) * d;
-                }
-            }
-        }
+        finish(o, g.W, g.s0, g.div.d, k, a.n & ~I_CLOSED_BIT, a.lT, a.lV, a.sS, a.sT, a.inc_has != 0, a.incV, a.incT);
     }
 };
 
@@ -226,7 +218,7 @@ int launch_mode(const IntLaunch &L, int sm, cudaStream_t s, cudaEvent_t e0, cuda
 
 }  // namespace
 
-size_t integral_carry_bytes(int64_t n) { return (size_t)((n + SegG::T - 1) / SegG::T) * 2 * sizeof(ICarry); }
+size_t integral_carry_bytes(int64_t n) { return (size_t)((n + SEG_T - 1) / SEG_T) * 2 * sizeof(ICarry); }
 
 int launch_segreduce_integral(const IntLaunch &L, int sm_count, cudaStream_t stream, cudaEvent_t e0, cudaEvent_t e1) {
     const bool step = L.out.step != nullptr, trap = L.out.trap != nullptr;

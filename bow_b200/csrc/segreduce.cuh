@@ -6,32 +6,41 @@
 // IntegralStep/IntegralTrapezoid/WeightedAverageStep/WeightedAverageLinear.
 //
 // Work decomposition (load balance independent of window sizes, SURVEY 7 "hard parts"):
-//   * fixed-size ROW tiles (T = NT*R rows) are assigned round-robin to persistent CTAs and staged
-//     into shared memory by TMA bulk copies (tile_pipe.cuh);
-//   * thread t reduces its R consecutive rows sequentially, left to right, exactly like the
-//     reference closure does inside a window.  A window "closes" after row i when row i+1 lies in a
-//     later window; the thread owning row i detects that from its R+1 timestamps by comparing
-//     against a running absolute window end (one exact division per thread and tile, none per row);
-//   * the thread keeps the state of the rows before its first closing (head) and after its last
-//     closing (tail); windows lying strictly inside one thread (windows shorter than R rows) are
-//     handled by an out-of-line rolled loop of the policy;
-//   * partial states of windows spanning several threads are stitched by a warp-shuffle segmented
-//     scan (flags = "a window closed inside this thread") plus a short cross-warp pass;
-//   * partial states of windows spanning several tiles go to per-tile head / tail carry records
-//     and are stitched left to right by a tiny fix-up kernel (deterministic, no atomics).
+//   * fixed-size ROW tiles (T = NT*RE rows, contiguous in memory) are assigned round-robin to persistent
+//     CTAs.  Thread t of the CTA owns the RE = NP*P CONSECUTIVE rows [t*RE, (t+1)*RE) of the tile and
+//     streams through them in NP phases of P = 16 rows, keeping its reduction state in registers.
+//   * staging: per phase ONE 2-D TMA box per column (cp.async.bulk.tensor.2d, SASS UTMALDG) of a tensor
+//     map that views the column as [n/RE][RE] elements: box = [NT rows][P+2 columns] lands in shared
+//     memory as [thread][18] (pitch 144 bytes: 16-byte reads of a quarter warp hit all 32 banks once).
+//     The boxes of the NP phases of a tile interleave inside the same contiguous T*8-byte region of
+//     global memory, so DRAM sees one sequential region per tile; mbarrier-tracked slots give
+//     double buffering at phase granularity.
+//   * inside its rows a thread reduces sequentially, left to right, exactly like the reference closure.
+//     A row whose time reaches the running absolute window end closes the open window (one exact division
+//     per thread and tile, none per row): the first such window of a thread is kept aside (head), later
+//     ones began and ended inside the thread and are written out directly; the rows after the last
+//     boundary are the thread's tail.
+//   * per TILE (not per phase) the tails are stitched: the right-edge boundary of a thread is found by
+//     comparing window indices with the next thread (shuffle), partial states of windows spanning several
+//     threads by a warp-shuffle segmented scan (flag = "a window closed in this thread") plus a short
+//     cross-warp pass;
+//   * every tile leaves a head record (its first window) and a tail record (the window open at its end);
+//     a tiny fix-up kernel joins records of equal window index left to right (deterministic, no atomics).
 //
 // Policy interface (all static, device):
-//   State, Carry, Out, Inc                      types (Inc = what a closing row knows about the row after it)
-//   identity(), accumulate(State&, t, raw), set_meta(State&, mask, ti0), combine(L, R), shfl_up(s, d)
-//   make_inc(at_end, valid_next, raw_next, t_next)   the inclusive row of a window (rolling.go:201-209)
-//   write(out, g, k, state, inc, vsm)           final values of a window that lies inside one tile
-//   make_carry(state, inc, vsm, key, closed)    -> Carry;  carry_key / carry_closed / carry_combine / write_carry
-//   middle(sh_out, W, s0, d, inv_rd, trow, vrow, vraw, jfirst, jlast, nexist)   windows strictly inside one thread's rows
+//   State, Carry, Out, Inc                      types (Inc = the inclusive row of a window, rolling.go:201-209)
+//   identity(), accumulate(State&, t, raw), note(State&, mask, vrow), combine(L, R), shfl_up(s, d)
+//   make_inc(at_end, valid_next, raw_next, t_next)
+//   write(out, g, k, state, inc)                final values of a window
+//   make_carry(state, inc, key, closed) -> Carry; carry_* accessors; write_carry
 #pragma once
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include <cstdlib>
+#include <cstring>
 
 #include "kernels.h"
-#include "tile_pipe.cuh"
 
 namespace bowgpu {
 
@@ -39,19 +48,29 @@ namespace bowgpu {
 #ifndef SEG_CFG_NT
 #define SEG_CFG_NT 128
 #endif
-#ifndef SEG_CFG_R
-#define SEG_CFG_R 17
+#ifndef SEG_CFG_NP
+#define SEG_CFG_NP 4
 #endif
 #ifndef SEG_CFG_CTAS
 #define SEG_CFG_CTAS 3
 #endif
 constexpr int SEG_NT = SEG_CFG_NT;
-constexpr int SEG_R = SEG_CFG_R;
-constexpr int SEG_MAX_STAGES = 8;
-using SegG = TileGeom<SEG_NT, SEG_R>;
+constexpr int SEG_P = 16;                     // rows per phase (box start columns must be 16-byte aligned in global memory)
+constexpr int SEG_NP = SEG_CFG_NP;            // phases per tile
+constexpr int SEG_RE = SEG_P * SEG_NP;        // consecutive rows owned by one thread in a tile
+constexpr int SEG_T = SEG_NT * SEG_RE;        // rows per tile
+constexpr int SEG_COLS = SEG_P + 2;           // box columns (the last two only pad the pitch to 144 bytes)
+constexpr int SEG_BOX_BYTES = SEG_NT * SEG_COLS * 8;
+constexpr int SEG_SLOT_BYTES = 2 * SEG_BOX_BYTES;  // time box + value box
+constexpr int SEG_BITS_BYTES = SEG_T / 8;
+constexpr int SEG_BITS_COPY = SEG_BITS_BYTES + 16;
+constexpr int SEG_BITS_STRIDE = (SEG_BITS_COPY + 127) / 128 * 128;
+constexpr int SEG_MAX_STAGES = 4;
 constexpr int SEG_NW = SEG_NT / 32;
-constexpr int SEG_STAGE_BYTES = SegG::STAGE_BYTES;
-constexpr int SEG_HEADER_BYTES = 1024;
+constexpr int SEG_HEADER_BYTES = 640;
+static_assert((SEG_P * 8) % 16 == 0 && (SEG_COLS * 8) % 16 == 0 && (SEG_COLS * 2) % 8 == 4, "box geometry: 16-byte aligned starts, pitch = odd multiple of 16 bytes");
+static_assert(SEG_T % 128 == 0, "tile validity bytes must be a multiple of 16");
+static_assert(SEG_BOX_BYTES % 128 == 0, "boxes keep every slot 128-byte aligned");
 
 template <class Pol>
 struct SegArgs {
@@ -72,135 +91,200 @@ struct WarpTotal {
     uint32_t _pad;
 };
 
+// first row of a warp's first thread, published for the last lane of the previous warp (and, for warp 0, the
+// first row of the tile for the tile's head record)
+struct WarpEdge {
+    int64_t kf;      // window index of the row
+    int64_t t;
+    uint64_t raw;
+    uint32_t flags;  // bit 0: the thread has rows, bit 1: the row's value is valid
+    uint32_t _pad;
+};
+constexpr uint32_t EDGE_HAS = 1u, EDGE_VALID = 2u;
+
 // exact division on the rare paths
 __device__ __noinline__ static uint64_t div_slow(uint64_t x, uint64_t d, double inv_rd) {
     DivU64 dv{d, inv_rd};
     return div_u64(x, dv);
 }
 
-// One tile.  FULL: every row of the tile, the row before it and the two rows after it exist and no
-// row lies before s0 — the common case, free of per-row existence predicates.
+// per-thread state that lives in registers across the phases of one tile
+template <class Pol>
+struct SegThread {
+    typename Pol::State st;    // open window (tail)
+    typename Pol::State head;  // first window that closed in this thread (valid when nclose > 0)
+    typename Pol::Inc inc_head;
+    int64_t eabs;              // absolute end of the open window
+    uint64_t kcur;             // its index
+    uint64_t kf;               // window of my first row
+    int64_t xlast;             // my last row's time
+    int64_t first_t;
+    uint64_t first_raw;
+    uint32_t first_flags;
+    int nclose;
+};
+
+// One phase: P rows of every thread.  FULL: all rows of the tile exist and none lies before s0 (the common case,
+// free of per-row existence predicates).
 template <class Pol, bool HAS_NULLS, bool FULL>
-__device__ __forceinline__ void seg_tile(const SegArgs<Pol> &P, const typename Pol::Out *sh_out, const int64_t tile,
-                                         const uint8_t *sb, WarpTotal<Pol> *wtot, volatile int *sh_flags, bool &bad) {
-    using G = SegG;
+__device__ __forceinline__ void seg_phase(SegThread<Pol> &c, const SegArgs<Pol> &A, const int64_t r0, const int phase,
+                                          const uint8_t *slot, const uint32_t *bsm, bool &bad) {
+    using Inc = typename Pol::Inc;
+    constexpr int P = SEG_P;
+    const int tid = threadIdx.x;
+    const WindowGeom &g = A.g;
+    const uint64_t d = g.div.d;
+    const int64_t *trow = reinterpret_cast<const int64_t *>(slot) + tid * SEG_COLS;
+    const uint64_t *vrow = reinterpret_cast<const uint64_t *>(slot + SEG_BOX_BYTES) + tid * SEG_COLS;
+    const int ti0 = tid * SEG_RE + phase * P;  // tile-relative index of my first row of this phase
+    int nmine = P;
+    if (!FULL) {
+        const int64_t left = g.n - r0 - ti0;
+        nmine = left < 0 ? 0 : (left > P ? P : (int)left);
+    }
+    if (!FULL && nmine == 0) return;
+
+    uint32_t vbits = (1u << P) - 1u;
+    if (HAS_NULLS) {
+        const uint32_t lo = bsm[ti0 >> 5], hi = bsm[(ti0 >> 5) + 1];
+        vbits &= __funnelshift_r(lo, hi, ti0 & 31);
+    }
+    bool early_any = false;
+    if (!FULL) {
+        vbits &= (1u << nmine) - 1u;
+        const int64_t e = g.early_rows - (r0 + ti0);  // rows before s0 (negative timestamps / left halo of a shard)
+        if (e > 0) {
+            early_any = true;
+            if (!g.early_keep) vbits &= e >= P ? 0u : ~((1u << (int)e) - 1u);
+        }
+    }
+
+    int64_t x[P];
+    uint64_t raw[P];
+    {
+        const longlong2 *t2 = reinterpret_cast<const longlong2 *>(trow);
+        const ulonglong2 *v2 = reinterpret_cast<const ulonglong2 *>(vrow);
+#pragma unroll
+        for (int q = 0; q < P / 2; ++q) {
+            const longlong2 a = t2[q];
+            const ulonglong2 b = v2[q];
+            x[2 * q] = a.x;
+            x[2 * q + 1] = a.y;
+            raw[2 * q] = b.x;
+            raw[2 * q + 1] = b.y;
+        }
+    }
+
+    if (phase == 0) {  // window of my first row and its absolute end (rows before s0 collapse onto window 0)
+        const bool early0 = !FULL && early_any;
+        c.kf = early0 ? 0 : div_u64((uint64_t)x[0] - (uint64_t)g.s0, g.div);
+        c.kcur = c.kf;
+        c.eabs = (int64_t)((uint64_t)g.s0 + (c.kf + 1) * d);
+        c.first_t = x[0];
+        c.first_raw = raw[0];
+        c.first_flags = EDGE_HAS | ((vbits & 1u) ? EDGE_VALID : 0u);
+    } else {
+        bad |= x[0] < c.xlast;
+    }
+
+    int segstart = 0;  // first row of this phase that belongs to the open window
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        if (FULL || j < nmine) {
+            if (j > 0) bad |= x[j] < x[j - 1];
+            if (!FULL) c.xlast = x[j];
+            if (x[j] >= c.eabs) {  // row j starts a later window: the open one is complete
+                Pol::note(c.st, vbits & ((1u << j) - 1u) & ~((1u << segstart) - 1u), vrow);
+                const Inc inc = Pol::make_inc(x[j] == c.eabs, (vbits >> j) & 1u, raw[j], x[j]);
+                if (c.nclose == 0) {
+                    c.head = c.st;
+                    c.inc_head = inc;
+                } else {
+                    Pol::write(A.out, g, (int64_t)c.kcur, c.st, inc);
+                }
+                ++c.nclose;
+                c.st = Pol::identity();
+                segstart = j;
+                if ((uint64_t)x[j] - (uint64_t)c.eabs < d) {
+                    ++c.kcur;
+                    c.eabs = (int64_t)((uint64_t)c.eabs + d);
+                } else {
+                    c.kcur = div_slow((uint64_t)x[j] - (uint64_t)g.s0, d, g.div.inv_rd);
+                    c.eabs = (int64_t)((uint64_t)g.s0 + (c.kcur + 1) * d);
+                }
+            }
+            if ((vbits >> j) & 1u) Pol::accumulate(c.st, x[j], raw[j]);
+        }
+    }
+    Pol::note(c.st, vbits & ~((1u << segstart) - 1u), vrow);
+    if (FULL) c.xlast = x[P - 1];
+}
+
+// End of a tile: stitch the per-thread pieces.
+template <class Pol, bool FULL>
+__device__ __forceinline__ void seg_stitch(SegThread<Pol> &c, const SegArgs<Pol> &A, const int64_t tile,
+                                           WarpTotal<Pol> *wtot, const WarpEdge *wedge, bool &bad) {
     using State = typename Pol::State;
     using Inc = typename Pol::Inc;
     using Carry = typename Pol::Carry;
-    constexpr int R = G::R;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const WindowGeom &g = P.g;
-    const uint64_t d = g.div.d;
-    const int64_t *tsm = reinterpret_cast<const int64_t *>(sb);
-    const uint64_t *vsm = reinterpret_cast<const uint64_t *>(sb + G::TIME_BYTES);
-    const uint32_t *bsm = reinterpret_cast<const uint32_t *>(sb + G::TIME_BYTES + G::VAL_BYTES);
-    const int64_t r0 = tile * G::T;
-    const int64_t nrem = g.n - r0;  // rows from the tile start to the end of the column (> 0)
-    const int nrem_i = FULL ? G::T + 2 : (nrem > G::T + 2 ? G::T + 2 : (int)nrem);
-    const int ti0 = tid * R;
-    const int nmine = FULL ? R : (nrem_i - ti0 < 0 ? 0 : (nrem_i - ti0 > R ? R : nrem_i - ti0));  // rows I own
-    const bool early_tile = !FULL && r0 < g.early_rows;
+    const WindowGeom &g = A.g;
+    const int64_t r0 = tile * SEG_T;
+    const bool has_rows = FULL || (c.first_flags & EDGE_HAS);
 
-    // validity of my R rows and of the row after them (bit R)
-    uint32_t vraw = (2u << R) - 1u;
-    if (HAS_NULLS) {
-        const uint32_t lo = bsm[ti0 >> 5], hi = bsm[(ti0 >> 5) + 1];
-        vraw &= __funnelshift_r(lo, hi, ti0 & 31);
-    }
-    uint32_t vbits = vraw & ((1u << R) - 1u);
-    if (!FULL) {
-        vbits &= (1u << nmine) - 1u;
-        if (early_tile && !g.early_keep) {  // rows before s0 are dropped (see WindowGeom)
-            const int64_t e = g.early_rows - (r0 + ti0);
-            if (e > 0) vbits &= e >= R ? 0u : ~((1u << (int)e) - 1u);
+    // ---- the boundary at my right edge: compare with the first row of the next thread ----------------------
+    uint64_t nk = __shfl_down_sync(0xffffffffu, (unsigned long long)c.kf, 1);
+    int64_t nt = __shfl_down_sync(0xffffffffu, (long long)c.first_t, 1);
+    uint64_t nraw = Pol::NEXT_VALUE ? __shfl_down_sync(0xffffffffu, (unsigned long long)c.first_raw, 1) : 0;
+    uint32_t nflags = __shfl_down_sync(0xffffffffu, c.first_flags, 1);
+    if (lane == 31) {
+        if (warp + 1 < SEG_NW) {
+            const WarpEdge e = wedge[warp + 1];
+            nk = (uint64_t)e.kf;
+            nt = e.t;
+            nraw = e.raw;
+            nflags = e.flags;
+        } else {
+            nflags = 0;  // last thread of the tile: nobody to the right
         }
     }
-
-    int64_t x[R + 1];
-    uint64_t raw[R + 1];
-#pragma unroll
-    for (int j = 0; j <= R; ++j) x[j] = tsm[ti0 + 2 + j];
-#pragma unroll
-    for (int j = 0; j < R; ++j) raw[j] = vsm[ti0 + j];
-    raw[R] = Pol::NEXT_VALUE ? vsm[ti0 + R] : 0;
-
-    // precondition check: time sorted ascending (every adjacent pair is checked exactly once)
-    if (FULL || (nmine > 0 && r0 + ti0 > 0)) bad |= x[0] < tsm[ti0 + 1];
-#pragma unroll
-    for (int j = 1; j < R; ++j)
-        if (FULL || j < nmine) bad |= x[j] < x[j - 1];
-
-    // window of my first row (rows before s0 collapse onto window 0) and its absolute end
-    uint64_t kf = 0;
-    if (nmine > 0) {
-        const bool early0 = early_tile && r0 + ti0 < g.early_rows;
-        kf = early0 ? 0 : div_u64((uint64_t)x[0] - (uint64_t)g.s0, g.div);
-    }
-    int64_t eabs = (int64_t)((uint64_t)g.s0 + (kf + 1) * d);
-    if (tid == 0) {  // does the window of my first row continue from the previous tile?
-        int lo_open = 0;
-        if (r0 > 0) {
-            const bool earlyp = early_tile && r0 - 1 < g.early_rows;
-            lo_open = earlyp ? kf == 0 : (uint64_t)tsm[1] - (uint64_t)g.s0 >= kf * d;
-        }
-        sh_flags[0] = lo_open;
-    }
-
-    State st = Pol::identity();
-    State head = Pol::identity();
-    Inc inc_head = Pol::make_inc(false, false, 0, 0);
-    uint32_t cmask = 0;  // bit j: the window of row j closes after row j
-#pragma unroll
-    for (int j = 0; j < R; ++j) {
-        if (FULL || j < nmine) {
-            if ((vbits >> j) & 1u) Pol::accumulate(st, x[j], raw[j]);
-            const bool next_exists = FULL || ti0 + j + 1 < nrem_i;
-            if (!next_exists || x[j + 1] >= eabs) {
-                if (cmask == 0) {
-                    head = st;
-                    if (Pol::NEXT_VALUE)
-                        inc_head = Pol::make_inc(next_exists && x[j + 1] == eabs, (vraw >> (j + 1)) & 1u, raw[j + 1],
-                                                 x[j + 1]);
-                }
-                cmask |= 1u << j;
-                st = Pol::identity();
-                if (next_exists) {
-                    if ((uint64_t)x[j + 1] - (uint64_t)eabs < d) {
-                        eabs = (int64_t)((uint64_t)eabs + d);
-                    } else {
-                        const uint64_t k = div_slow((uint64_t)x[j + 1] - (uint64_t)g.s0, d, g.div.inv_rd);
-                        eabs = (int64_t)((uint64_t)g.s0 + (k + 1) * d);
-                    }
-                }
-            }
+    const bool next_has = (nflags & EDGE_HAS) != 0;
+    bool closes_right = false;
+    if (has_rows) {
+        if (next_has) {
+            closes_right = nk != c.kcur;
+            bad |= nt < c.xlast;
+        } else if (!FULL) {
+            int64_t mine = g.n - r0 - (int64_t)tid * SEG_RE;
+            if (mine > SEG_RE) mine = SEG_RE;
+            closes_right = r0 + (int64_t)tid * SEG_RE + mine == g.n;  // I own the last row of the column
         }
     }
-    const int jfirst = __ffs(cmask) - 1, jlast = 31 - __clz(cmask);  // valid when cmask != 0
-    if (cmask) {
-        Pol::set_meta(head, vbits & ((2u << jfirst) - 1u), ti0);
-        Pol::set_meta(st, vbits & ~((2u << jlast) - 1u), ti0);
-    } else {
-        Pol::set_meta(st, vbits, ti0);
-    }
-    // windows lying strictly inside this thread's rows (short windows only)
-    if (jlast > jfirst) {
-        const int nexist = FULL ? R + 1 : (nrem_i - ti0 > R + 1 ? R + 1 : nrem_i - ti0);  // of my R+1 entries
-        Pol::middle(sh_out, g.W, g.s0, d, g.div.inv_rd, tsm + ti0 + 2, vsm + ti0, vraw, jfirst, jlast, nexist);
+    bool tail_open = has_rows;  // (meaningful for the last thread of the tile only)
+    if (closes_right) {
+        const Inc inc = next_has ? Pol::make_inc(nt == c.eabs, (nflags & EDGE_VALID) != 0, nraw, nt)
+                                 : Pol::make_inc(false, false, 0, 0);
+        if (c.nclose == 0) {
+            c.head = c.st;
+            c.inc_head = inc;
+        } else {
+            Pol::write(A.out, g, (int64_t)c.kcur, c.st, inc);
+        }
+        ++c.nclose;
+        c.st = Pol::identity();
+        tail_open = false;
     }
 
-    // ---- stitch windows spanning threads: segmented inclusive scan of the tails -------------
-    uint32_t f = cmask != 0;
-    State sc = st;
+    // ---- stitch windows spanning threads: segmented inclusive scan of the tails ------------------------------
+    const uint32_t ball = __ballot_sync(0xffffffffu, c.nclose != 0);
+    State sc = c.st;
 #pragma unroll
     for (int dd = 1; dd < 32; dd <<= 1) {
         const State o = Pol::shfl_up(sc, dd);
-        const uint32_t of = __shfl_up_sync(0xffffffffu, f, dd);
-        if (lane >= dd) {
-            if (!f) sc = Pol::combine(o, sc);
-            f |= of;
-        }
+        // no flag in lanes (lane-dd, lane]  <=>  the run ending at lane-dd belongs to my open segment
+        const uint32_t span = lane >= dd ? (0xFFFFFFFFu >> (31 - lane)) & ~((2u << (lane - dd)) - 1u) : 0u;
+        if (lane >= dd && (ball & span) == 0) sc = Pol::combine(o, sc);
     }
-    const uint32_t ball = __ballot_sync(0xffffffffu, cmask != 0);
     if (lane == 31) {
         wtot[warp].st = sc;
         wtot[warp].flag = ball != 0;
@@ -208,7 +292,6 @@ __device__ __forceinline__ void seg_tile(const SegArgs<Pol> &P, const typename P
     State ex = Pol::shfl_up(sc, 1);
     if (lane == 0) ex = Pol::identity();
     __syncthreads();
-    const bool left_open = sh_flags[0] != 0;
     State acc = Pol::identity();
     bool any_prev = false;
     for (int u = 0; u < warp; ++u) {
@@ -224,112 +307,205 @@ __device__ __forceinline__ void seg_tile(const SegArgs<Pol> &P, const typename P
     const State excl = flag_before ? ex : Pol::combine(acc, ex);
     const bool any_excl = any_prev || flag_before;
 
-    if (cmask) {  // this thread closes the window that was open at its left edge
-        const State h = Pol::combine(excl, head);
-        if (!any_excl && left_open)
-            P.carry_head[tile] = Pol::make_carry(h, inc_head, vsm, (int64_t)kf, true);
-        else
-            Pol::write(P.out, g, (int64_t)kf, h, inc_head, vsm);
+    const WarpEdge tile_first = wedge[0];
+    if (c.nclose) {  // this thread closes the window that was open at its left edge
+        const State h = Pol::combine(excl, c.head);
+        if (!any_excl) {  // ... which reaches the left edge of the tile: the fix-up decides whether it began earlier
+            Carry r = Pol::make_carry(h, c.inc_head, (int64_t)c.kf, true);
+            Pol::carry_set_edge(r, tile_first.t, tile_first.raw, (tile_first.flags & EDGE_VALID) != 0);
+            A.carry_head[tile] = r;
+        } else {
+            Pol::write(A.out, g, (int64_t)c.kf, h, c.inc_head);
+        }
     }
-    if (tid == SEG_NT - 1) {  // tile-level records: the window open at the right edge
-        const bool flag_incl = flag_before || cmask != 0;
+    if (tid == SEG_NT - 1) {  // tile-level records
+        const bool flag_incl = flag_before || c.nclose != 0;
         const State incl = flag_incl ? sc : Pol::combine(acc, sc);
         const bool any_incl = any_prev || flag_incl;
-        // the last row of the tile closes its window: end of data, or my last row closed
-        const bool closes = nrem <= G::T || ((cmask >> (R - 1)) & 1u);
         const Inc noinc = Pol::make_inc(false, false, 0, 0);
-        // tail records take their window index from the next tile's head record (key 0 = present)
-        Carry c = Pol::make_carry(incl, noinc, vsm, 0, false);
-        Carry none = c;
-        Pol::carry_set_key(none, -1);
-        if (!any_incl && left_open) {  // the whole tile lies inside one window that began earlier
-            Pol::carry_set_key(c, (int64_t)kf);  // (every thread of the tile has the same kf)
-            P.carry_head[tile] = c;              // not closed
-            P.carry_tail[tile] = none;
-        } else {
-            if (!left_open) P.carry_head[tile] = none;
-            P.carry_tail[tile] = closes ? none : c;
+        Carry tl = Pol::make_carry(incl, noinc, -1, false);
+        Pol::carry_set_edge(tl, c.xlast, 0, false);  // last row of the tile (cross-tile order check)
+        if (!any_incl) {  // no boundary anywhere in the tile: it lies inside one window
+            Carry hd = Pol::make_carry(incl, noinc, tile_first.kf, false);
+            Pol::carry_set_edge(hd, tile_first.t, tile_first.raw, (tile_first.flags & EDGE_VALID) != 0);
+            A.carry_head[tile] = hd;
+        } else if (tail_open) {
+            Pol::carry_set_key(tl, (int64_t)c.kcur);
         }
+        A.carry_tail[tile] = tl;
     }
 }
 
 template <class Pol, bool HAS_NULLS, int MIN_CTAS>
 __global__ void __launch_bounds__(SEG_NT, MIN_CTAS)
-    segreduce_kernel(const SegArgs<Pol> P, const int64_t ntiles, const int nstages) {
-    using G = SegG;
+    segreduce_kernel(const __grid_constant__ SegArgs<Pol> A, const __grid_constant__ CUtensorMap tm_time,
+                     const __grid_constant__ CUtensorMap tm_val, const int64_t ntiles, const int nstages) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);                            // [SEG_MAX_STAGES]
-    WarpTotal<Pol> *wtot = reinterpret_cast<WarpTotal<Pol> *>(smem_raw + 64);           // [SEG_NW]
-    static_assert(64 + SEG_NW * sizeof(WarpTotal<Pol>) + 16 <= 640, "header layout");
-    volatile int *sh_flags = reinterpret_cast<volatile int *>(smem_raw + 640);
-    typename Pol::Out *sh_out = reinterpret_cast<typename Pol::Out *>(smem_raw + 704);
-    static_assert(704 + sizeof(typename Pol::Out) <= SEG_HEADER_BYTES, "header layout");
-    uint8_t *stages = smem_raw + SEG_HEADER_BYTES;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);                    // [SEG_MAX_STAGES]
+    WarpEdge *wedge = reinterpret_cast<WarpEdge *>(smem_raw + 64);              // [SEG_NW]
+    WarpTotal<Pol> *wtot = reinterpret_cast<WarpTotal<Pol> *>(smem_raw + 64 + SEG_NW * sizeof(WarpEdge));
+    static_assert(64 + SEG_NW * (sizeof(WarpEdge) + sizeof(WarpTotal<Pol>)) <= SEG_HEADER_BYTES, "header layout");
+    uint8_t *bits = smem_raw + SEG_HEADER_BYTES;                                // [2][SEG_BITS_STRIDE]
+    uint8_t *slots = bits + 2 * SEG_BITS_STRIDE;
+    static_assert((SEG_HEADER_BYTES + 2 * SEG_BITS_STRIDE) % 128 == 0, "slots must be 128-byte aligned");
 
     const int tid = threadIdx.x;
-    const WindowGeom &g = P.g;
-    TileSrc src{P.time, P.values, HAS_NULLS ? P.validity : nullptr, g.n};
+    const WindowGeom &g = A.g;
+    const int64_t bitmap_total = ((g.n + 7) / 8 + 15) & ~(int64_t)15;  // device bitmaps are padded to 16 bytes
+
+    auto tile_full = [&](int64_t tile) {  // staged by TMA: whole tile + one more row exist, no row before s0
+        const int64_t r0 = tile * SEG_T;
+        return g.n - r0 > SEG_T && r0 >= g.early_rows;
+    };
+    // item q of this CTA: tile = blockIdx.x + (q / NP) * gridDim.x, phase = q % NP
+    auto issue_item = [&](int64_t q) {  // one thread
+        const int64_t tile = blockIdx.x + (q / SEG_NP) * (int64_t)gridDim.x;
+        if (tile >= ntiles || !tile_full(tile)) return;
+        const int phase = (int)(q % SEG_NP);
+        const int s = (int)(q % nstages);
+        uint8_t *slot = slots + (size_t)s * SEG_SLOT_BYTES;
+        uint32_t bbytes = 0;
+        if (HAS_NULLS && phase == 0) {
+            const int64_t b0 = tile * SEG_BITS_BYTES;
+            int64_t b1 = b0 + SEG_BITS_COPY;
+            if (b1 > bitmap_total) b1 = bitmap_total;
+            bbytes = (uint32_t)(b1 - b0);
+        }
+        mbar_arrive_expect_tx(&full[s], 2 * SEG_BOX_BYTES + bbytes);
+        tma_box_2d(slot, &tm_time, phase * SEG_P, (int32_t)(tile * SEG_NT), &full[s]);
+        tma_box_2d(slot + SEG_BOX_BYTES, &tm_val, phase * SEG_P, (int32_t)(tile * SEG_NT), &full[s]);
+        if (bbytes)
+            bulk_g2s(bits + ((q / SEG_NP) & 1) * SEG_BITS_STRIDE, A.validity + tile * SEG_BITS_BYTES, bbytes, &full[s]);
+    };
 
     if (tid == 0) {
-        *sh_out = P.out;
         for (int s = 0; s < nstages; ++s) mbar_init(&full[s], 1);
         fence_mbar_init();
         fence_proxy_async();
     }
     __syncthreads();
-    if (tid == 0) {
-        int64_t tl = blockIdx.x;
-        for (int s = 0; s < nstages && tl < ntiles; ++s, tl += gridDim.x)
-            issue_tile<G, true>(src, tl, stages + (size_t)s * SEG_STAGE_BYTES, &full[s]);
-    }
+    if (tid == 0)
+        for (int q = 0; q < nstages; ++q) issue_item(q);
 
-    int stage = 0;
-    uint32_t phase = 0;
+    uint32_t parity = 0;  // bit s: phase parity of slot s
     bool bad = false;
+    int64_t q = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        mbar_wait(&full[stage], phase);
-        const uint8_t *sb = stages + (size_t)stage * SEG_STAGE_BYTES;
-        const int64_t r0 = tile * G::T;
-        const bool full_tile = r0 > 0 && g.n - r0 >= G::T + 2 && r0 >= g.early_rows;
-        if (full_tile)
-            seg_tile<Pol, HAS_NULLS, true>(P, sh_out, tile, sb, wtot, sh_flags, bad);
+        const int64_t r0 = tile * SEG_T;
+        const bool fullt = tile_full(tile);
+        const uint32_t *bsm = reinterpret_cast<const uint32_t *>(bits + ((q / SEG_NP) & 1) * SEG_BITS_STRIDE);
+        SegThread<Pol> c;
+        c.st = Pol::identity();
+        c.head = Pol::identity();
+        c.inc_head = Pol::make_inc(false, false, 0, 0);
+        c.nclose = 0;
+        c.first_flags = 0;
+        c.first_t = 0;
+        c.first_raw = 0;
+        c.kf = c.kcur = 0;
+        c.eabs = 0;
+        c.xlast = 0;
+#pragma unroll 1
+        for (int phase = 0; phase < SEG_NP; ++phase, ++q) {
+            const int s = (int)(q % nstages);
+            uint8_t *slot = slots + (size_t)s * SEG_SLOT_BYTES;
+            if (fullt) {
+                mbar_wait(&full[s], (parity >> s) & 1u);
+                parity ^= 1u << s;
+                seg_phase<Pol, HAS_NULLS, true>(c, A, r0, phase, slot, bsm, bad);
+            } else {
+                // tile at an edge of the column (or holding rows before s0): staged by plain loads with bounds checks
+                int64_t *ts = reinterpret_cast<int64_t *>(slot);
+                uint64_t *vs = reinterpret_cast<uint64_t *>(slot + SEG_BOX_BYTES);
+                for (int e = tid; e < SEG_NT * SEG_P; e += SEG_NT) {
+                    const int tt = e / SEG_P, cc = e - tt * SEG_P;
+                    const int64_t row = r0 + (int64_t)tt * SEG_RE + phase * SEG_P + cc;
+                    const bool in = row < g.n;
+                    ts[tt * SEG_COLS + cc] = in ? A.time[row] : 0;
+                    vs[tt * SEG_COLS + cc] = in ? A.values[row] : 0;
+                }
+                if (HAS_NULLS && phase == 0) {
+                    uint32_t *bw = const_cast<uint32_t *>(bsm);
+                    const uint32_t *src = reinterpret_cast<const uint32_t *>(A.validity) + tile * (SEG_BITS_BYTES / 4);
+                    const int64_t words_left = bitmap_total / 4 - tile * (SEG_BITS_BYTES / 4);
+                    for (int w = tid; w < SEG_BITS_COPY / 4; w += SEG_NT) bw[w] = w < words_left ? src[w] : 0u;
+                }
+                __syncthreads();
+                seg_phase<Pol, HAS_NULLS, false>(c, A, r0, phase, slot, bsm, bad);
+            }
+            if (phase == 0 && (tid & 31) == 0) {  // publish my first row for the previous warp's last lane
+                WarpEdge e;
+                e.kf = (int64_t)c.kf;
+                e.t = c.first_t;
+                e.raw = c.first_raw;
+                e.flags = c.first_flags;
+                e._pad = 0;
+                wedge[tid >> 5] = e;
+            }
+            __syncthreads();  // every read of this slot is done
+            if (tid == 0) issue_item(q + nstages);
+        }
+        if (fullt)
+            seg_stitch<Pol, true>(c, A, tile, wtot, wedge, bad);
         else
-            seg_tile<Pol, HAS_NULLS, false>(P, sh_out, tile, sb, wtot, sh_flags, bad);
-        __syncthreads();  // every read of this stage (and of wtot) is done
-        if (tid == 0) {
-            const int64_t nxt = tile + (int64_t)nstages * gridDim.x;
-            if (nxt < ntiles) issue_tile<G, true>(src, nxt, stages + (size_t)stage * SEG_STAGE_BYTES, &full[stage]);
-        }
-        if (++stage == nstages) {
-            stage = 0;
-            phase ^= 1u;
-        }
+            seg_stitch<Pol, false>(c, A, tile, wtot, wedge, bad);
+        __syncthreads();  // wtot / wedge are reused by the next tile
     }
-    if (bad) atomicOr(P.status, ST_UNSORTED);
+    if (bad) atomicOr(A.status, ST_UNSORTED);
 }
 
-// Stitches windows spanning tiles, strictly left to right: tail of tile j, then the head records
-// of the following tiles until the one where the window closes.
+// Joins the per-tile records, strictly left to right.  Thread j owns the windows whose first row lies in tile j
+// and that are not complete inside it: the one at the left edge of the tile (head record, unless it continues a
+// window of an earlier tile) and the one open at its right edge (tail record).
 template <class Pol>
-__global__ void seg_fixup_kernel(const SegArgs<Pol> P, const int64_t ntiles) {
+__global__ void seg_fixup_kernel(const __grid_constant__ SegArgs<Pol> A, const int64_t ntiles) {
+    using Carry = typename Pol::Carry;
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= ntiles) return;
-    typename Pol::Carry a = P.carry_tail[j];
-    if (Pol::carry_key(a) < 0) return;
-    int64_t key = -1;
-    for (int64_t i = j + 1; i < ntiles; ++i) {
-        const typename Pol::Carry h = P.carry_head[i];
-        const int64_t hk = Pol::carry_key(h);
-        if (hk < 0 || (key >= 0 && hk != key)) break;
-        key = hk;
-        Pol::carry_combine(a, h);
-        if (Pol::carry_closed(h)) break;
+    const WindowGeom &g = A.g;
+    auto walk = [&](Carry a, int64_t i) {
+        const int64_t key = Pol::carry_key(a);
+        for (; i < ntiles; ++i) {
+            const Carry h = A.carry_head[i];
+            if (Pol::carry_key(h) != key) {  // the window ended exactly at the tile boundary
+                const int64_t E = (int64_t)((uint64_t)g.s0 + ((uint64_t)key + 1) * g.div.d);
+                Pol::carry_inc_from_edge(a, h, E);
+                Pol::write_carry(A.out, g, key, a);
+                return;
+            }
+            Pol::carry_combine(a, h);
+            if (Pol::carry_closed(h)) {
+                Pol::write_carry(A.out, g, key, a);
+                return;
+            }
+        }
+        Pol::carry_clear_inc(a);
+        Pol::write_carry(A.out, g, key, a);  // the column ends inside the window
+    };
+    const Carry hd = A.carry_head[j];
+    const Carry tl = A.carry_tail[j];
+    bool starts = true;
+    if (j > 0) {
+        const Carry pt = A.carry_tail[j - 1];
+        int64_t open_key = Pol::carry_key(pt);
+        if (open_key < 0) {
+            const Carry ph = A.carry_head[j - 1];
+            if (!Pol::carry_closed(ph)) open_key = Pol::carry_key(ph);
+        }
+        starts = open_key != Pol::carry_key(hd);
+        if (Pol::carry_edge_t(hd) < Pol::carry_edge_t(pt)) atomicOr(A.status, ST_UNSORTED);
     }
-    if (key < 0) return;  // cannot happen: an open tail is always continued by the next tile's head
-    Pol::write_carry(P.out, P.g, key, a);
+    if (starts) {
+        if (Pol::carry_closed(hd))
+            Pol::write_carry(A.out, g, Pol::carry_key(hd), hd);
+        else
+            walk(hd, j + 1);
+    }
+    if (Pol::carry_key(tl) >= 0) walk(tl, j + 1);
 }
 
 // launch knobs (defaults chosen on B200): pipeline depth and resident CTAs per SM
+inline int seg_smem_bytes(int nstages) { return SEG_HEADER_BYTES + 2 * SEG_BITS_STRIDE + nstages * SEG_SLOT_BYTES; }
 inline void seg_knobs(int &nstages, int &ctas, int def_stages, int def_ctas) {
     const char *a = getenv("BOWGPU_SEG_STAGES"), *b = getenv("BOWGPU_SEG_CTAS");
     nstages = a ? atoi(a) : def_stages;
@@ -337,27 +513,55 @@ inline void seg_knobs(int &nstages, int &ctas, int def_stages, int def_ctas) {
     if (ctas < 1) ctas = 1;
     if (nstages < 1) nstages = 1;
     if (nstages > SEG_MAX_STAGES) nstages = SEG_MAX_STAGES;
-    while (nstages > 1 && (SEG_HEADER_BYTES + nstages * SEG_STAGE_BYTES + 1024) * ctas > 232448) --nstages;
+    while (nstages > 1 && (seg_smem_bytes(nstages) + 1024) * ctas > 233472) --nstages;
+}
+
+// Tensor map viewing a column of n 8-byte elements as [n / RE][RE]; box = [NT][P+2].  Only whole rows of the view
+// are addressable, which is all the kernel asks for (tiles that are not complete are staged by plain loads).
+inline int seg_make_tmap(CUtensorMap *m, const void *col, int64_t n) {
+    memset(m, 0, sizeof *m);
+    const int64_t outer = n / SEG_RE;
+    if (outer == 0) return 0;
+    static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr);
+        if (e != cudaSuccess || qr != cudaDriverEntryPointSuccess || !fn) return (int)cudaErrorNotSupported;
+        encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)SEG_RE, (cuuint64_t)outer};
+    const cuuint64_t strides[1] = {(cuuint64_t)SEG_RE * 8};
+    const cuuint32_t box[2] = {(cuuint32_t)SEG_COLS, (cuuint32_t)SEG_NT};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_INT64, 2, const_cast<void *>(col), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
 template <class Pol, bool HAS_NULLS, int MIN_CTAS>
 int seg_launch(const SegArgs<Pol> &A, int sm_count, cudaStream_t stream, cudaEvent_t e0, cudaEvent_t e1) {
-    const int64_t ntiles = (A.g.n + SegG::T - 1) / SegG::T;
+    const int64_t ntiles = (A.g.n + SEG_T - 1) / SEG_T;
     if (ntiles == 0) return 0;
     auto kern = segreduce_kernel<Pol, HAS_NULLS, MIN_CTAS>;
     static int nstages = 0, ctas = 0;
     if (!nstages) seg_knobs(nstages, ctas, 2, MIN_CTAS);
-    const int smem = SEG_HEADER_BYTES + nstages * SEG_STAGE_BYTES;
+    const int smem = seg_smem_bytes(nstages);
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
+    CUtensorMap tm_time, tm_val;
+    int rc = seg_make_tmap(&tm_time, A.time, A.g.n);
+    if (!rc) rc = seg_make_tmap(&tm_val, A.values, A.g.n);
+    if (rc) return rc;
     int64_t grid = (int64_t)sm_count * ctas;
     if (grid > ntiles) grid = ntiles;
     if (e0) cudaEventRecord(e0, stream);
-    kern<<<(unsigned)grid, SEG_NT, smem, stream>>>(A, ntiles, nstages);
+    kern<<<(unsigned)grid, SEG_NT, smem, stream>>>(A, tm_time, tm_val, ntiles, nstages);
     if (e1) cudaEventRecord(e1, stream);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;

@@ -2,7 +2,7 @@
 //
 // A persistent CTA walks row tiles  tile = blockIdx.x + it * gridDim.x  of T = NT * R rows.  For
 // every tile one elected thread issues 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) of the
-// time rows (with a 2-row halo on both sides), the value rows and the validity bytes into one of
+// time rows (with a halo on both sides), the value rows and the validity bytes into one of
 // STAGES shared-memory stages; completion is tracked by one mbarrier per stage.  All threads wait
 // on the barrier, work out of shared memory, __syncthreads(), and the elected thread refills the
 // stage with the tile STAGES iterations ahead.  No registers are tied up by loads in flight, and
@@ -20,7 +20,12 @@ struct TileGeom {
     static constexpr int NT = NT_;
     static constexpr int R = R_;
     static constexpr int T = NT * R;                 // rows per tile
-    static constexpr int TIME_ENTRIES = T + 4;       // rows r0-2 .. r0+T+1
+#ifndef TILE_HALO_LO
+#define TILE_HALO_LO 16
+#endif
+    static constexpr int HALO = TILE_HALO_LO;        // time rows staged before the tile: 16 rows = 128 bytes keep every
+                                                     // bulk copy of the time column 128-byte aligned in global memory
+    static constexpr int TIME_ENTRIES = T + HALO + 2;  // rows r0-HALO .. r0+T+1
     static constexpr int TIME_BYTES = TIME_ENTRIES * 8;
     static constexpr int VAL_ENTRIES = T + 2;        // rows r0 .. r0+T+1 (the row after the tile is the
     static constexpr int VAL_BYTES = VAL_ENTRIES * 8;  // inclusive row of a window closing at the tile end)
@@ -59,10 +64,10 @@ struct TileSrc {
 template <class G, bool WITH_VALUES>
 __device__ __forceinline__ void issue_tile(const TileSrc &src, int64_t tile, uint8_t *stage, uint64_t *bar) {
     const int64_t r0 = tile * G::T;
-    const int64_t lo = r0 == 0 ? 0 : r0 - 2;
+    const int64_t lo = r0 == 0 ? 0 : r0 - G::HALO;
     int64_t hi = r0 + G::T + 2;
     if (hi > src.n) hi = src.n;
-    uint8_t *tdst = stage + (r0 == 0 ? 16 : 0);
+    uint8_t *tdst = stage + (r0 == 0 ? G::HALO * 8 : 0);
     const uint32_t tbytes = (uint32_t)(hi - lo) * 8u;
     int64_t vhi = r0 + G::VAL_ENTRIES;
     if (vhi > src.n) vhi = src.n;

@@ -27,7 +27,7 @@ STATUS = {0: "OK", 1: "EINVAL", 2: "ETYPE", 3: "EFIRSTNULL", 4: "EPREVROW", 5: "
 # every symbol include/bowgpu.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "bowgpu_abi_version", "bowgpu_ctx_create", "bowgpu_ctx_destroy", "bowgpu_last_error", "bowgpu_status_string",
-    "bowgpu_ctx_synchronize", "bowgpu_ctx_enable_timing", "bowgpu_ctx_last_timing", "bowgpu_ctx_sm_count",
+    "bowgpu_ctx_synchronize", "bowgpu_ctx_enable_timing", "bowgpu_ctx_last_timing", "bowgpu_ctx_sm_count", "bowgpu_ctx_trim",
     "bowgpu_frame_create", "bowgpu_frame_destroy", "bowgpu_frame_num_rows", "bowgpu_frame_num_cols",
     "bowgpu_frame_col_dtype", "bowgpu_frame_col_has_validity", "bowgpu_frame_col_device_ptrs",
     "bowgpu_frame_download", "bowgpu_frame_download_range", "bowgpu_frame_generate",
@@ -107,7 +107,7 @@ def lib():
                                                  C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
         L.bowgpu_rolling_early_rows.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
         for name in ("bowgpu_ctx_destroy", "bowgpu_frame_destroy", "bowgpu_rolling_destroy", "bowgpu_last_error",
-                     "bowgpu_ctx_synchronize", "bowgpu_ctx_sm_count", "bowgpu_frame_num_rows",
+                     "bowgpu_ctx_synchronize", "bowgpu_ctx_sm_count", "bowgpu_ctx_trim", "bowgpu_frame_num_rows",
                      "bowgpu_frame_num_cols", "bowgpu_rolling_num_windows", "bowgpu_rolling_first_window_start",
                      "bowgpu_rolling_inclusive"):
             getattr(L, name).argtypes = [C.c_void_p]
@@ -176,6 +176,10 @@ class Ctx:
         t = Timing()
         self.check(lib().bowgpu_ctx_last_timing(self.h, C.byref(t)))
         return t
+
+    def trim(self):
+        """returns cached column buffers of destroyed frames to the driver"""
+        self.check(lib().bowgpu_ctx_trim(self.h))
 
     @property
     def sm_count(self) -> int:

@@ -135,6 +135,9 @@ int32_t bowgpu_ctx_synchronize(bowgpu_ctx *ctx);
 int32_t bowgpu_ctx_enable_timing(bowgpu_ctx *ctx, int32_t enable);
 int32_t bowgpu_ctx_last_timing(bowgpu_ctx *ctx, bowgpu_timing *out); /* synchronizes */
 int32_t bowgpu_ctx_sm_count(const bowgpu_ctx *ctx);
+/* Column buffers of frames come from a stream-ordered pool owned by the ctx; destroyed frames leave their
+ * blocks cached for the next Interpolate / upload.  Returns the cached blocks to the driver (synchronizes). */
+int32_t bowgpu_ctx_trim(bowgpu_ctx *ctx);
 
 /* ---- frames ----------------------------------------------------------------------------- */
 /* Copies `ncols` Arrow arrays into device memory (mem == BOWGPU_MEM_HOST: chunked pinned staging,

@@ -1,0 +1,136 @@
+#!/usr/bin/env python
+"""Device-resident timings of the BASELINE.json configs[1..4] pipelines on one B200 (informational; the
+contract line is bench.py).  Prints one JSON line per config: rows/s, ms, algorithmic bytes and
+the achieved fraction of the measured HBM peak for the whole chain."""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from bow_b200 import native as N  # noqa: E402
+
+SEC = 1_000_000_000
+SCALE = float(os.environ.get("BOW_BENCH_SCALE", "1.0"))
+PEAK = 6548.5
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def dev_outs(W, nspecs):
+    vals = [torch.empty(max(W, 1), dtype=torch.int64, device="cuda") for _ in range(nspecs)]
+    bits = [torch.empty((W + 7) // 8 + 16, dtype=torch.uint8, device="cuda") for _ in range(nspecs)]
+    outs = (N.OutCol * nspecs)()
+    for j in range(nspecs):
+        outs[j].values, outs[j].validity = vals[j].data_ptr(), bits[j].data_ptr()
+    return outs, (vals, bits)
+
+
+def timed(ctx, fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / reps
+
+
+def report(name, n, secs, alg_bytes, extra=None):
+    line = {"config": name, "rows": n, "ms": secs * 1e3, "rows_per_s": n / secs, "algorithmic_bytes": alg_bytes,
+            "achieved_GBs": alg_bytes / secs / 1e9, "frac_of_measured_peak": alg_bytes / secs / 1e9 / PEAK}
+    line.update(extra or {})
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ctx = N.Ctx(0)
+    which = sys.argv[1:] or ["1", "1b", "2", "3", "4"]
+    if "1" in which or "1b" in which:
+        for tag, n in (("1", int(1e8 * SCALE)), ("1b", int(1e9 * SCALE))):
+            if tag not in which:
+                continue
+            fr = N.Frame.generate(ctx, n, ncols=1, seed=42)
+            r = N.Rolling(fr, 0, 60 * SEC)
+            specs = [("WindowStart", 0), ("ArithmeticMean", 1), ("Sum", 1), ("Min", 1), ("Max", 1), ("Count", 1)]
+            W = r.num_windows
+            outs, keep = dev_outs(W, len(specs))
+            arr = N.make_specs(specs)
+            dt = timed(ctx, lambda: r.aggregate_device(arr, len(specs), outs), reps=20)
+            report(f"configs[1] {n} rows mean/sum/min/max/count", n, dt, 16 * n + len(specs) * (8 * W + W // 8))
+            r.close(); fr.close(); del keep
+    if "2" in which:
+        n = int(1e9 * SCALE)
+        fr = N.Frame.generate(ctx, n, ncols=4, seed=7, null_mask=0xF, null_mod=10)
+        r = N.Rolling(fr, 0, 900 * SEC, offset=420 * SEC)
+        ops = ["WindowStart"] + ["Linear"] * 4
+        specs = [("WindowStart", 0)]
+        for c in range(1, 5):
+            specs += [("WeightedAverageLinear", c), ("IntegralTrapezoid", c)]
+        W = r.num_windows
+        outs, keep = dev_outs(W, len(specs))
+        arr = N.make_specs(specs)
+
+        def chain():
+            fi = r.interpolate(ops)
+            r2 = N.Rolling(fi, 0, 900 * SEC, offset=420 * SEC)
+            r2.aggregate_device(arr, len(specs), outs)
+            ctx.synchronize()
+            r2.close(); fi.close()
+        dt = timed(ctx, chain, reps=3, warm=1)
+        alg = 40 * n + 4 * n // 8 + len(specs) * (8 * W + W // 8)     # fused chain, inputs read once
+        report("configs[2] Interpolate(WindowStart, Linear x4) -> WeightedAverageLinear + IntegralTrapezoid x4", n, dt, alg,
+               {"note": "the interpolated frame is materialised: actual traffic ~3x algorithmic"})
+        fi = r.interpolate(ops)
+        r2 = N.Rolling(fi, 0, 900 * SEC, offset=420 * SEC)
+        dt2 = timed(ctx, lambda: r2.aggregate_device(arr, len(specs), outs), reps=5)
+        report("configs[2] Aggregate only (on the interpolated frame)", n, dt2, alg)
+        r2.close(); fi.close(); r.close(); fr.close(); del keep
+    if "3" in which:
+        n = int(1e9 * SCALE)
+        fr = N.Frame.generate(ctx, n, ncols=1, seed=3, step=SEC, null_mask=1, null_mod=10, kind=1)
+        r = N.Rolling(fr, 0, SEC)
+        specs = [("WindowStart", 0), ("First", 1), ("Last", 1), ("Min", 1), ("Max", 1)]
+        W = r.num_windows
+        outs, keep = dev_outs(W, len(specs))
+        arr = N.make_specs(specs)
+        dt = timed(ctx, lambda: r.aggregate_device(arr, len(specs), outs), reps=10)
+        report("configs[3] bursty Aggregate First/Last/Min/Max (no interpolation)", n, dt,
+               16 * n + n // 8 + len(specs) * (8 * W + W // 8))
+
+        def chain():
+            fi = r.interpolate(["WindowStart", "StepPrevious"])
+            r2 = N.Rolling(fi, 0, SEC)
+            r2.aggregate_device(arr, len(specs), outs)
+            ctx.synchronize()
+            r2.close(); fi.close()
+        dt = timed(ctx, chain, reps=3, warm=1)
+        report("configs[3] bursty Interpolate(WindowStart, StepPrevious) -> First/Last/Min/Max", n, dt,
+               16 * n + n // 8 + len(specs) * (8 * W + W // 8))
+        r.close(); fr.close(); del keep
+    if "4" in which:
+        n = int(5e8 * SCALE)
+        fr = N.Frame.generate(ctx, n, ncols=16, seed=11, null_mask=0xAAAA, int_mask=0x00FF, null_mod=10)
+        r = N.Rolling(fr, 0, 60 * SEC)
+        opsl = ["Count", "Sum", "ArithmeticMean", "Min", "Max", "First", "Last", "IntegralStep", "IntegralTrapezoid",
+                "WeightedAverageStep", "WeightedAverageLinear"]
+        specs = [("WindowStart", 0)] + [(op, c) for c in range(1, 17) for op in opsl]
+        W = r.num_windows
+        outs, keep = dev_outs(W, len(specs))
+        arr = N.make_specs(specs)
+        dt = timed(ctx, lambda: r.aggregate_device(arr, len(specs), outs), reps=3, warm=1)
+        report("configs[4] one GPU share: 16 columns x all aggregations (177 outputs)", n, dt,
+               136 * n + 8 * n // 8 + len(specs) * (8 * W + W // 8))
+        r.close(); fr.close(); del keep
+
+
+if __name__ == "__main__":
+    main()
