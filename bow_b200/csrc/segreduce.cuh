@@ -54,6 +54,10 @@ namespace bowgpu {
 #ifndef SEG_CFG_CTAS
 #define SEG_CFG_CTAS 3
 #endif
+#ifndef SEG_CFG_UNROLL
+#define SEG_CFG_UNROLL 2
+#endif
+constexpr int SEG_UNROLL = SEG_CFG_UNROLL;  // row pairs per trip of the streaming loop
 constexpr int SEG_NT = SEG_CFG_NT;
 constexpr int SEG_P = 16;                     // rows per phase (box start columns must be 16-byte aligned in global memory)
 constexpr int SEG_NP = SEG_CFG_NP;            // phases per tile
@@ -159,43 +163,33 @@ __device__ __forceinline__ void seg_phase(SegThread<Pol> &c, const SegArgs<Pol> 
         }
     }
 
-    int64_t x[P];
-    uint64_t raw[P];
-    {
-        const longlong2 *t2 = reinterpret_cast<const longlong2 *>(trow);
-        const ulonglong2 *v2 = reinterpret_cast<const ulonglong2 *>(vrow);
-#pragma unroll
-        for (int q = 0; q < P / 2; ++q) {
-            const longlong2 a = t2[q];
-            const ulonglong2 b = v2[q];
-            x[2 * q] = a.x;
-            x[2 * q + 1] = a.y;
-            raw[2 * q] = b.x;
-            raw[2 * q + 1] = b.y;
-        }
-    }
+    const longlong2 *t2 = reinterpret_cast<const longlong2 *>(trow);
+    const ulonglong2 *v2 = reinterpret_cast<const ulonglong2 *>(vrow);
+    longlong2 ta = t2[0];
+    ulonglong2 va = v2[0];
 
     if (phase == 0) {  // window of my first row and its absolute end (rows before s0 collapse onto window 0)
         const bool early0 = !FULL && early_any;
-        c.kf = early0 ? 0 : div_u64((uint64_t)x[0] - (uint64_t)g.s0, g.div);
+        c.kf = early0 ? 0 : div_u64((uint64_t)ta.x - (uint64_t)g.s0, g.div);
         c.kcur = c.kf;
         c.eabs = (int64_t)((uint64_t)g.s0 + (c.kf + 1) * d);
-        c.first_t = x[0];
-        c.first_raw = raw[0];
+        c.first_t = ta.x;
+        c.first_raw = va.x;
         c.first_flags = EDGE_HAS | ((vbits & 1u) ? EDGE_VALID : 0u);
-    } else {
-        bad |= x[0] < c.xlast;
+        c.xlast = ta.x;
     }
 
     int segstart = 0;  // first row of this phase that belongs to the open window
-#pragma unroll
-    for (int j = 0; j < P; ++j) {
+    // One row: order check against the previous row, window boundary test against the running absolute end,
+    // accumulate.  The loop over row pairs is only partially unrolled (SEG_CFG_UNROLL pairs per trip) so that the
+    // streaming path stays resident in the instruction cache; the next pair is fetched one trip ahead.
+    auto row = [&](const int j, const int64_t xj, const uint64_t rj) {
         if (FULL || j < nmine) {
-            if (j > 0) bad |= x[j] < x[j - 1];
-            if (!FULL) c.xlast = x[j];
-            if (x[j] >= c.eabs) {  // row j starts a later window: the open one is complete
+            bad |= xj < c.xlast;
+            c.xlast = xj;
+            if (xj >= c.eabs) {  // row j starts a later window: the open one is complete
                 Pol::note(c.st, vbits & ((1u << j) - 1u) & ~((1u << segstart) - 1u), vrow);
-                const Inc inc = Pol::make_inc(x[j] == c.eabs, (vbits >> j) & 1u, raw[j], x[j]);
+                const Inc inc = Pol::make_inc(xj == c.eabs, (vbits >> j) & 1u, rj, xj);
                 if (c.nclose == 0) {
                     c.head = c.st;
                     c.inc_head = inc;
@@ -205,19 +199,27 @@ __device__ __forceinline__ void seg_phase(SegThread<Pol> &c, const SegArgs<Pol> 
                 ++c.nclose;
                 c.st = Pol::identity();
                 segstart = j;
-                if ((uint64_t)x[j] - (uint64_t)c.eabs < d) {
+                if ((uint64_t)xj - (uint64_t)c.eabs < d) {
                     ++c.kcur;
                     c.eabs = (int64_t)((uint64_t)c.eabs + d);
                 } else {
-                    c.kcur = div_slow((uint64_t)x[j] - (uint64_t)g.s0, d, g.div.inv_rd);
+                    c.kcur = div_slow((uint64_t)xj - (uint64_t)g.s0, d, g.div.inv_rd);
                     c.eabs = (int64_t)((uint64_t)g.s0 + (c.kcur + 1) * d);
                 }
             }
-            if ((vbits >> j) & 1u) Pol::accumulate(c.st, x[j], raw[j]);
+            if ((vbits >> j) & 1u) Pol::accumulate(c.st, xj, rj);
         }
+    };
+#pragma unroll(SEG_UNROLL)
+    for (int q = 0; q < P / 2; ++q) {
+        const longlong2 tb = t2[q + 1 < P / 2 ? q + 1 : q];  // (the pitch pads two more columns; stay inside anyway)
+        const ulonglong2 vb = v2[q + 1 < P / 2 ? q + 1 : q];
+        row(2 * q, ta.x, va.x);
+        row(2 * q + 1, ta.y, va.y);
+        ta = tb;
+        va = vb;
     }
     Pol::note(c.st, vbits & ~((1u << segstart) - 1u), vrow);
-    if (FULL) c.xlast = x[P - 1];
 }
 
 // End of a tile: stitch the per-thread pieces.
@@ -534,8 +536,14 @@ inline int seg_make_tmap(CUtensorMap *m, const void *col, int64_t n) {
     const cuuint64_t strides[1] = {(cuuint64_t)SEG_RE * 8};
     const cuuint32_t box[2] = {(cuuint32_t)SEG_COLS, (cuuint32_t)SEG_NT};
     const cuuint32_t estr[2] = {1, 1};
+    static int l2p = -1;  // L2 promotion of the box fetches (tuning knob; 0 none, 1 64B, 2 128B, 3 256B)
+    if (l2p < 0) {
+        const char *e = getenv("BOWGPU_TMAP_L2");
+        l2p = e ? atoi(e) : 1;
+        if (l2p < 0 || l2p > 3) l2p = 3;
+    }
     const CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_INT64, 2, const_cast<void *>(col), dims, strides, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, (CUtensorMapL2promotion)l2p,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
