@@ -920,7 +920,6 @@ extern "C" int32_t bowgpu_rolling_aggregate(bowgpu_rolling *r, const bowgpu_agg_
     uint8_t *carry = (uint8_t *)arena_take(ctx, carry_bytes);
 
     timing_begin(ctx);
-    std::vector<EpilogueSpec> epi(nspecs);
     // per spec: the per-window count that decides validity, and the base quantity a derived op divides
     std::vector<const int64_t *> spec_cnt(nspecs, nullptr);
     std::vector<const double *> spec_src(nspecs, nullptr);
@@ -1040,21 +1039,69 @@ extern "C" int32_t bowgpu_rolling_aggregate(bowgpu_rolling *r, const bowgpu_agg_
             }
         }
     }
-    for (int j = 0; j < nspecs; ++j) {
-        EpilogueSpec &e = epi[j];
-        memset(&e, 0, sizeof e);
-        e.op = specs[j].op;
-        e.out_is_int = outs[j].dtype == BOWGPU_INT64;
-        e.cnt = spec_cnt[j];
-        e.ok = nullptr;
-        e.sum_src = spec_src[j];
-        e.values = dvals[j];
-        e.validity = dbits[j];
-        e.nfactors = specs[j].nfactors;
-        for (int i = 0; i < e.nfactors; ++i) e.factors[i] = specs[j].factors[i];
+    // ---- epilogue: specs without Factor are grouped by the count array that decides their validity (fast path);
+    // the others go through the generic per-spec pass
+    {
+        std::vector<EpiGroup> groups;
+        std::vector<EpilogueSpec> generic;
+        auto group_for = [&](const int64_t *cnt, auto full) -> EpiGroup & {
+            for (auto &G : groups)
+                if (G.cnt == cnt && !full(G)) return G;
+            EpiGroup G;
+            memset(&G, 0, sizeof G);
+            G.cnt = cnt;
+            groups.push_back(G);
+            return groups.back();
+        };
+        for (int j = 0; j < nspecs; ++j) {
+            const int op = specs[j].op;
+            if (specs[j].nfactors > 0) {
+                EpilogueSpec e;
+                memset(&e, 0, sizeof e);
+                e.op = op;
+                e.out_is_int = outs[j].dtype == BOWGPU_INT64;
+                e.cnt = spec_cnt[j];
+                e.sum_src = spec_src[j];
+                e.values = dvals[j];
+                e.validity = dbits[j];
+                e.nfactors = specs[j].nfactors;
+                for (int i = 0; i < e.nfactors; ++i) e.factors[i] = specs[j].factors[i];
+                generic.push_back(e);
+                continue;
+            }
+            const bool always = op == BOWGPU_AGG_WINDOW_START || op == BOWGPU_AGG_COUNT || op == BOWGPU_AGG_SUM;
+            const bool divides = op == BOWGPU_AGG_MEAN || op == BOWGPU_AGG_WAVG_STEP || op == BOWGPU_AGG_WAVG_LINEAR;
+            const bool zeroes = !divides && op != BOWGPU_AGG_WINDOW_START && op != BOWGPU_AGG_COUNT;
+            // WindowStart does not depend on any count: it rides along with the first group that has room
+            const int64_t *gkey = spec_cnt[j];
+            if (op == BOWGPU_AGG_WINDOW_START)
+                for (int jj = 0; jj < nspecs && !gkey; ++jj)
+                    if (specs[jj].nfactors == 0) gkey = spec_cnt[jj];
+            EpiGroup &G = group_for(gkey, [&](const EpiGroup &g_) {
+                return (always ? g_.n_bm_all >= EPIG_ALL : g_.n_bm_cnt >= EPIG_BM) || (divides && g_.n_div >= EPIG_DIV) ||
+                       (zeroes && g_.n_null >= EPIG_NULL) || (op == BOWGPU_AGG_WINDOW_START && g_.n_ws >= EPIG_WS);
+            });
+            if (always)
+                G.bm_all[G.n_bm_all++] = dbits[j];
+            else
+                G.bm_cnt[G.n_bm_cnt++] = dbits[j];
+            if (divides) {
+                G.div_dst[G.n_div] = (double *)dvals[j];
+                G.div_src[G.n_div] = spec_src[j];
+                G.div_by_cnt[G.n_div++] = op == BOWGPU_AGG_MEAN;
+            }
+            if (zeroes) G.null_vals[G.n_null++] = (uint64_t *)dvals[j];
+            if (op == BOWGPU_AGG_WINDOW_START) G.ws[G.n_ws++] = (int64_t *)dvals[j];
+        }
+        for (const auto &G : groups) {
+            CK(launch_epilogue_group(G, g, ctx->stream));
+            count_launch(ctx);
+        }
+        if (!generic.empty()) {
+            CK(launch_epilogue(generic.data(), (int)generic.size(), g, ctx->stream));
+            count_launch(ctx, ((int)generic.size() + 15) / 16);
+        }
     }
-    CK(launch_epilogue(epi.data(), nspecs, g, ctx->stream));
-    count_launch(ctx, (nspecs + 15) / 16);
     timing_end(ctx);
     if (mem == BOWGPU_MEM_DEVICE) return BOWGPU_OK;  // asynchronous: errors surface in bowgpu_ctx_synchronize
     for (int j = 0; j < nspecs; ++j) {

@@ -18,93 +18,165 @@ struct EpiBatch {
     EpilogueSpec s[EPI_MAX];
 };
 
-// One thread per window, looping over the specs of the batch: the per-window counts shared by the
-// aggregations of one input column are fetched from DRAM once (repeats hit L1).
-template <int NS>
-__global__ void __launch_bounds__(256) epilogue_kernel(const __grid_constant__ EpiBatch B, const int nspecs,
-                                                       const WindowGeom g) {
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool in = k < g.W;
-    const int lane = threadIdx.x & 31;
-    // phase 1: every global read of this window, all in flight together (the pass is latency bound otherwise)
-    int64_t cv[NS];
-    double sv[NS];
-    uint8_t okv[NS];
+// Each warp owns 128 consecutive windows; lane l handles windows base + l + 32*i (i = 0..3): coalesced 8-byte
+// accesses with four independent loads in flight per array, and one ballot per i yields a whole 32-bit word of
+// the validity bitmap.  Specs are walked in a rolled loop; the per-window count array shared by the
+// aggregations of one input column is fetched once (consecutive specs with the same pointer reuse it).
+constexpr int EPI_NT = 256, EPI_WPT = 4;  // threads per block, windows per thread
+
+__global__ void __launch_bounds__(EPI_NT) epilogue_kernel(const __grid_constant__ EpiBatch B, const int nspecs,
+                                                          const WindowGeom g) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t base = ((int64_t)blockIdx.x * (EPI_NT / 32) + warp) * (32 * EPI_WPT);
+    if (base >= g.W) return;
+    int64_t k[EPI_WPT];
+    bool in[EPI_WPT];
 #pragma unroll
-    for (int si = 0; si < NS; ++si) {
-        cv[si] = 0;
-        sv[si] = 0.0;
-        okv[si] = 0;
-        if (si < nspecs && in) {
-            const EpilogueSpec &sp = B.s[si];
-            if (sp.cnt) cv[si] = sp.cnt[k];
-            if (sp.sum_src) sv[si] = sp.sum_src[k];
-            if (sp.ok) okv[si] = sp.ok[k];
+    for (int i = 0; i < EPI_WPT; ++i) {
+        k[i] = base + lane + 32 * i;
+        in[i] = k[i] < g.W;
+    }
+    const int64_t *last_cnt = nullptr;
+    int64_t c[EPI_WPT] = {0, 0, 0, 0};
+    for (int si = 0; si < nspecs; ++si) {
+        const EpilogueSpec &sp = B.s[si];
+        uint64_t *vals = reinterpret_cast<uint64_t *>(sp.values);
+        if (sp.cnt != last_cnt) {
+#pragma unroll
+            for (int i = 0; i < EPI_WPT; ++i) c[i] = (sp.cnt && in[i]) ? sp.cnt[k[i]] : 0;
+            last_cnt = sp.cnt;
+        }
+        double sv[EPI_WPT];
+        uint8_t okv[EPI_WPT];
+#pragma unroll
+        for (int i = 0; i < EPI_WPT; ++i) {
+            sv[i] = (sp.sum_src && in[i]) ? sp.sum_src[k[i]] : 0.0;
+            okv[i] = (sp.ok && in[i]) ? sp.ok[k[i]] : 0;
+        }
+        const bool always = sp.op == BOWGPU_AGG_WINDOW_START || sp.op == BOWGPU_AGG_COUNT || sp.op == BOWGPU_AGG_SUM;
+        const bool count_in_place = sp.op == BOWGPU_AGG_COUNT && sp.nfactors == 0 && sp.values == (const void *)sp.cnt;
+#pragma unroll
+        for (int i = 0; i < EPI_WPT; ++i) {
+            bool valid = false;
+            if (in[i]) {
+                const bool okk = sp.ok ? okv[i] != 0 : c[i] > 0;
+                valid = always || okk;
+                bool have = false;  // value already computed in a register
+                uint64_t bits = 0;
+                if (sp.op == BOWGPU_AGG_WINDOW_START) {
+                    bits = (uint64_t)g.s0 + (uint64_t)k[i] * g.div.d;
+                    have = true;
+                } else if (sp.op == BOWGPU_AGG_COUNT) {
+                    bits = (uint64_t)c[i];
+                    have = !count_in_place;  // the segreduce kernel wrote the counts straight into this output
+                } else if (!okk) {
+                    bits = 0;  // null slot, or Sum of an empty / all-null window = 0.0
+                    have = true;
+                } else if (sp.op == BOWGPU_AGG_MEAN) {
+                    bits = f64_as_bits(__ddiv_rn(sv[i], (double)c[i]));  // arithmeticmean.go:28
+                    have = true;
+                } else if (sp.op == BOWGPU_AGG_WAVG_STEP || sp.op == BOWGPU_AGG_WAVG_LINEAR) {
+                    // integral / float64(w.LastValue - w.FirstValue), weightedmean.go:17,31
+                    bits = f64_as_bits(__ddiv_rn(sv[i], (double)(int64_t)g.div.d));
+                    have = true;
+                }
+                if (valid && sp.nfactors > 0) {
+                    if (!have) bits = vals[k[i]];
+                    for (int f = 0; f < sp.nfactors; ++f) {
+                        if (sp.out_is_int)
+                            bits = (uint64_t)f64_to_i64_go(__dmul_rn((double)(int64_t)bits, sp.factors[f]));
+                        else
+                            bits = f64_as_bits(__dmul_rn(bits_as_f64(bits), sp.factors[f]));
+                    }
+                    have = true;
+                }
+                if (have) vals[k[i]] = bits;
+            }
+            // one ballot = the 32 validity bits of windows base + 32 i .. + 31; the last word is stored bytewise so that
+            // nothing beyond ceil(W/8) bytes is touched (the caller's buffer ends there)
+            const uint32_t ball = __ballot_sync(0xffffffffu, valid);
+            const int64_t w0 = base + 32 * i;
+            if (lane == 0 && w0 < g.W) {
+                if (w0 + 32 <= g.W) {
+                    *reinterpret_cast<uint32_t *>(sp.validity + (w0 >> 3)) = ball;
+                } else {
+                    for (int64_t b = 0; w0 + 8 * b < g.W; ++b) sp.validity[(w0 >> 3) + b] = (uint8_t)(ball >> (8 * b));
+                }
+            }
         }
     }
+}
+
+__global__ void __launch_bounds__(EPI_NT) epilogue_group_kernel(const __grid_constant__ EpiGroup G, const WindowGeom g) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t base = ((int64_t)blockIdx.x * (EPI_NT / 32) + warp) * (32 * EPI_WPT);
+    if (base >= g.W) return;
+    int64_t c[EPI_WPT];
 #pragma unroll
-    for (int si = 0; si < NS; ++si) {
-        if (si >= nspecs) break;
-        const EpilogueSpec &sp = B.s[si];
-        bool valid = false;
-        if (in) {
-            const int64_t c = cv[si];
-            const bool okk = sp.ok ? okv[si] != 0 : c > 0;
-            uint64_t *vals = reinterpret_cast<uint64_t *>(sp.values);
-            const bool always = sp.op == BOWGPU_AGG_WINDOW_START || sp.op == BOWGPU_AGG_COUNT || sp.op == BOWGPU_AGG_SUM;
-            valid = always || okk;
-            bool have = false;  // value already computed in a register
-            uint64_t bits = 0;
-            if (sp.op == BOWGPU_AGG_WINDOW_START) {
-                bits = (uint64_t)g.s0 + (uint64_t)k * g.div.d;
-                have = true;
-            } else if (sp.op == BOWGPU_AGG_COUNT) {
-                bits = (uint64_t)c;
-                have = true;
-            } else if (!okk) {
-                bits = 0;  // null slot, or Sum of an empty / all-null window = 0.0
-                have = true;
-            } else if (sp.op == BOWGPU_AGG_MEAN) {
-                bits = f64_as_bits(__ddiv_rn(sv[si], (double)c));  // arithmeticmean.go:28
-                have = true;
-            } else if (sp.op == BOWGPU_AGG_WAVG_STEP || sp.op == BOWGPU_AGG_WAVG_LINEAR) {
-                // integral / float64(w.LastValue - w.FirstValue), weightedmean.go:17,31
-                bits = f64_as_bits(__ddiv_rn(sv[si], (double)(int64_t)g.div.d));
-                have = true;
-            }
-            if (valid && sp.nfactors > 0) {
-                if (!have) bits = vals[k];
-                for (int i = 0; i < sp.nfactors; ++i) {
-                    if (sp.out_is_int)
-                        bits = (uint64_t)f64_to_i64_go(__dmul_rn((double)(int64_t)bits, sp.factors[i]));
-                    else
-                        bits = f64_as_bits(__dmul_rn(bits_as_f64(bits), sp.factors[i]));
-                }
-                have = true;
-            }
-            if (have) vals[k] = bits;
+    for (int i = 0; i < EPI_WPT; ++i) {
+        const int64_t k = base + lane + 32 * i;
+        c[i] = (G.cnt && k < g.W) ? G.cnt[k] : 0;
+    }
+    double sv[EPIG_DIV][EPI_WPT];
+#pragma unroll
+    for (int j = 0; j < EPIG_DIV; ++j)
+#pragma unroll
+        for (int i = 0; i < EPI_WPT; ++i) {
+            const int64_t k = base + lane + 32 * i;
+            sv[j][i] = (j < G.n_div && k < g.W && c[i] > 0) ? G.div_src[j][k] : 0.0;
         }
+    const double width = (double)(int64_t)g.div.d;  // float64(w.LastValue - w.FirstValue), weightedmean.go:17,31
+#pragma unroll
+    for (int i = 0; i < EPI_WPT; ++i) {
+        const int64_t k = base + lane + 32 * i;
+        const bool in = k < g.W;
+        const bool valid = in && c[i] > 0;
+        if (in) {
+            if (!valid)
+                for (int j = 0; j < G.n_null; ++j) G.null_vals[j][k] = 0;  // null slot; Sum of an empty window = 0.0
+#pragma unroll
+            for (int j = 0; j < EPIG_DIV; ++j)
+                if (j < G.n_div)  // arithmeticmean.go:28 / weightedmean.go:17,31; null slots hold 0
+                    G.div_dst[j][k] = valid ? __ddiv_rn(sv[j][i], G.div_by_cnt[j] ? (double)c[i] : width) : 0.0;
+            for (int j = 0; j < G.n_ws; ++j) G.ws[j][k] = (int64_t)((uint64_t)g.s0 + (uint64_t)k * g.div.d);
+        }
+        // one ballot = the 32 validity bits of windows w0 .. w0 + 31; a partial last word is stored bytewise so that
+        // nothing beyond ceil(W/8) bytes is touched
         const uint32_t ball = __ballot_sync(0xffffffffu, valid);
-        if ((lane & 7) == 0 && in) sp.validity[k >> 3] = (uint8_t)(ball >> lane);
+        const uint32_t ball_in = __ballot_sync(0xffffffffu, in);
+        const int64_t w0 = base + 32 * i;
+        if (lane == 0 && w0 < g.W) {
+            const bool whole = w0 + 32 <= g.W;
+            for (int j = 0; j < G.n_bm_cnt + G.n_bm_all; ++j) {
+                uint8_t *bm = j < G.n_bm_cnt ? G.bm_cnt[j] : G.bm_all[j - G.n_bm_cnt];
+                const uint32_t word = j < G.n_bm_cnt ? ball : ball_in;
+                if (whole)
+                    *reinterpret_cast<uint32_t *>(bm + (w0 >> 3)) = word;
+                else
+                    for (int64_t b = 0; w0 + 8 * b < g.W; ++b) bm[(w0 >> 3) + b] = (uint8_t)(word >> (8 * b));
+            }
+        }
     }
 }
 
 }  // namespace
 
+int launch_epilogue_group(const EpiGroup &G, WindowGeom g, cudaStream_t stream) {
+    if (g.W <= 0) return 0;
+    const int64_t per_block = (int64_t)EPI_NT * EPI_WPT;
+    epilogue_group_kernel<<<(unsigned)((g.W + per_block - 1) / per_block), EPI_NT, 0, stream>>>(G, g);
+    return (int)cudaGetLastError();
+}
+
 int launch_epilogue(const EpilogueSpec *specs, int nspecs, WindowGeom g, cudaStream_t stream) {
     if (g.W <= 0) return 0;
-    const int nt = 256;
+    const int64_t per_block = (int64_t)EPI_NT * EPI_WPT;
+    const unsigned grid = (unsigned)((g.W + per_block - 1) / per_block);
     for (int b = 0; b < nspecs; b += EPI_MAX) {
         EpiBatch B;
         const int m = nspecs - b < EPI_MAX ? nspecs - b : EPI_MAX;
         for (int i = 0; i < m; ++i) B.s[i] = specs[b + i];
-        const unsigned grid = (unsigned)((g.W + nt - 1) / nt);
-        if (m <= 4)
-            epilogue_kernel<4><<<grid, nt, 0, stream>>>(B, m, g);
-        else if (m <= 8)
-            epilogue_kernel<8><<<grid, nt, 0, stream>>>(B, m, g);
-        else
-            epilogue_kernel<EPI_MAX><<<grid, nt, 0, stream>>>(B, m, g);
+        epilogue_kernel<<<grid, EPI_NT, 0, stream>>>(B, m, g);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
     }

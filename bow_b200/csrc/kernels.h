@@ -152,6 +152,23 @@ struct EpilogueSpec {
 };
 int launch_epilogue(const EpilogueSpec *specs_host, int nspecs, WindowGeom g, cudaStream_t stream);
 
+// Fast path for the outputs of one input column that share a per-window count (and carry no Factor): one read of
+// the count drives every validity bitmap, the zeros of null slots, the mean / weighted-average divisions and the
+// WindowStart column.
+constexpr int EPIG_NULL = 8, EPIG_BM = 12, EPIG_ALL = 4, EPIG_DIV = 4, EPIG_WS = 4;
+struct EpiGroup {
+    const int64_t *cnt;            // null: a group of always-valid outputs only (WindowStart)
+    int32_t n_null, n_bm_cnt, n_bm_all, n_div, n_ws, _pad;
+    uint64_t *null_vals[EPIG_NULL];  // final values are already there; slots of windows with cnt == 0 are zeroed
+    uint8_t *bm_cnt[EPIG_BM];        // validity bitmaps: valid iff cnt > 0
+    uint8_t *bm_all[EPIG_ALL];       // validity bitmaps: always valid (Count, Sum, WindowStart)
+    double *div_dst[EPIG_DIV];       // dst = src / (by_cnt ? float64(cnt) : float64(interval)), 0 where cnt == 0
+    const double *div_src[EPIG_DIV];
+    int32_t div_by_cnt[EPIG_DIV];
+    int64_t *ws[EPIG_WS];            // WindowStart outputs
+};
+int launch_epilogue_group(const EpiGroup &G, WindowGeom g, cudaStream_t stream);
+
 // ---- utilities ------------------------------------------------------------------------------------
 // dst bitmap (bit offset 0, padded bytes zeroed up to dst_bytes) from src bitmap at bit offset `off`
 int launch_bitmap_realign(const uint8_t *src, int64_t off, int64_t nbits, uint8_t *dst, int64_t dst_bytes,
