@@ -18,9 +18,14 @@ namespace bowgpu {
 
 namespace {
 
+#ifndef SEG_INT_CTAS
+#define SEG_INT_CTAS 3
+#endif
+
 struct IState {
     double fT, fV, lT, lV, sS, sT;
-    uint32_t n;
+    uint32_t n;    // points (updated when rows are noted, i.e. at window boundaries and phase ends)
+    uint32_t has;  // a point has been accumulated since the run began (per-row flag; n > 0 once noted)
 };
 
 struct alignas(16) ICarry {
@@ -63,23 +68,31 @@ struct IntegralPol {
         s.fT = s.fV = s.lT = s.lV = 0.0;
         s.sS = s.sT = 0.0;
         s.n = 0;
+        s.has = 0;
         return s;
     }
+    // One valid point, branch free: the joint term with the previous point is formed unconditionally and selected
+    // away for the first point of a run (adding +0.0 never changes a sum that started at +0.0).
     static __device__ __forceinline__ void accumulate(State &s, int64_t t, uint64_t raw) {
         const double T = (double)t, v = val(raw);
-        if (s.n) {
-            const double dt = T - s.lT;
-            if (STEP) s.sS += s.lV * dt;              // integral.go:57
-            if (TRAP) s.sT += (s.lV + v) / 2 * dt;    // integral.go:28
-        } else {
-            s.fT = T;
-            s.fV = v;
-        }
+        const double dt = T - s.lT;
+        if (STEP) s.sS += s.has ? s.lV * dt : 0.0;                // integral.go:57
+        if (TRAP) s.sT += s.has ? (s.lV + v) / 2 * dt : 0.0;      // integral.go:28
         s.lT = T;
         s.lV = v;
-        s.n += 1;
+        s.has = 1;
     }
-    static __device__ __forceinline__ void note(State &, uint32_t, const uint64_t *) {}
+    // the number of points and the first point of a run come from the validity bits of the rows that joined it
+    static __device__ __forceinline__ void note(State &s, uint32_t mask, const int64_t *trow, const uint64_t *vrow) {
+        if (mask) {
+            if (s.n == 0) {
+                const int j = __ffs(mask) - 1;
+                s.fT = (double)trow[j];
+                s.fV = val(vrow[j]);
+            }
+            s.n += __popc(mask);
+        }
+    }
     static __device__ __forceinline__ State combine(const State &L, const State &R) {
         State o;
         const bool l = L.n != 0, r = R.n != 0;
@@ -97,6 +110,7 @@ struct IntegralPol {
         o.lT = r ? R.lT : L.lT;
         o.lV = r ? R.lV : L.lV;
         o.n = L.n + R.n;
+        o.has = o.n != 0;
         return o;
     }
     static __device__ __forceinline__ State shfl_up(const State &s, int d) {
@@ -108,6 +122,7 @@ struct IntegralPol {
         if (STEP) o.sS = __shfl_up_sync(0xffffffffu, s.sS, d);
         if (TRAP) o.sT = __shfl_up_sync(0xffffffffu, s.sT, d);
         o.n = __shfl_up_sync(0xffffffffu, s.n, d);
+        o.has = o.n != 0;
         return o;
     }
     static __device__ __forceinline__ void finish(const Out &o, int64_t W, int64_t s0, uint64_t d, int64_t k, int64_t n,
@@ -207,13 +222,13 @@ int launch_mode(const IntLaunch &L, int sm, cudaStream_t s, cudaEvent_t e0, cuda
     if (L.is_int) {
         SegArgs<IntegralPol<STEP, TRAP, true>> A;
         fill(A);
-        return nulls ? seg_launch<IntegralPol<STEP, TRAP, true>, true, 2>(A, sm, s, e0, e1)
-                     : seg_launch<IntegralPol<STEP, TRAP, true>, false, 2>(A, sm, s, e0, e1);
+        return nulls ? seg_launch<IntegralPol<STEP, TRAP, true>, true, SEG_INT_CTAS>(A, sm, s, e0, e1)
+                     : seg_launch<IntegralPol<STEP, TRAP, true>, false, SEG_INT_CTAS>(A, sm, s, e0, e1);
     }
     SegArgs<IntegralPol<STEP, TRAP, false>> A;
     fill(A);
-    return nulls ? seg_launch<IntegralPol<STEP, TRAP, false>, true, 2>(A, sm, s, e0, e1)
-                 : seg_launch<IntegralPol<STEP, TRAP, false>, false, 2>(A, sm, s, e0, e1);
+    return nulls ? seg_launch<IntegralPol<STEP, TRAP, false>, true, SEG_INT_CTAS>(A, sm, s, e0, e1)
+                 : seg_launch<IntegralPol<STEP, TRAP, false>, false, SEG_INT_CTAS>(A, sm, s, e0, e1);
 }
 
 }  // namespace

@@ -29,7 +29,7 @@
 //
 // Policy interface (all static, device):
 //   State, Carry, Out, Inc                      types (Inc = the inclusive row of a window, rolling.go:201-209)
-//   identity(), accumulate(State&, t, raw), note(State&, mask, vrow), combine(L, R), shfl_up(s, d)
+//   identity(), accumulate(State&, t, raw), note(State&, mask, trow, vrow), combine(L, R), shfl_up(s, d)
 //   make_inc(at_end, valid_next, raw_next, t_next)
 //   write(out, g, k, state, inc)                final values of a window
 //   make_carry(state, inc, key, closed) -> Carry; carry_* accessors; write_carry
@@ -188,7 +188,7 @@ __device__ __forceinline__ void seg_phase(SegThread<Pol> &c, const SegArgs<Pol> 
             bad |= xj < c.xlast;
             c.xlast = xj;
             if (xj >= c.eabs) {  // row j starts a later window: the open one is complete
-                Pol::note(c.st, vbits & ((1u << j) - 1u) & ~((1u << segstart) - 1u), vrow);
+                Pol::note(c.st, vbits & ((1u << j) - 1u) & ~((1u << segstart) - 1u), trow, vrow);
                 const Inc inc = Pol::make_inc(xj == c.eabs, (vbits >> j) & 1u, rj, xj);
                 if (c.nclose == 0) {
                     c.head = c.st;
@@ -219,7 +219,7 @@ __device__ __forceinline__ void seg_phase(SegThread<Pol> &c, const SegArgs<Pol> 
         ta = tb;
         va = vb;
     }
-    Pol::note(c.st, vbits & ~((1u << segstart) - 1u), vrow);
+    Pol::note(c.st, vbits & ~((1u << segstart) - 1u), trow, vrow);
 }
 
 // End of a tile: stitch the per-thread pieces.
