@@ -79,6 +79,8 @@ struct bowgpu_rolling {
     bool has_after_early = false;
     bool has_prev = false;
     bool shard = false;  // range-partitioned shard: rows before s0 are the left halo (never part of a window)
+    bool whole = false;  // aggregation.Aggregate over the whole Bow: one window, see WindowGeom
+    int64_t whole_first = 0, whole_last = 0;
     std::vector<PrevCell> prev;
 };
 
@@ -271,6 +273,10 @@ WindowGeom make_geom(const bowgpu_rolling *r, bool inclusive_eff) {
     // iteration is inclusive (rolling.go:194-211: they are only part of the slice if lastRowIndex is set)
     g.early_keep = 0;
     g.shard = r->shard;
+    g.whole = r->whole;
+    g.whole_first = r->whole_first;
+    g.whole_last = r->whole_last;
+    g._pad = 0;
     if (!r->shard && r->early_rows > 0 && r->has_after_early) {
         const uint64_t rel = (uint64_t)r->t_after_early - (uint64_t)r->s0;
         g.early_keep = rel < (uint64_t)r->interval || (inclusive_eff && rel == (uint64_t)r->interval);
@@ -863,6 +869,10 @@ extern "C" int32_t bowgpu_agg_needs_inclusive(int32_t op) {
     return op == BOWGPU_AGG_INTEGRAL_TRAPEZOID || op == BOWGPU_AGG_WAVG_LINEAR;
 }
 
+static int32_t whole_return_type(int32_t op, int32_t input_dtype) {  // whole.go:44-46: iterator type := input column type
+    return op == BOWGPU_AGG_WINDOW_START ? input_dtype : bowgpu_agg_return_type(op, input_dtype);
+}
+
 extern "C" int32_t bowgpu_rolling_aggregate(bowgpu_rolling *r, const bowgpu_agg_spec *specs, int32_t nspecs,
                                             bowgpu_out_col *outs, int32_t mem) {
     if (!r || !specs || !outs || nspecs <= 0) return BOWGPU_EINVAL;
@@ -878,8 +888,11 @@ extern "C" int32_t bowgpu_rolling_aggregate(bowgpu_rolling *r, const bowgpu_agg_
         if (bowgpu_agg_needs_inclusive(specs[j].op)) inclusive_eff = true;
         if (specs[j].col == r->time_col) keeps_interval = true;
     }
-    if (!keeps_interval) return fail(ctx, BOWGPU_ENOINTERVALCOL, "must keep interval column");  // aggregation.go:163-166
-    for (int j = 0; j < nspecs; ++j) outs[j].dtype = bowgpu_agg_return_type(specs[j].op, f->cols[specs[j].col].dtype);
+    if (!keeps_interval && !r->whole)
+        return fail(ctx, BOWGPU_ENOINTERVALCOL, "must keep interval column");  // aggregation.go:163-166
+    for (int j = 0; j < nspecs; ++j)
+        outs[j].dtype = r->whole ? whole_return_type(specs[j].op, f->cols[specs[j].col].dtype)
+                                 : bowgpu_agg_return_type(specs[j].op, f->cols[specs[j].col].dtype);
     const WindowGeom g = make_geom(r, inclusive_eff);
     const int64_t W = g.W;
     if (W == 0) return BOWGPU_OK;
@@ -1055,6 +1068,12 @@ extern "C" int32_t bowgpu_rolling_aggregate(bowgpu_rolling *r, const bowgpu_agg_
         };
         for (int j = 0; j < nspecs; ++j) {
             const int op = specs[j].op;
+            if (r->whole && op == BOWGPU_AGG_WINDOW_START && f->cols[specs[j].col].dtype != BOWGPU_INT64) {
+                // whole.go:87 SetOrDropStrict: the int64 window start does not fit the Float64 buffer -> null
+                CK(cudaMemsetAsync(dvals[j], 0, (size_t)W * 8, ctx->stream));
+                CK(cudaMemsetAsync(dbits[j], 0, (size_t)((W + 7) / 8), ctx->stream));
+                continue;
+            }
             if (specs[j].nfactors > 0) {
                 EpilogueSpec e;
                 memset(&e, 0, sizeof e);
@@ -1111,6 +1130,49 @@ extern "C" int32_t bowgpu_rolling_aggregate(bowgpu_rolling *r, const bowgpu_agg_
         if (rc) return rc;
     }
     return check_status(ctx);
+}
+
+// aggregation.Aggregate(b, intervalCol, aggrs...) (rolling/aggregation/whole.go:12-93): every aggregation over ONE window
+// that holds the whole frame.  Runs the same kernels as Rolling.Aggregate with an interval that spans all rows.
+extern "C" int32_t bowgpu_frame_aggregate_whole(bowgpu_frame *frame, int32_t time_col, const bowgpu_agg_spec *specs,
+                                                int32_t nspecs, bowgpu_out_col *outs, int32_t mem) {
+    if (!frame || !specs || !outs || nspecs <= 0) return BOWGPU_EINVAL;
+    bowgpu_ctx *ctx = frame->ctx;
+    Guard gd(ctx);
+    const int ncols = (int)frame->cols.size();
+    if (time_col < 0 || time_col >= ncols) return fail(ctx, BOWGPU_EINVAL, "time column index %d out of range", time_col);
+    if (frame->cols[time_col].dtype != BOWGPU_INT64)
+        return fail(ctx, BOWGPU_ETYPE, "the GPU path needs an Int64 interval column");
+    for (int j = 0; j < nspecs; ++j) {
+        if (specs[j].col < 0 || specs[j].col >= ncols) return fail(ctx, BOWGPU_EINVAL, "column aggregation %d: no column %d", j, specs[j].col);
+        if (specs[j].op < 0 || specs[j].op >= BOWGPU_AGG__COUNT) return fail(ctx, BOWGPU_EUNSUPPORTED, "column aggregation %d: unknown opcode %d", j, specs[j].op);
+        outs[j].dtype = whole_return_type(specs[j].op, frame->cols[specs[j].col].dtype);
+    }
+    const int64_t n = frame->n;
+    if (n == 0) return BOWGPU_OK;  // whole.go:49-50: zero-length output columns
+    const DevCol &tc = frame->cols[time_col];
+    if (tc.validity && tc.null_count != 0)
+        return fail(ctx, BOWGPU_ENULLTIME, "interval column holds %lld nulls: the GPU path requires a non-null, sorted interval column",
+                    (long long)tc.null_count);
+    int64_t ends[2];
+    CK(cudaMemcpyAsync(&ends[0], tc.values, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&ends[1], tc.values + (n - 1), 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ends[1] < ends[0]) return fail(ctx, BOWGPU_EUNSORTED, "time column is not sorted ascending");
+    if (ends[1] == INT64_MAX) return fail(ctx, BOWGPU_EUNSUPPORTED, "last time value is the largest int64");
+    bowgpu_rolling r;
+    r.frame = frame;
+    r.time_col = time_col;
+    r.interval = (int64_t)((uint64_t)ends[1] - (uint64_t)ends[0] + 1);  // all rows fall into window 0, none at its end
+    if (r.interval <= 0) return fail(ctx, BOWGPU_EUNSUPPORTED, "time span does not fit 63 bits");
+    r.s0 = ends[0];
+    r.W = 1;
+    r.t_first = ends[0];
+    r.t_last = ends[1];
+    r.whole = true;
+    r.whole_first = f64_to_i64_go((double)ends[0]);  // int64(firstValue) through GetNextFloat64, whole.go:54-70
+    r.whole_last = f64_to_i64_go((double)ends[1]);
+    return bowgpu_rolling_aggregate(&r, specs, nspecs, outs, mem);
 }
 
 extern "C" int32_t bowgpu_rolling_interpolate(bowgpu_rolling *r, const int32_t *ops, int32_t nops, bowgpu_frame **out_frame,

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(EPI_NT) epilogue_kernel(const __grid_constant_
                 bool have = false;  // value already computed in a register
                 uint64_t bits = 0;
                 if (sp.op == BOWGPU_AGG_WINDOW_START) {
-                    bits = (uint64_t)g.s0 + (uint64_t)k[i] * g.div.d;
+                    bits = (uint64_t)window_first_value(g, k[i]);
                     have = true;
                 } else if (sp.op == BOWGPU_AGG_COUNT) {
                     bits = (uint64_t)c[i];
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(EPI_NT) epilogue_kernel(const __grid_constant_
                     have = true;
                 } else if (sp.op == BOWGPU_AGG_WAVG_STEP || sp.op == BOWGPU_AGG_WAVG_LINEAR) {
                     // integral / float64(w.LastValue - w.FirstValue), weightedmean.go:17,31
-                    bits = f64_as_bits(__ddiv_rn(sv[i], (double)(int64_t)g.div.d));
+                    bits = f64_as_bits(__ddiv_rn(sv[i], g.whole ? (double)(g.whole_last - g.whole_first) : (double)(int64_t)g.div.d));
                     have = true;
                 }
                 if (valid && sp.nfactors > 0) {
@@ -125,7 +125,8 @@ __global__ void __launch_bounds__(EPI_NT) epilogue_group_kernel(const __grid_con
             const int64_t k = base + lane + 32 * i;
             sv[j][i] = (j < G.n_div && k < g.W && c[i] > 0) ? G.div_src[j][k] : 0.0;
         }
-    const double width = (double)(int64_t)g.div.d;  // float64(w.LastValue - w.FirstValue), weightedmean.go:17,31
+    // float64(w.LastValue - w.FirstValue), weightedmean.go:17,31 (the interval, except for the whole-Bow window)
+    const double width = g.whole ? (double)(g.whole_last - g.whole_first) : (double)(int64_t)g.div.d;
 #pragma unroll
     for (int i = 0; i < EPI_WPT; ++i) {
         const int64_t k = base + lane + 32 * i;
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(EPI_NT) epilogue_group_kernel(const __grid_con
             for (int j = 0; j < EPIG_DIV; ++j)
                 if (j < G.n_div)  // arithmeticmean.go:28 / weightedmean.go:17,31; null slots hold 0
                     G.div_dst[j][k] = valid ? __ddiv_rn(sv[j][i], G.div_by_cnt[j] ? (double)c[i] : width) : 0.0;
-            for (int j = 0; j < G.n_ws; ++j) G.ws[j][k] = (int64_t)((uint64_t)g.s0 + (uint64_t)k * g.div.d);
+            for (int j = 0; j < G.n_ws; ++j) G.ws[j][k] = window_first_value(g, k);
         }
         // one ballot = the 32 validity bits of windows w0 .. w0 + 31; a partial last word is stored bytewise so that
         // nothing beyond ceil(W/8) bytes is touched

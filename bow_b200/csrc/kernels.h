@@ -20,7 +20,18 @@ struct WindowGeom {
     int64_t early_rows;
     int32_t early_keep;
     int32_t shard;
+    // aggregation.Aggregate over the whole Bow (rolling/aggregation/whole.go): ONE window holding every row, whose
+    // FirstValue / LastValue are the first / last times (through float64) instead of lattice values
+    int64_t whole_first, whole_last;
+    int32_t whole;
+    int32_t _pad;
 };
+__host__ __device__ __forceinline__ int64_t window_first_value(const WindowGeom &g, int64_t k) {
+    return g.whole ? g.whole_first : (int64_t)((uint64_t)g.s0 + (uint64_t)k * g.div.d);
+}
+__host__ __device__ __forceinline__ int64_t window_last_value(const WindowGeom &g, int64_t k) {
+    return g.whole ? g.whole_last : (int64_t)((uint64_t)g.s0 + ((uint64_t)k + 1) * g.div.d);
+}
 
 // status word bits written by the kernels
 enum { ST_UNSORTED = 1 };

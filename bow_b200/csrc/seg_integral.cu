@@ -125,12 +125,12 @@ struct IntegralPol {
         o.has = o.n != 0;
         return o;
     }
-    static __device__ __forceinline__ void finish(const Out &o, int64_t W, int64_t s0, uint64_t d, int64_t k, int64_t n,
+    static __device__ __forceinline__ void finish(const Out &o, const WindowGeom &g, int64_t k, int64_t n,
                                                   double lT, double lV, double sS, double sT, bool inc_has,
                                                   double incV, double incT) {
-        if ((uint64_t)k >= (uint64_t)W) return;
+        if ((uint64_t)k >= (uint64_t)g.W) return;
         if (STEP && n > 0) {
-            const double E = (double)(int64_t)((uint64_t)s0 + ((uint64_t)k + 1) * d);  // float64(w.LastValue)
+            const double E = (double)window_last_value(g, k);  // float64(w.LastValue)
             o.step[k] = sS + lV * (E - lT);                                             // integral.go:53-57
             o.n_step[k] = n;
         }
@@ -143,7 +143,7 @@ struct IntegralPol {
     }
     static __device__ __forceinline__ void write(const Out &o, const WindowGeom &g, int64_t k, const State &s,
                                                  const Inc &inc) {
-        finish(o, g.W, g.s0, g.div.d, k, s.n, s.lT, s.lV, s.sS, s.sT, TRAP && inc.has, inc.v, inc.T);
+        finish(o, g, k, s.n, s.lT, s.lV, s.sS, s.sT, TRAP && inc.has, inc.v, inc.T);
     }
     static __device__ __forceinline__ Carry make_carry(const State &s, const Inc &inc, int64_t key, bool closed) {
         Carry c;
@@ -202,7 +202,7 @@ struct IntegralPol {
         a.incT = h.incT;
     }
     static __device__ __forceinline__ void write_carry(const Out &o, const WindowGeom &g, int64_t k, const Carry &a) {
-        finish(o, g.W, g.s0, g.div.d, k, a.n & ~I_CLOSED_BIT, a.lT, a.lV, a.sS, a.sT, a.inc_has != 0, a.incV, a.incT);
+        finish(o, g, k, a.n & ~I_CLOSED_BIT, a.lT, a.lV, a.sS, a.sT, a.inc_has != 0, a.incV, a.incT);
     }
 };
 

@@ -34,7 +34,7 @@ SYMBOLS = [
     "bowgpu_rolling_create", "bowgpu_rolling_create_shard", "bowgpu_rolling_destroy", "bowgpu_rolling_num_windows",
     "bowgpu_rolling_first_window_start", "bowgpu_rolling_inclusive", "bowgpu_rolling_early_rows",
     "bowgpu_rolling_bounds", "bowgpu_rolling_aggregate", "bowgpu_agg_return_type", "bowgpu_agg_needs_inclusive",
-    "bowgpu_rolling_interpolate",
+    "bowgpu_rolling_interpolate", "bowgpu_frame_aggregate_whole",
 ]
 
 
@@ -103,6 +103,8 @@ def lib():
         L.bowgpu_rolling_bounds.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.bowgpu_rolling_aggregate.argtypes = [C.c_void_p, C.POINTER(AggSpec), C.c_int32, C.POINTER(OutCol),
                                                C.c_int32]
+        L.bowgpu_frame_aggregate_whole.argtypes = [C.c_void_p, C.c_int32, C.POINTER(AggSpec), C.c_int32, C.POINTER(OutCol),
+                                                   C.c_int32]
         L.bowgpu_rolling_interpolate.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int32,
                                                  C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
         L.bowgpu_rolling_early_rows.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
@@ -256,6 +258,25 @@ class Frame:
         for j, (v, b) in enumerate(bufs):
             vals = v[:n] if outs[j].dtype == INT64 else v[:n].view(np.float64)
             res.append((vals, unpack_bits(b, n)))
+        return res
+
+    def aggregate_whole(self, time_col: int, specs: Sequence[tuple]):
+        """aggregation.Aggregate over the whole frame (rolling/aggregation/whole.go) -> list of (values, valid mask)
+        with one entry each (none for an empty frame)"""
+        n_out = 1 if self.num_rows else 0
+        arr = make_specs(specs)
+        outs = (OutCol * len(specs))()
+        bufs = []
+        for j in range(len(specs)):
+            v = np.full(1, -7, dtype=np.int64)
+            b = np.full(1, 0xAA, dtype=np.uint8)
+            bufs.append((v, b))
+            outs[j].values, outs[j].validity = v.ctypes.data, b.ctypes.data
+        self.ctx.check(lib().bowgpu_frame_aggregate_whole(self.h, time_col, arr, len(specs), outs, MEM_HOST))
+        res = []
+        for j, (v, b) in enumerate(bufs):
+            vals = v[:n_out] if outs[j].dtype == INT64 else v[:n_out].view(np.float64)
+            res.append((vals, unpack_bits(b, n_out)))
         return res
 
     def close(self):

@@ -216,6 +216,15 @@ int32_t bowgpu_rolling_aggregate(bowgpu_rolling *r, const bowgpu_agg_spec *specs
 int32_t bowgpu_agg_return_type(int32_t op, int32_t input_dtype);
 int32_t bowgpu_agg_needs_inclusive(int32_t op); /* integral.go:9, weightedmean.go:24 */
 
+/* aggregation.Aggregate(b, intervalColName, aggrs...) — every aggregation over ONE window holding the whole Bow
+ * (rolling/aggregation/whole.go:12-93).  outs[j] receives ONE entry (none when the frame has no rows): 8 value
+ * bytes + 1 validity byte.  Window.FirstValue / LastValue are the first / last times taken through float64
+ * (whole.go:54-70); the return type uses the INPUT column as iterator type (whole.go:44-46) and values are stored
+ * with SetOrDropStrict (whole.go:87), so WindowStart of a Float64 column is null.  The interval column need not be
+ * among the aggregated columns.  Same GPU-path precondition: sorted, non-null Int64 interval column. */
+int32_t bowgpu_frame_aggregate_whole(bowgpu_frame *frame, int32_t time_col, const bowgpu_agg_spec *specs,
+                                     int32_t nspecs, bowgpu_out_col *outs, int32_t mem);
+
 /* Rolling.Interpolate (interpolation.go:30-161).  ops[j] is the interpolation of column j (the
  * reference matches columns by position, bowappend.go:28-47, so nops must equal the number of
  * columns).  The result is a new device-resident frame with n_out rows. */

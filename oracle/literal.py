@@ -725,3 +725,47 @@ def InterpLinear(col: str) -> ColInterpolation:           # interpolation/linear
             coef = num / d
         return ((v2 - v0) * coef) + v0
     return ColInterpolation(col, [INT64, FLOAT64], fn)
+
+
+# ----------------------------------------------------------------------------
+# rolling/aggregation/whole.go:12-93 — aggregation.Aggregate: ONE window over the whole Bow
+# ----------------------------------------------------------------------------
+def whole_aggregate(b: Frame, interval_col_name: str, *aggrs: ColAggregation) -> Frame:
+    if b is None:
+        raise ValueError("nil bow")
+    if len(aggrs) == 0:
+        raise ValueError("at least one column aggregation is required")
+    interval_col = b.column_index(interval_col_name)
+    names, types, cols = [], [], []
+    for i, a in enumerate(aggrs):
+        if a.input_name == "":
+            raise ValueError(f"column aggregation {i}: no input name")
+        try:
+            a.input_index = b.column_index(a.input_name)
+        except KeyError as e:
+            raise KeyError(f"column aggregation {i}: {e.args[0]}")
+        name = a.output_name or b.names[a.input_index]
+        typ = a.return_type(b.types[a.input_index], b.types[a.input_index])     # whole.go:44-46
+        if b.num_rows() == 0:
+            buf = []
+        else:
+            buf = [None]
+            first_value, first_index = b.get_next_float64(interval_col, 0)       # whole.go:54-57
+            if first_index == -1:
+                first_value = -1.0
+            last_value, last_index = b.get_prev_float64(interval_col, b.num_rows() - 1)
+            if last_index == -1:
+                last_value = -1.0
+            w = Window(b, 0, interval_col, f64_to_i64(first_value), f64_to_i64(last_value), True)
+            val = a.fn(a.input_index, w)
+            for tr in a.transformations:
+                val = tr(val)
+            # Buffer.SetOrDropStrict (bowbuffer.go:82-104): plain type assertion, no conversion
+            if typ == INT64 and isinstance(val, int) and not isinstance(val, bool):
+                buf[0] = val
+            elif typ == FLOAT64 and isinstance(val, float):
+                buf[0] = val
+        names.append(name)
+        types.append(typ)
+        cols.append(buf)
+    return Frame(names, types, cols)

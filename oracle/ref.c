@@ -471,6 +471,67 @@ int bowref_aggregate(const bowref_rolling *r, const bowref_agg_spec *specs, int3
     return BOWREF_OK;
 }
 
+/* aggregation.Aggregate (whole frame, ONE window), rolling/aggregation/whole.go:12-93.
+ * The window holds every row of the Bow; FirstValue / LastValue are the first / last non-null times taken
+ * through float64 (GetNextFloat64 / GetPrevFloat64, whole.go:54-62; -1 when the column has none); the return
+ * type is resolved with the INPUT column as iterator type (whole.go:44-46) and the value is stored with
+ * SetOrDropStrict (whole.go:87, bowbuffer.go:82-104): a dynamic type different from the buffer type gives null.
+ * outs[j].values / validity hold 1 entry (0 entries when the Bow has no rows). */
+static int32_t whole_return_type(int op, int32_t input_type) {
+    switch (op) {
+    case BOWREF_AGG_WINDOW_START: return input_type; /* IteratorDependent, iterator := input column */
+    case BOWREF_AGG_COUNT: return BOWREF_INT64;
+    case BOWREF_AGG_FIRST:
+    case BOWREF_AGG_LAST: return input_type;
+    default: return BOWREF_FLOAT64;
+    }
+}
+int bowref_aggregate_whole(const bowref_col *cols, int32_t ncols, int32_t time_col, const bowref_agg_spec *specs,
+                           int32_t nspecs, bowref_out_col *outs) {
+    if (nspecs <= 0 || time_col < 0 || time_col >= ncols) return BOWREF_EINVAL;
+    const int64_t n = ncols ? cols[0].length : 0;
+    bowref_rolling r;
+    memset(&r, 0, sizeof r);
+    r.cols = cols;
+    r.ncols = ncols;
+    r.time_col = time_col;
+    r.nrows = n;
+    for (int j = 0; j < nspecs; j++) {
+        const bowref_agg_spec *a = &specs[j];
+        if (a->col < 0 || a->col >= ncols) return BOWREF_EINVAL;
+        const int32_t typ = whole_return_type(a->op, cols[a->col].dtype);
+        outs[j].dtype = typ;
+        if (n == 0) continue;
+        memset(outs[j].values, 0, 8);
+        outs[j].validity[0] = 0;
+        const bowref_col *tc = &cols[time_col];
+        double first_value = -1, last_value = -1;
+        for (int64_t i = 0; i < n; i++)
+            if (col_valid(tc, i)) { first_value = col_f64(tc, i); break; }
+        for (int64_t i = n - 1; i >= 0; i--)
+            if (col_valid(tc, i)) { last_value = col_f64(tc, i); break; }
+        bowref_window w;
+        memset(&w, 0, sizeof w);
+        w.lo = 0;
+        w.hi = n;
+        w.first_index = 0;
+        w.first_value = f64_to_i64(first_value);
+        w.last_value = f64_to_i64(last_value);
+        w.is_inclusive = 1;
+        ref_value v = agg_closure(&r, a->op, a->col, &w);
+        for (int k = 0; k < a->nfactors; k++) v = apply_factor(v, a->factors[k]);
+        if (v.is_nil) continue;
+        if (typ == BOWREF_INT64 && v.is_int) { /* SetOrDropStrict: value.(int64) */
+            ((int64_t *)outs[j].values)[0] = v.i;
+            outs[j].validity[0] = 1;
+        } else if (typ == BOWREF_FLOAT64 && !v.is_int) { /* value.(float64) */
+            ((double *)outs[j].values)[0] = v.f;
+            outs[j].validity[0] = 1;
+        }
+    }
+    return BOWREF_OK;
+}
+
 /* ---- Window iteration export: first[k], end[k] (exclusive, incl. the inclusive row), inclusive flag */
 int64_t bowref_windows(const bowref_rolling *r, int64_t *first_index, int64_t *lo, int64_t *hi, int64_t *first_value,
                        uint8_t *is_inclusive) {

@@ -179,3 +179,31 @@ class RefRolling:
             v = vals[j][:n_out] if self.frame.dtypes[j] == INT64 else vals[j][:n_out].view(np.float64)
             res.append((v, unpack_bits(bms[j], n_out)))
         return res
+
+
+def aggregate_whole(frame: Frame, time_col: int, specs: Sequence[tuple]):
+    """aggregation.Aggregate over the whole frame (rolling/aggregation/whole.go) -> list of (values, valid mask)
+    with one entry each (zero entries for an empty frame)."""
+    n_out = 1 if frame.n else 0
+    arr = (AggSpec * len(specs))()
+    outs = (OutCol * len(specs))()
+    bufs = []
+    for j, s in enumerate(specs):
+        op = AGG[s[0]] if isinstance(s[0], str) else s[0]
+        arr[j].op, arr[j].col = op, s[1]
+        fs = list(s[2]) if len(s) > 2 and s[2] else []
+        arr[j].nfactors = len(fs)
+        for k, f in enumerate(fs):
+            arr[j].factors[k] = f
+        v = np.zeros(1, dtype=np.int64)
+        b = np.zeros(1, dtype=np.uint8)
+        bufs.append((v, b))
+        outs[j].values, outs[j].validity = v.ctypes.data, b.ctypes.data
+    rc = lib().bowref_aggregate_whole(frame.arr, frame.ncols, time_col, arr, len(specs), outs)
+    if rc:
+        raise RefError(rc)
+    res = []
+    for j, (v, b) in enumerate(bufs):
+        vals = v[:n_out] if outs[j].dtype == INT64 else v[:n_out].view(np.float64)
+        res.append((vals, unpack_bits(b, n_out)))
+    return res

@@ -240,3 +240,31 @@ FACTOR = [
 
 # rolling/aggregation_test.go:125-171 TestWindow_UnsetInclusive
 UNSET_INCLUSIVE = dict(cols=[[1, 2], [1, 2]], first_value=0, last_value=2, expected_cols=[[1], [1]])
+
+
+# ---- aggregation.Aggregate over the whole Bow: rolling/aggregation/whole_test.go:11-290 (Int64 / Float64 cases) ----
+# entries: (name, rows [(time, value)], aggregations [(constructor name, column name, output name or None)],
+#           expected {"names": [...], "types": [...], "cols": [[...], ...]} or an error string, citation)
+WHOLE_ROWS = [(10, 1.0), (20, 2.0), (30, 3.0)]
+WHOLE_CASES = [
+    ("empty bow", [], [("WindowStart", "time", None), ("ArithmeticMean", "value", None)],
+     {"names": ["time", "value"], "types": ["int64", "float64"], "cols": [[], []]}, "whole_test.go:12-29"),
+    ("keep columns", WHOLE_ROWS, [("WindowStart", "time", None), ("ArithmeticMean", "value", None)],
+     {"names": ["time", "value"], "types": ["int64", "float64"], "cols": [[10], [2.0]]}, "whole_test.go:31-54"),
+    ("swap columns", WHOLE_ROWS, [("ArithmeticMean", "value", None), ("WindowStart", "time", None)],
+     {"names": ["value", "time"], "types": ["float64", "int64"], "cols": [[2.0], [10]]}, "whole_test.go:56-79"),
+    ("rename columns", WHOLE_ROWS, [("WindowStart", "time", "a"), ("ArithmeticMean", "value", "b")],
+     {"names": ["a", "b"], "types": ["int64", "float64"], "cols": [[10], [2.0]]}, "whole_test.go:81-104"),
+    ("less columns than original", WHOLE_ROWS, [("ArithmeticMean", "value", None)],
+     {"names": ["value"], "types": ["float64"], "cols": [[2.0]]}, "whole_test.go:106-127"),
+    ("more columns than original", WHOLE_ROWS,
+     [("ArithmeticMean", "value", "a"), ("ArithmeticMean", "value", "b"), ("ArithmeticMean", "value", "c")],
+     {"names": ["a", "b", "c"], "types": ["float64"] * 3, "cols": [[2.0], [2.0], [2.0]]}, "whole_test.go:129-154"),
+    ("invalid column", WHOLE_ROWS, [("WindowStart", "-", None)], "column aggregation 0: no column '-'",
+     "whole_test.go:156-168"),
+    ("float", WHOLE_ROWS, [("WindowStart", "time", None), ("ArithmeticMean", "value", None)],
+     {"names": ["time", "value"], "types": ["int64", "float64"], "cols": [[10], [2.0]]}, "whole_test.go:170-193"),
+    ("float only nil", [(10, N), (20, N), (30, N)],
+     [("WindowStart", "time", None), ("WeightedAverageLinear", "value", None)],
+     {"names": ["time", "value"], "types": ["int64", "float64"], "cols": [[10], [N]]}, "whole_test.go:194-217"),
+]

@@ -278,3 +278,55 @@ def test_sharded_matches_oracle(ctx, g):
             else:
                 assert np.allclose(gv, wv, rtol=1e-11, atol=1e-9), (kind, sp)
     runtime.set_default_ctx(None)
+
+
+# ---- aggregation.Aggregate over the whole Bow (rolling/aggregation/whole.go) ---------------------------------------
+WHOLE_ALL = ["WindowStart", "Count", "Sum", "ArithmeticMean", "Min", "Max", "First", "Last", "IntegralStep",
+             "IntegralTrapezoid", "WeightedAverageStep", "WeightedAverageLinear"]
+
+
+@pytest.mark.parametrize("name,rows,aggs,expected,cite", [c for c in G.WHOLE_CASES if not isinstance(c[3], str)],
+                         ids=[c[0] for c in G.WHOLE_CASES if not isinstance(c[3], str)])
+def test_whole_golden(ctx, name, rows, aggs, expected, cite):
+    from bow_b200 import native as N
+    t = np.array([r[0] for r in rows], dtype=np.int64)
+    v = np.array([0.0 if r[1] is None else r[1] for r in rows], dtype=np.float64)
+    m = np.array([r[1] is not None for r in rows], dtype=bool)
+    fr = N.Frame.from_numpy(ctx, [(t, None), (v, m)])
+    got = fr.aggregate_whole(0, [(ctor, 0 if col == "time" else 1) for ctor, col, _ in aggs])
+    for (gv, gm), want in zip(got, expected["cols"]):
+        assert [x if ok else None for x, ok in zip(gv.tolist(), gm.tolist())] == want, cite
+    fr.close()
+
+
+@pytest.mark.parametrize("kind", ["regular", "dense", "sparse", "bursty"])
+def test_whole_random_vs_oracle(ctx, kind):
+    """one window over the whole frame, all aggregations on a float64 and an int64 column (+ Factor), sizes around
+    the tile edges; bit-exact except sums / means / integrals (1e-12 relative to the sum of |terms|)"""
+    from bow_b200 import native as N
+    rng = np.random.default_rng(hash(("whole", kind)) & 0xFFFF)
+    for n in (0, 1, 2, 17, 300, 8191, 8192, 8193, 16385, 40000):
+        t = H.random_times(rng, n, kind)
+        if n:
+            t = t - int(t[0]) + int(rng.integers(0, 1000))
+        vf = H.random_values(rng, n, np.float64, float(rng.choice([0.0, 0.3])), specials=(n % 3 == 0 and n < 400))
+        vi = H.random_values(rng, n, np.int64, float(rng.choice([0.0, 0.6])))
+        cols = [(t, None), vf, vi]
+        specs = [(op, c, [0.5] if (op, c) in (("Sum", 1), ("Count", 2), ("WindowStart", 0)) else None)
+                 for c in (0, 1, 2) for op in WHOLE_ALL]
+        fr = N.Frame.from_numpy(ctx, cols)
+        got = fr.aggregate_whole(0, specs)
+        want = R.aggregate_whole(R.Frame(cols), 0, specs)
+        fr.close()
+        span = float(t[-1] - t[0]) if n else 0.0
+        for sp, (gv, gm), (wv, wm) in zip(specs, got, want):
+            assert gv.dtype == wv.dtype and np.array_equal(gm, wm), (kind, n, sp)
+            if not gm.any():
+                continue
+            a, b = gv[0], wv[0]
+            if sp[0] in ("Sum", "ArithmeticMean", "IntegralStep", "IntegralTrapezoid", "WeightedAverageStep",
+                         "WeightedAverageLinear") and np.isfinite(b):
+                scale = 1e4 * max(n, 1) * (max(span, 1.0) if "Integral" in sp[0] else 1.0)
+                assert abs(a - b) <= 1e-12 * max(abs(b), scale), (kind, n, sp, a, b)
+            else:
+                assert H.same_value(a.item(), b.item()), (kind, n, sp, a, b)

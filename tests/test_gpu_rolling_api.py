@@ -172,3 +172,20 @@ def test_config1_fixture(interval):
             assert np.allclose(gv, wv, rtol=1e-12, atol=0), sp
         else:
             assert np.array_equal(gv.view(np.int64), wv.view(np.int64)), sp
+
+
+@pytest.mark.parametrize("name,rows,aggs,expected,cite", G.WHOLE_CASES, ids=[c[0] for c in G.WHOLE_CASES])
+def test_whole_aggregate_api(name, rows, aggs, expected, cite):  # rolling/aggregation/whole_test.go
+    b = rows_bow(rows)
+    la = []
+    for ctor, col, out in aggs:
+        a = getattr(aggregation, ctor)(col)
+        la.append(a.RenameOutput(out) if out else a)
+    if isinstance(expected, str):
+        with pytest.raises(B.BowError) as ei:
+            aggregation.Aggregate(b, G.TIME, *la)
+        assert str(ei.value) == expected, cite
+        return
+    got = aggregation.Aggregate(b, G.TIME, *la)
+    want = B.NewBowFromColBasedInterfaces(expected["names"], [TYPES[t] for t in expected["types"]], expected["cols"])
+    assert got.Equal(want), f"{cite}\nexpected: {want}\nactual: {got}"
