@@ -644,12 +644,21 @@ def IntegralStep(col: str) -> ColAggregation:
     return ColAggregation(col, False, T_FLOAT64, _integral_step)
 
 
+def go_fdiv(a: float, b: float) -> float:
+    """Go float64 division: x/0 is +-Inf or NaN, never a panic."""
+    if b == 0.0:
+        if a == 0.0 or a != a:
+            return math.nan
+        return math.copysign(math.inf, a) * math.copysign(1.0, b)
+    return a / b
+
+
 def WeightedAverageStep(col: str) -> ColAggregation:      # weightedmean.go:8-20
     def fn(c, w):
         v = _integral_step(c, w)
         if v is None:
             return None
-        return v / float(w.last_value - w.first_value)
+        return go_fdiv(v, float(w.last_value - w.first_value))
     return ColAggregation(col, False, T_FLOAT64, fn)
 
 
@@ -658,7 +667,7 @@ def WeightedAverageLinear(col: str) -> ColAggregation:    # weightedmean.go:22-3
         v = _integral_trapezoid(c, w)
         if v is None:
             return None
-        return v / float(w.last_value - w.first_value)
+        return go_fdiv(v, float(w.last_value - w.first_value))
     return ColAggregation(col, True, T_FLOAT64, fn)
 
 

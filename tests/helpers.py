@@ -87,3 +87,9 @@ def random_values(rng: np.random.Generator, n: int, dtype, null_p: float, specia
     if null_p > 0:
         mask = rng.random(n) >= null_p
     return v, mask
+
+
+def seed_of(*key) -> int:
+    """deterministic seed from a test's parameters (Python's hash() of strings changes from run to run)"""
+    import zlib
+    return zlib.crc32(repr(key).encode())

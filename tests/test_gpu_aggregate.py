@@ -111,7 +111,7 @@ for kind in ("regular", "dense", "sparse", "bursty"):
 
 @pytest.mark.parametrize("kind,n", CASES, ids=[f"{k}-{n}" for k, n in CASES])
 def test_random_vs_oracle(ctx, kind, n):
-    rng = np.random.default_rng(hash((kind, n)) & 0xFFFF)
+    rng = np.random.default_rng(H.seed_of((kind, n)))
     for trial in range(4):
         t = H.random_times(rng, n, kind)
         dtype = np.int64 if trial == 1 else np.float64
@@ -135,7 +135,7 @@ ICASES = [(k, n) for k in ("regular", "dense", "sparse", "bursty") for n in (1, 
 def test_random_integrals_vs_oracle(ctx, kind, n):
     """float64 integrals / weighted averages: |gpu - ref| <= 1e-12 * max(|ref|, integral of |v|)"""
     from bow_b200 import native as N
-    rng = np.random.default_rng(hash((kind, n, "i")) & 0xFFFF)
+    rng = np.random.default_rng(H.seed_of((kind, n, "i")))
     for trial in range(4):
         t = H.random_times(rng, n, kind)
         dtype = np.int64 if trial == 1 else np.float64
@@ -304,7 +304,7 @@ def test_whole_random_vs_oracle(ctx, kind):
     """one window over the whole frame, all aggregations on a float64 and an int64 column (+ Factor), sizes around
     the tile edges; bit-exact except sums / means / integrals (1e-12 relative to the sum of |terms|)"""
     from bow_b200 import native as N
-    rng = np.random.default_rng(hash(("whole", kind)) & 0xFFFF)
+    rng = np.random.default_rng(H.seed_of(("whole", kind)))
     for n in (0, 1, 2, 17, 300, 8191, 8192, 8193, 16385, 40000):
         t = H.random_times(rng, n, kind)
         if n:

@@ -62,7 +62,7 @@ ICASES = [(k, n) for k in ("regular", "dense", "sparse", "bursty") for n in (1, 
 @pytest.mark.parametrize("kind,n", ICASES, ids=[f"{k}-{n}" for k, n in ICASES])
 def test_random_interpolate_vs_oracle(ctx, kind, n):
     from bow_b200 import native as N
-    rng = np.random.default_rng(hash((kind, n, "interp")) & 0xFFFF)
+    rng = np.random.default_rng(H.seed_of((kind, n, "interp")))
     for trial in range(5):
         t = H.random_times(rng, n, kind)
         a = H.random_values(rng, n, np.float64, [0.0, 0.3, 0.1, 0.9, 0.5][trial])

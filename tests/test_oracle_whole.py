@@ -53,7 +53,7 @@ ALL = ["WindowStart", "Count", "Sum", "ArithmeticMean", "Min", "Max", "First", "
 
 @pytest.mark.parametrize("kind", ["regular", "dense", "sparse"])
 def test_whole_refc_matches_literal(kind):
-    rng = np.random.default_rng(hash(kind) & 0xFFFF)
+    rng = np.random.default_rng(H.seed_of(kind))
     for trial in range(25):
         n = int(rng.integers(0, 60))
         t = H.random_times(rng, n, kind)

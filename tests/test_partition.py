@@ -62,7 +62,7 @@ def check_plan(shards, n, W):
 @pytest.mark.parametrize("kind", ["regular", "dense", "sparse", "bursty"])
 @pytest.mark.parametrize("g", [1, 2, 3, 8])
 def test_plan_and_concat_matches_unsharded(kind, g):
-    rng = np.random.default_rng(hash((kind, g)) & 0xFFFF)
+    rng = np.random.default_rng(H.seed_of((kind, g)))
     for n, interval in ((0, 5), (1, 5), (50, 3), (5000, 7), (20000, 2), (20000, 400)):
         t = H.random_times(rng, n, kind)
         if n:
@@ -174,7 +174,7 @@ def oracle_interp_executor(cols, time_col, interval, s0, num_windows, inclusive,
 @pytest.mark.parametrize("kind", ["regular", "sparse", "bursty"])
 @pytest.mark.parametrize("g", [1, 2, 5])
 def test_sharded_interpolate_matches_unsharded(kind, g):
-    rng = np.random.default_rng(hash((kind, g, "i")) & 0xFFFF)
+    rng = np.random.default_rng(H.seed_of((kind, g, "i")))
     for n, interval in ((1, 5), (40, 3), (6000, 7), (20000, 300)):
         t = H.random_times(rng, n, kind)
         t = t - int(t[0]) + 1000
