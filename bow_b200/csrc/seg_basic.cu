@@ -89,6 +89,9 @@ struct BasicPol {
     static __device__ __forceinline__ State combine(const State &L, const State &R) {
         State o;
         o.sum = L.sum + R.sum;
+        o.mn = CUDART_INF;  // fields the instantiated ops do not maintain stay at their identity values
+        o.mx = -CUDART_INF;
+        o.first = o.last = 0;
         if (OPS & OPS_MINMAX) {
             o.mn = (R.mn < L.mn) ? R.mn : L.mn;
             o.mx = (R.mx > L.mx) ? R.mx : L.mx;
@@ -101,6 +104,9 @@ struct BasicPol {
     static __device__ __forceinline__ State shfl_up(const State &s, int d) {
         State o;
         o.sum = __shfl_up_sync(0xffffffffu, s.sum, d);
+        o.mn = CUDART_INF;
+        o.mx = -CUDART_INF;
+        o.first = o.last = 0;
         if (OPS & OPS_MINMAX) {
             o.mn = __shfl_up_sync(0xffffffffu, s.mn, d);
             o.mx = __shfl_up_sync(0xffffffffu, s.mx, d);

@@ -95,6 +95,7 @@ struct IntegralPol {
     }
     static __device__ __forceinline__ State combine(const State &L, const State &R) {
         State o;
+        o.sS = o.sT = 0.0;  // (the sum this instantiation does not maintain)
         const bool l = L.n != 0, r = R.n != 0;
         const double dt = R.fT - L.lT;
         if (STEP) {
@@ -119,6 +120,7 @@ struct IntegralPol {
         o.fV = __shfl_up_sync(0xffffffffu, s.fV, d);
         o.lT = __shfl_up_sync(0xffffffffu, s.lT, d);
         o.lV = __shfl_up_sync(0xffffffffu, s.lV, d);
+        o.sS = o.sT = 0.0;
         if (STEP) o.sS = __shfl_up_sync(0xffffffffu, s.sS, d);
         if (TRAP) o.sT = __shfl_up_sync(0xffffffffu, s.sT, d);
         o.n = __shfl_up_sync(0xffffffffu, s.n, d);

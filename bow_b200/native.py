@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -163,6 +164,11 @@ class Ctx:
         if rc:
             raise BowGpuError(rc, "bowgpu_ctx_create failed (is a B200 visible? bow_b200 has no CPU fallback)")
         self.device = device
+        self._children = weakref.WeakSet()   # frames / rollings created on this ctx: closed before the ctx itself
+
+    def _adopt(self, obj):
+        self._children.add(obj)
+        return obj
 
     def check(self, rc: int):
         if rc:
@@ -189,6 +195,8 @@ class Ctx:
 
     def close(self):
         if self.h:
+            for child in list(self._children):   # a frame outliving its ctx would free into a destroyed pool
+                child.close()
             lib().bowgpu_ctx_destroy(self.h)
             self.h = C.c_void_p()
 
@@ -204,6 +212,7 @@ class Frame:
 
     def __init__(self, ctx: Ctx, handle: C.c_void_p, keep=None):
         self.ctx, self.h, self.keep = ctx, handle, keep
+        ctx._adopt(self)
 
     @classmethod
     def from_numpy(cls, ctx: Ctx, cols: Sequence[NpCol], offset: int = 0) -> "Frame":
@@ -312,6 +321,7 @@ class Rolling:
         """shard = (s0, num_windows): range-partitioned variant (bowgpu_rolling_create_shard)."""
         self.frame, self.ctx = frame, frame.ctx
         self.h = C.c_void_p()
+        self.ctx._adopt(self)
         parr, self._keep = (None, None)
         if prev_row is not None:
             parr, self._keep = cols_from_numpy(prev_row)
