@@ -154,6 +154,72 @@ class Bow:
     def __str__(self) -> str:
         return self.Record.to_pandas().to_string() if self.NumRows() else f"<empty Bow {self.Record.schema.names}>"
 
+    # -- whole-column fills on the GPU (bowfill.go:14-288); Go's (Bow, error) -> returned Bow / raised BowError ----
+    def _gpu_fill(self, run) -> "Bow":
+        from . import native as N
+        from .rolling import _cols_from_bow
+        from .runtime import default_ctx
+        try:
+            arr, keep = _cols_from_bow(self)
+            frame = N.Frame.from_col_descs(default_ctx(), arr, self.NumCols(), N.MEM_HOST, keep)
+            try:
+                out = run(frame)
+                try:
+                    cols = out.download()
+                finally:
+                    out.close()
+            finally:
+                frame.close()
+        except N.BowGpuError as e:
+            raise BowError(str(e).split(": ", 1)[-1])
+        series = [NewSeriesFromNumpy(self.ColumnName(j), v, m) for j, (v, m) in enumerate(cols)]
+        rec = pa.RecordBatch.from_arrays([s_.Array for s_ in series], names=[s_.Name for s_ in series])
+        if self.Record.schema.metadata:   # NewBowWithMetadata(b.Metadata(), ...), bowfill.go:101,151,252
+            rec = rec.replace_schema_metadata(self.Record.schema.metadata)
+        return Bow(rec)
+
+    def _check_fill_types(self, colIndices, numeric_only: bool):
+        n = self.NumCols()
+        for c in colIndices:  # selectCols, bowfill.go:266-288
+            if c < 0 or c > n - 1:
+                raise BowError(f"selectCols: colIndex '{c}' out of range")
+        for c in (colIndices or range(n)):
+            t = self.ColumnType(c)
+            if t not in (Type.Int64, Type.Float64):
+                if numeric_only:
+                    raise BowError(f"column '{self.ColumnName(c)}' is of unsupported type '{t}'")
+                raise BowError(f"column '{self.ColumnName(c)}': only Int64 / Float64 columns run on the GPU backend")
+        for c in range(n):
+            if self.ColumnType(c) not in (Type.Int64, Type.Float64):
+                raise BowError(f"column '{self.ColumnName(c)}': only Int64 / Float64 columns run on the GPU backend")
+
+    def FillPrevious(self, *colIndices: int) -> "Bow":  # bowfill.go:160-164
+        self._check_fill_types(colIndices, False)
+        return self._gpu_fill(lambda f: f.fill("Previous", *colIndices))
+
+    def FillNext(self, *colIndices: int) -> "Bow":  # bowfill.go:154-158
+        self._check_fill_types(colIndices, False)
+        return self._gpu_fill(lambda f: f.fill("Next", *colIndices))
+
+    def FillMean(self, *colIndices: int) -> "Bow":  # bowfill.go:104-152
+        self._check_fill_types(colIndices, True)
+        return self._gpu_fill(lambda f: f.fill("Mean", *colIndices))
+
+    def FillLinear(self, refColIndex: int, toFillColIndex: int) -> "Bow":  # bowfill.go:14-102
+        n = self.NumCols()
+        if refColIndex < 0 or refColIndex > n - 1:
+            raise BowError("refColIndex is out of range")
+        if toFillColIndex < 0 or toFillColIndex > n - 1:
+            raise BowError("toFillColIndex is out of range")
+        if refColIndex == toFillColIndex:
+            raise BowError("refColIndex and toFillColIndex are equal")
+        if self.ColumnType(refColIndex) not in (Type.Int64, Type.Float64):
+            raise BowError(f"refColIndex '{refColIndex}' is of type '{self.ColumnType(refColIndex)}'")
+        if self.ColumnType(toFillColIndex) not in (Type.Int64, Type.Float64):
+            raise BowError(f"toFillColIndex '{toFillColIndex}' is of unsupported type '{self.ColumnType(toFillColIndex)}'")
+        self._check_fill_types((), False)
+        return self._gpu_fill(lambda f: f.fill_linear(refColIndex, toFillColIndex))
+
 
 def NewBow(*series: Series) -> Bow:
     """bow.go:109-116: fresh schema, no metadata, every field nullable (bowrecord.go:36-40)"""

@@ -683,6 +683,155 @@ extern "C" int32_t bowgpu_frame_generate(bowgpu_ctx *ctx, const bowgpu_gen_spec 
     return BOWGPU_OK;
 }
 
+
+// ================================================================================================
+// whole-column fills (bowfill.go)
+// ================================================================================================
+namespace {
+
+// copies column `src` of n rows into a freshly allocated column of the new frame
+int32_t clone_col(bowgpu_ctx *ctx, DevCol &dst, const DevCol &src, int64_t n) {
+    int32_t rc = alloc_col(ctx, dst, n, src.dtype, src.validity != nullptr);
+    if (rc) return rc;
+    dst.null_count = src.null_count;
+    if (n > 0) {
+        CK(cudaMemcpyAsync(dst.values, src.values, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (src.validity)
+            CK(cudaMemcpyAsync(dst.validity, src.validity, (size_t)bitmap_bytes_padded(n), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return BOWGPU_OK;
+}
+
+// fills column c of `f` into `dst` (allocated here); ref_col < 0 unless method == LINEAR
+int32_t fill_col(bowgpu_ctx *ctx, const bowgpu_frame *f, int c, int method, int ref_col, DevCol &dst) {
+    const DevCol &src = f->cols[c];
+    const int64_t n = f->n;
+    int32_t rc = alloc_col(ctx, dst, n, src.dtype, true);
+    if (rc) return rc;
+    rc = arena_reserve(ctx, fill_scratch_bytes(n) + 512);
+    if (rc) return rc;
+    arena_reset(ctx);
+    int64_t *scratch = (int64_t *)arena_take(ctx, fill_scratch_bytes(n));
+    FillLaunch L;
+    memset(&L, 0, sizeof L);
+    L.values = src.values;
+    L.validity = src.validity;
+    L.out_values = dst.values;
+    L.out_validity = dst.validity;
+    L.n = n;
+    L.is_int = src.dtype == BOWGPU_INT64;
+    if (ref_col >= 0) {
+        L.ref_values = f->cols[ref_col].values;
+        L.ref_validity = f->cols[ref_col].validity;
+        L.ref_is_int = f->cols[ref_col].dtype == BOWGPU_INT64;
+    }
+    CK(launch_fill(method, L, scratch, ctx->stream));
+    count_launch(ctx, 3, false);
+    rc = count_nulls(ctx, dst, n);  // synchronizes: the arena scratch is free again afterwards
+    if (rc) return rc;
+    if (dst.null_count == 0) {
+        pool_free(ctx, dst.validity);
+        dst.validity = nullptr;
+        dst.own_validity = false;
+    }
+    return BOWGPU_OK;
+}
+
+}  // namespace
+
+extern "C" int32_t bowgpu_frame_fill(bowgpu_frame *frame, int32_t method, const int32_t *cols, int32_t ncols,
+                                     bowgpu_frame **out) {
+    if (!frame || !out || ncols < 0 || (ncols > 0 && !cols)) return BOWGPU_EINVAL;
+    *out = nullptr;
+    bowgpu_ctx *ctx = frame->ctx;
+    Guard gd(ctx);
+    if (method != BOWGPU_FILL_PREVIOUS && method != BOWGPU_FILL_NEXT && method != BOWGPU_FILL_MEAN)
+        return fail(ctx, BOWGPU_EINVAL, "bow.Fill: method '%d' is not supported", method);
+    const int nc = (int)frame->cols.size();
+    std::vector<char> sel(nc, ncols == 0 ? 1 : 0);  // selectCols, bowfill.go:266-288
+    for (int i = 0; i < ncols; ++i) {
+        if (cols[i] < 0 || cols[i] > nc - 1) return fail(ctx, BOWGPU_EINVAL, "selectCols: colIndex '%d' out of range", cols[i]);
+        sel[cols[i]] = 1;
+    }
+    bowgpu_frame *of = new (std::nothrow) bowgpu_frame();
+    if (!of) return BOWGPU_ENOMEM;
+    of->ctx = ctx;
+    of->n = frame->n;
+    of->cols.resize(nc);
+    int32_t rc = BOWGPU_OK;
+    timing_begin(ctx);
+    for (int c = 0; c < nc && rc == BOWGPU_OK; ++c) {
+        const DevCol &src = frame->cols[c];
+        if (!sel[c] || !src.validity || src.null_count == 0 || frame->n == 0)
+            rc = clone_col(ctx, of->cols[c], src, frame->n);  // NewSeriesFromCol, bowfill.go:129-132,176-179
+        else
+            rc = fill_col(ctx, frame, c, method, -1, of->cols[c]);
+    }
+    timing_end(ctx);
+    if (rc == BOWGPU_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+        rc = fail(ctx, BOWGPU_ECUDA, "fill: %s", cudaGetErrorString(cudaGetLastError()));
+    if (rc != BOWGPU_OK) {
+        cudaStreamSynchronize(ctx->stream);
+        for (auto &c : of->cols) free_col(ctx, c);
+        delete of;
+        return rc;
+    }
+    *out = of;
+    return BOWGPU_OK;
+}
+
+extern "C" int32_t bowgpu_frame_fill_linear(bowgpu_frame *frame, int32_t ref_col, int32_t tofill_col, bowgpu_frame **out) {
+    if (!frame || !out) return BOWGPU_EINVAL;
+    *out = nullptr;
+    bowgpu_ctx *ctx = frame->ctx;
+    Guard gd(ctx);
+    const int nc = (int)frame->cols.size();
+    if (ref_col < 0 || ref_col > nc - 1) return fail(ctx, BOWGPU_EINVAL, "refColIndex is out of range");  // bowfill.go:18-28
+    if (tofill_col < 0 || tofill_col > nc - 1) return fail(ctx, BOWGPU_EINVAL, "toFillColIndex is out of range");
+    if (ref_col == tofill_col) return fail(ctx, BOWGPU_EINVAL, "refColIndex and toFillColIndex are equal");
+    const DevCol &rcol = frame->cols[ref_col];
+    const int64_t n = frame->n;
+    const bool ref_empty = n == 0 || (rcol.validity && rcol.null_count == n);  // IsColEmpty, bowfill.go:37-39
+    bool do_fill = !ref_empty && frame->cols[tofill_col].validity && frame->cols[tofill_col].null_count != 0;
+    if (!ref_empty) {  // IsColSorted, bowfill.go:41-44
+        int32_t rc = arena_reserve(ctx, fill_scratch_bytes(n) + 1024);
+        if (rc) return rc;
+        arena_reset(ctx);
+        int64_t *scratch = (int64_t *)arena_take(ctx, fill_scratch_bytes(n));
+        int32_t *d_flags = (int32_t *)arena_take(ctx, 16);
+        CK(cudaMemsetAsync(d_flags, 0, 16, ctx->stream));
+        CK(launch_sorted_flags(rcol.values, rcol.validity, rcol.dtype == BOWGPU_INT64, n, scratch, d_flags, ctx->stream));
+        int32_t h = 0;
+        CK(cudaMemcpyAsync(&h, d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (h == 3) return fail(ctx, BOWGPU_EUNSORTED, "refColIndex '%d' is empty or not sorted", ref_col);
+    }
+    bowgpu_frame *of = new (std::nothrow) bowgpu_frame();
+    if (!of) return BOWGPU_ENOMEM;
+    of->ctx = ctx;
+    of->n = n;
+    of->cols.resize(nc);
+    int32_t rc = BOWGPU_OK;
+    timing_begin(ctx);
+    for (int c = 0; c < nc && rc == BOWGPU_OK; ++c) {
+        if (c == tofill_col && do_fill)
+            rc = fill_col(ctx, frame, c, BOWGPU_FILL_LINEAR, ref_col, of->cols[c]);
+        else
+            rc = clone_col(ctx, of->cols[c], frame->cols[c], n);
+    }
+    timing_end(ctx);
+    if (rc == BOWGPU_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+        rc = fail(ctx, BOWGPU_ECUDA, "fill: %s", cudaGetErrorString(cudaGetLastError()));
+    if (rc != BOWGPU_OK) {
+        cudaStreamSynchronize(ctx->stream);
+        for (auto &c : of->cols) free_col(ctx, c);
+        delete of;
+        return rc;
+    }
+    *out = of;
+    return BOWGPU_OK;
+}
+
 // ================================================================================================
 // rolling
 // ================================================================================================

@@ -189,6 +189,23 @@ int launch_bitmap_popcount(const uint8_t *bm, int64_t nbits, unsigned long long 
 // lower bound of `x` in sorted time[0..n) -> *out (device)
 int launch_lower_bound(const int64_t *time, int64_t n, int64_t x, int64_t *out, cudaStream_t stream);
 
+// ---- whole-column fills (fill.cu): bowfill.go ----------------------------------------------------------------------
+struct FillLaunch {
+    const uint64_t *values;      // column to fill
+    const uint8_t *validity;     // its bitmap (bit offset 0), never null
+    const uint64_t *ref_values;  // FillLinear: reference column values / validity (null = all valid) / dtype
+    const uint8_t *ref_validity;
+    uint64_t *out_values;        // n rows
+    uint8_t *out_validity;       // padded device bitmap (written whole words)
+    int64_t n;
+    int32_t is_int, ref_is_int;
+};
+size_t fill_scratch_bytes(int64_t n);
+int launch_fill(int method, const FillLaunch &L, int64_t *scratch, cudaStream_t stream);
+// IsColSorted over the valid rows (bowassertion.go:15-81): *flags |= 1 if some valid row < previous valid, 2 if >
+int launch_sorted_flags(const uint64_t *values, const uint8_t *validity, int is_int, int64_t n, int64_t *scratch,
+                        int32_t *flags, cudaStream_t stream);
+
 // ---- synthetic generators (generate.cu) ----------------------------------------------------------
 int launch_gen_regular(int64_t *time, int64_t n, int64_t row0, int64_t t0, int64_t step, cudaStream_t stream);
 // BURSTY: per-window row counts (to be scanned in place with launch_exclusive_scan) and the time column

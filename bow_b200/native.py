@@ -22,6 +22,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 AGG = dict(WindowStart=0, Count=1, Sum=2, ArithmeticMean=3, Min=4, Max=5, First=6, Last=7,
            IntegralStep=8, IntegralTrapezoid=9, WeightedAverageStep=10, WeightedAverageLinear=11)
 INTERP = dict(WindowStart=0, Linear=1, StepPrevious=2, None_=3)
+FILL = dict(Previous=0, Next=1, Mean=2, Linear=3)
 STATUS = {0: "OK", 1: "EINVAL", 2: "ETYPE", 3: "EFIRSTNULL", 4: "EPREVROW", 5: "ENOINTERVALCOL", 6: "ECAPACITY",
           7: "EUNSORTED", 8: "ENULLTIME", 9: "ECUDA", 10: "ENOMEM", 11: "EUNSUPPORTED"}
 
@@ -35,7 +36,7 @@ SYMBOLS = [
     "bowgpu_rolling_create", "bowgpu_rolling_create_shard", "bowgpu_rolling_destroy", "bowgpu_rolling_num_windows",
     "bowgpu_rolling_first_window_start", "bowgpu_rolling_inclusive", "bowgpu_rolling_early_rows",
     "bowgpu_rolling_bounds", "bowgpu_rolling_aggregate", "bowgpu_agg_return_type", "bowgpu_agg_needs_inclusive",
-    "bowgpu_rolling_interpolate", "bowgpu_frame_aggregate_whole",
+    "bowgpu_rolling_interpolate", "bowgpu_frame_aggregate_whole", "bowgpu_frame_fill", "bowgpu_frame_fill_linear",
 ]
 
 
@@ -104,6 +105,8 @@ def lib():
         L.bowgpu_rolling_bounds.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.bowgpu_rolling_aggregate.argtypes = [C.c_void_p, C.POINTER(AggSpec), C.c_int32, C.POINTER(OutCol),
                                                C.c_int32]
+        L.bowgpu_frame_fill.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p)]
+        L.bowgpu_frame_fill_linear.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
         L.bowgpu_frame_aggregate_whole.argtypes = [C.c_void_p, C.c_int32, C.POINTER(AggSpec), C.c_int32, C.POINTER(OutCol),
                                                    C.c_int32]
         L.bowgpu_rolling_interpolate.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int32,
@@ -268,6 +271,20 @@ class Frame:
             vals = v[:n] if outs[j].dtype == INT64 else v[:n].view(np.float64)
             res.append((vals, unpack_bits(b, n)))
         return res
+
+    def fill(self, method, *cols: int) -> "Frame":
+        """Bow.FillPrevious / FillNext / FillMean (bowfill.go); no column index = every column"""
+        m = FILL[method] if isinstance(method, str) else int(method)
+        arr = (C.c_int32 * max(1, len(cols)))(*cols)
+        h = C.c_void_p()
+        self.ctx.check(lib().bowgpu_frame_fill(self.h, m, arr, len(cols), C.byref(h)))
+        return Frame(self.ctx, h)
+
+    def fill_linear(self, ref_col: int, tofill_col: int) -> "Frame":
+        """Bow.FillLinear (bowfill.go:14-102)"""
+        h = C.c_void_p()
+        self.ctx.check(lib().bowgpu_frame_fill_linear(self.h, ref_col, tofill_col, C.byref(h)))
+        return Frame(self.ctx, h)
 
     def aggregate_whole(self, time_col: int, specs: Sequence[tuple]):
         """aggregation.Aggregate over the whole frame (rolling/aggregation/whole.go) -> list of (values, valid mask)

@@ -225,6 +225,22 @@ int32_t bowgpu_agg_needs_inclusive(int32_t op); /* integral.go:9, weightedmean.g
 int32_t bowgpu_frame_aggregate_whole(bowgpu_frame *frame, int32_t time_col, const bowgpu_agg_spec *specs,
                                      int32_t nspecs, bowgpu_out_col *outs, int32_t mem);
 
+/* ---- whole-column fills (bowfill.go) ------------------------------------------------------------------------------ */
+enum {
+    BOWGPU_FILL_PREVIOUS = 0, /* Bow.FillPrevious  bowfill.go:160-164 (LOCF) */
+    BOWGPU_FILL_NEXT = 1,     /* Bow.FillNext      bowfill.go:154-158 (NOCB) */
+    BOWGPU_FILL_MEAN = 2,     /* Bow.FillMean      bowfill.go:104-152 (Int64 results rounded half away from zero) */
+    BOWGPU_FILL_LINEAR = 3    /* Bow.FillLinear    bowfill.go:14-102 */
+};
+/* FillPrevious / FillNext / FillMean of the columns cols[0..ncols) (ncols == 0: every column, selectCols
+ * bowfill.go:266-288).  Every null row looks at the nearest valid rows of the ORIGINAL column.  The result is a new
+ * device-resident frame (columns that are not filled are copied). */
+int32_t bowgpu_frame_fill(bowgpu_frame *frame, int32_t method, const int32_t *cols, int32_t ncols, bowgpu_frame **out);
+/* Bow.FillLinear(refColIndex, toFillColIndex): the reference column must be sorted (ascending or descending, nulls
+ * skipped: IsColSorted, bowassertion.go:15-81) else BOWGPU_EUNSORTED; an all-null reference column or a column
+ * without nulls returns a copy. */
+int32_t bowgpu_frame_fill_linear(bowgpu_frame *frame, int32_t ref_col, int32_t tofill_col, bowgpu_frame **out);
+
 /* Rolling.Interpolate (interpolation.go:30-161).  ops[j] is the interpolation of column j (the
  * reference matches columns by position, bowappend.go:28-47, so nops must equal the number of
  * columns).  The result is a new device-resident frame with n_out rows. */

@@ -778,3 +778,137 @@ def whole_aggregate(b: Frame, interval_col_name: str, *aggrs: ColAggregation) ->
         types.append(typ)
         cols.append(buf)
     return Frame(names, types, cols)
+
+
+# ----------------------------------------------------------------------------
+# bowfill.go:14-288, bowassertion.go:15-87 — whole-column fills (Int64 / Float64 columns)
+# ----------------------------------------------------------------------------
+def is_col_empty(b: Frame, c: int) -> bool:               # bowassertion.go:84-87
+    return all(b.get_value(c, r) is None for r in range(b.num_rows()))
+
+
+def is_col_sorted(b: Frame, c: int) -> bool:              # bowassertion.go:15-81 (nil values are skipped)
+    if is_col_empty(b, c):
+        return False
+    vals = [b.get_value(c, r) for r in range(b.num_rows()) if b.get_value(c, r) is not None]
+    order, curr = 0, vals[0]
+    for nxt in vals[1:]:
+        if order == 0:
+            if curr < nxt:
+                order = 1
+            elif curr > nxt:
+                order = -1
+        if (order == 1 and nxt < curr) or (order == -1 and nxt > curr):
+            return False
+        curr = nxt
+    return True
+
+
+def go_round(x: float) -> float:
+    """math.Round: half away from zero; NaN and +-Inf pass through"""
+    if x != x or x in (math.inf, -math.inf):
+        return x
+    a = abs(x)
+    if a >= 2.0 ** 52:
+        return x
+    t = float(math.floor(a))
+    if a - t >= 0.5:          # exact: both are doubles below 2^52
+        t += 1.0
+    return math.copysign(t, x)
+
+
+def _select_cols(b: Frame, col_indices) -> List[bool]:    # bowfill.go:266-288
+    sel = [False] * b.num_cols()
+    if len(col_indices) == 0:
+        return [True] * b.num_cols()
+    for c in col_indices:
+        if c < 0 or c > b.num_cols() - 1:
+            raise ValueError(f"selectCols: colIndex '{c}' out of range")
+        sel[c] = True
+    return sel
+
+
+def _fill(method: str, b: Frame, *col_indices: int) -> Frame:   # bowfill.go:166-253
+    sel = _select_cols(b, col_indices)
+    cols = []
+    for c in range(b.num_cols()):
+        col = [b.get_value(c, r) for r in range(b.num_rows())]
+        if sel[c] and any(v is None for v in col):
+            for r in range(b.num_rows()):
+                if col[r] is not None:
+                    continue
+                rr = r - 1 if method == "Previous" else r + 1       # getFillRowIndex, bowfill.go:255-264
+                while 0 <= rr < b.num_rows() and b.get_value(c, rr) is None:
+                    rr += -1 if method == "Previous" else 1
+                if 0 <= rr < b.num_rows():
+                    col[r] = b.get_value(c, rr)
+        cols.append(col)
+    return Frame(list(b.names), list(b.types), cols)
+
+
+def fill_previous(b: Frame, *col_indices: int) -> Frame:  # bowfill.go:160-164
+    return _fill("Previous", b, *col_indices)
+
+
+def fill_next(b: Frame, *col_indices: int) -> Frame:      # bowfill.go:154-158
+    return _fill("Next", b, *col_indices)
+
+
+def fill_mean(b: Frame, *col_indices: int) -> Frame:      # bowfill.go:104-152
+    sel = _select_cols(b, col_indices)
+    for c in range(b.num_cols()):
+        if sel[c] and b.types[c] not in (INT64, FLOAT64):
+            raise TypeError(f"column '{b.names[c]}' is of unsupported type '{b.types[c]}'")
+    cols = []
+    for c in range(b.num_cols()):
+        col = [b.get_value(c, r) for r in range(b.num_rows())]
+        if sel[c] and any(v is None for v in col):
+            for r in range(b.num_rows()):
+                if col[r] is not None:
+                    continue
+                prev_val, prev_row = b.get_prev_float64(c, r - 1)
+                next_val, next_row = b.get_next_float64(c, r + 1)
+                if prev_row > -1 and next_row > -1:
+                    m = (prev_val + next_val) / 2
+                    col[r] = f64_to_i64(go_round(m)) if b.types[c] == INT64 else m
+        cols.append(col)
+    return Frame(list(b.names), list(b.types), cols)
+
+
+def fill_linear(b: Frame, ref: int, to_fill: int) -> Frame:     # bowfill.go:14-102
+    if ref < 0 or ref > b.num_cols() - 1:
+        raise ValueError("refColIndex is out of range")
+    if to_fill < 0 or to_fill > b.num_cols() - 1:
+        raise ValueError("toFillColIndex is out of range")
+    if ref == to_fill:
+        raise ValueError("refColIndex and toFillColIndex are equal")
+    if b.types[ref] not in (INT64, FLOAT64):
+        raise TypeError(f"refColIndex '{ref}' is of type '{b.types[ref]}'")
+    if is_col_empty(b, ref):
+        return b
+    if not is_col_sorted(b, ref):
+        raise ValueError(f"refColIndex '{ref}' is empty or not sorted")
+    if b.types[to_fill] not in (INT64, FLOAT64):
+        raise TypeError(f"toFillColIndex '{to_fill}' is of unsupported type '{b.types[to_fill]}'")
+    col = [b.get_value(to_fill, r) for r in range(b.num_rows())]
+    if all(v is not None for v in col):
+        return b
+    is_int = b.types[to_fill] == INT64
+    for r in range(b.num_rows()):
+        if col[r] is not None:
+            continue
+        prev_to_fill, row_prev = b.get_prev_float64(to_fill, r - 1)
+        next_to_fill, row_next = b.get_next_float64(to_fill, r + 1)
+        row_ref, valid1 = b.get_float64(ref, r)
+        prev_ref, valid2 = b.get_float64(ref, row_prev)
+        next_ref, valid3 = b.get_float64(ref, row_next)
+        if not (valid1 and valid2 and valid3):
+            continue
+        # (bowfill.go:76-83 stores prevToFill when nextRef == prevRef, then falls through and overwrites it)
+        tmp = row_ref - prev_ref
+        tmp = go_fdiv(tmp, next_ref - prev_ref)
+        tmp *= next_to_fill - prev_to_fill
+        tmp += prev_to_fill
+        col[r] = f64_to_i64(go_round(tmp)) if is_int else tmp
+    cols = [[b.get_value(c, r) for r in range(b.num_rows())] if c != to_fill else col for c in range(b.num_cols())]
+    return Frame(list(b.names), list(b.types), cols)

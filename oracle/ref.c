@@ -654,4 +654,67 @@ int64_t bowref_interpolate(const bowref_rolling *r, const int32_t *ops, int32_t 
     return n_out;
 }
 
+/* ---- whole-column fills, bowfill.go:14-288 (Int64 / Float64 columns) --------------------------------------
+ * method: 0 FillPrevious, 1 FillNext, 2 FillMean, 3 FillLinear (ref_col = sorted reference column).
+ * out_values: n 8-byte slots, out_validity: ceil(n/8) bytes (bit offset 0).  Returns 0, or BOWREF_EINVAL. */
+static double go_round(double x) { /* math.Round: half away from zero */
+    if (x != x || x - x != 0.0) return x;
+    double a = x < 0 ? -x : x;
+    if (a >= 4503599627370496.0) return x;
+    double f = (double)(int64_t)a; /* floor for 0 <= a < 2^52, exact */
+    if (a - f >= 0.5) f += 1.0;    /* a - f is exact */
+    return x < 0 ? -f : (x == 0 ? x : f);
+}
+int bowref_fill(const bowref_col *cols, int32_t ncols, int32_t method, int32_t col, int32_t ref_col, void *out_values,
+                uint8_t *out_validity) {
+    if (col < 0 || col >= ncols || method < 0 || method > 3) return BOWREF_EINVAL;
+    if (method == 3 && (ref_col < 0 || ref_col >= ncols || ref_col == col)) return BOWREF_EINVAL;
+    const bowref_col *c = &cols[col];
+    const int64_t n = c->length;
+    const int is_int = c->dtype == BOWREF_INT64;
+    int64_t *ov = (int64_t *)out_values;
+    memset(out_validity, 0, (size_t)((n + 7) / 8));
+    for (int64_t r = 0; r < n; r++) {
+        if (col_valid(c, r)) {
+            ov[r] = col_raw(c, r);
+            out_validity[r >> 3] |= (uint8_t)(1u << (r & 7));
+            continue;
+        }
+        ov[r] = 0;
+        int64_t p = r - 1, q = r + 1;
+        while (p >= 0 && !col_valid(c, p)) p--;
+        while (q < n && !col_valid(c, q)) q++;
+        if (q >= n) q = -1;
+        int ok = 0;
+        int64_t raw = 0;
+        if (method == 0) { /* bowfill.go:160-164, 255-264 */
+            if (p >= 0) { raw = col_raw(c, p); ok = 1; }
+        } else if (method == 1) { /* bowfill.go:154-158 */
+            if (q >= 0) { raw = col_raw(c, q); ok = 1; }
+        } else if (method == 2) { /* bowfill.go:136-146 */
+            if (p >= 0 && q >= 0) {
+                double m = (col_f64(c, p) + col_f64(c, q)) / 2;
+                raw = is_int ? f64_to_i64(go_round(m)) : f64_as_raw(m);
+                ok = 1;
+            }
+        } else { /* bowfill.go:66-95 */
+            const bowref_col *rc = &cols[ref_col];
+            if (p >= 0 && q >= 0 && col_valid(rc, r) && col_valid(rc, p) && col_valid(rc, q)) {
+                double prev_to_fill = col_f64(c, p), next_to_fill = col_f64(c, q);
+                double tmp = col_f64(rc, r) - col_f64(rc, p);
+                tmp /= col_f64(rc, q) - col_f64(rc, p);
+                tmp *= next_to_fill - prev_to_fill;
+                tmp += prev_to_fill;
+                raw = is_int ? f64_to_i64(go_round(tmp)) : f64_as_raw(tmp);
+                ok = 1;
+            }
+        }
+        if (ok) {
+            ov[r] = raw;
+            out_validity[r >> 3] |= (uint8_t)(1u << (r & 7));
+        }
+    }
+    return BOWREF_OK;
+}
+
 int32_t bowref_sizeof_rolling(void) { return (int32_t)sizeof(bowref_rolling); }

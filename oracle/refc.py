@@ -207,3 +207,20 @@ def aggregate_whole(frame: Frame, time_col: int, specs: Sequence[tuple]):
         vals = v[:n_out] if outs[j].dtype == INT64 else v[:n_out].view(np.float64)
         res.append((vals, unpack_bits(b, n_out)))
     return res
+
+
+FILL = dict(Previous=0, Next=1, Mean=2, Linear=3)
+
+
+def fill(frame: Frame, method, col: int, ref_col: int = -1):
+    """FillPrevious / FillNext / FillMean / FillLinear of ONE column (bowfill.go) -> (values, valid mask)"""
+    n = frame.n
+    v = np.zeros(max(n, 1), dtype=np.int64)
+    b = np.zeros((n + 7) // 8 + 1, dtype=np.uint8)
+    m = FILL[method] if isinstance(method, str) else method
+    rc = lib().bowref_fill(frame.arr, frame.ncols, m, col, ref_col, v.ctypes.data_as(C.c_void_p),
+                           b.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise RefError(rc)
+    vals = v[:n] if frame.dtypes[col] == INT64 else v[:n].view(np.float64)
+    return vals, unpack_bits(b, n)

@@ -53,7 +53,7 @@ def report(name, n, secs, alg_bytes, extra=None):
 
 def main():
     ctx = N.Ctx(0)
-    which = sys.argv[1:] or ["1", "1b", "2", "3", "4"]
+    which = sys.argv[1:] or ["1", "1b", "2", "3", "4", "fill"]
     if "1" in which or "1b" in which:
         for tag, n in (("1", int(1e8 * SCALE)), ("1b", int(1e9 * SCALE))):
             if tag not in which:
@@ -130,6 +130,23 @@ def main():
         report("configs[4] one GPU share: 16 columns x all aggregations (177 outputs)", n, dt,
                136 * n + 8 * n // 8 + len(specs) * (8 * W + W // 8))
         r.close(); fr.close(); del keep
+    if "fill" in which:   # next row of SURVEY 8(f): whole-column fills (bowfill.go)
+        n = int(1e9 * SCALE)
+        fr = N.Frame.generate(ctx, n, ncols=2, seed=5, null_mask=0x3, null_mod=10)
+        for method in ("Previous", "Mean"):
+            def run():
+                out = fr.fill(method, 1)
+                out.close()
+            dt = timed(ctx, run, reps=3, warm=1)
+            report(f"Fill{method} of one float64 column with 10 % nulls (2 untouched columns are copied)", n, dt,
+                   16 * n + 2 * n // 8 + 2 * 16 * n)
+
+        def run_lin():
+            out = fr.fill_linear(0, 1)
+            out.close()
+        dt = timed(ctx, run_lin, reps=3, warm=1)
+        report("FillLinear(time, value) incl. IsColSorted of the reference column", n, dt, 8 * n + 16 * n + 2 * n // 8 + 2 * 16 * n)
+        fr.close()
 
 
 if __name__ == "__main__":

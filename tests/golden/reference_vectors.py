@@ -268,3 +268,47 @@ WHOLE_CASES = [
      [("WindowStart", "time", None), ("WeightedAverageLinear", "value", None)],
      {"names": ["time", "value"], "types": ["int64", "float64"], "cols": [[10], [N]]}, "whole_test.go:194-217"),
 ]
+
+
+# ---- whole-column fills: bowfill_test.go:11-380 (newFreshBow with Int64 and with Float64 columns a..e) -----------
+FILL_ROWS = [
+    [20, 6, 30, 400, -10],
+    [13, N, N, N, N],
+    [10, 4, 10, 10, -5],
+    [0, N, 3, 4, 0],
+    [N, N, N, N, N],
+    [-2, 1, N, N, -8],
+]
+# entries: (name, method, args, expected rows for Int64 columns, expected rows for Float64 columns, citation)
+FILL_CASES = [
+    ("Mean one column", "FillMean", (1,),
+     [[20, 6, 30, 400, -10], [13, 5, N, N, N], [10, 4, 10, 10, -5], [0, 3, 3, 4, 0], [N, 3, N, N, N], [-2, 1, N, N, -8]],
+     [[20, 6, 30, 400, -10], [13, 5, N, N, N], [10, 4, 10, 10, -5], [0, 2.5, 3, 4, 0], [N, 2.5, N, N, N],
+      [-2, 1, N, N, -8]], "bowfill_test.go:30-49,206-225"),
+    ("Mean all columns", "FillMean", (),
+     [[20, 6, 30, 400, -10], [13, 5, 20, 205, -8], [10, 4, 10, 10, -5], [0, 3, 3, 4, 0], [-1, 3, N, N, -4],
+      [-2, 1, N, N, -8]],
+     [[20, 6, 30, 400, -10], [13, 5, 20, 205, -7.5], [10, 4, 10, 10, -5], [0, 2.5, 3, 4, 0], [-1, 2.5, N, N, -4],
+      [-2, 1, N, N, -8]], "bowfill_test.go:51-70,227-246"),
+    ("Next one column", "FillNext", (1,),
+     [[20, 6, 30, 400, -10], [13, 4, N, N, N], [10, 4, 10, 10, -5], [0, 1, 3, 4, 0], [N, 1, N, N, N], [-2, 1, N, N, -8]],
+     None, "bowfill_test.go:72-91,248-267"),
+    ("Next all columns", "FillNext", (),
+     [[20, 6, 30, 400, -10], [13, 4, 10, 10, -5], [10, 4, 10, 10, -5], [0, 1, 3, 4, 0], [-2, 1, N, N, -8],
+      [-2, 1, N, N, -8]], None, "bowfill_test.go:93-112,269-288"),
+    ("Previous one column", "FillPrevious", (1,),
+     [[20, 6, 30, 400, -10], [13, 6, N, N, N], [10, 4, 10, 10, -5], [0, 4, 3, 4, 0], [N, 4, N, N, N], [-2, 1, N, N, -8]],
+     None, "bowfill_test.go:114-133,290-309"),
+    ("Previous all columns", "FillPrevious", (),
+     [[20, 6, 30, 400, -10], [13, 6, 30, 400, -10], [10, 4, 10, 10, -5], [0, 4, 3, 4, 0], [0, 4, 3, 4, 0],
+      [-2, 1, 3, 4, -8]], None, "bowfill_test.go:135-154,311-330"),
+    ("Linear refCol a toFillCol b (desc)", "FillLinear", (0, 1),
+     [[20, 6, 30, 400, -10], [13, 5, N, N, N], [10, 4, 10, 10, -5], [0, 2, 3, 4, 0], [N, N, N, N, N], [-2, 1, N, N, -8]],
+     [[20, 6, 30, 400, -10], [13, 4.6, N, N, N], [10, 4, 10, 10, -5], [0, 1.5, 3, 4, 0], [N, N, N, N, N],
+      [-2, 1, N, N, -8]], "bowfill_test.go:156-174,332-351"),
+    ("Linear refCol a toFillCol e (asc)", "FillLinear", (0, 4),
+     [[20, 6, 30, 400, -10], [13, N, N, N, -7], [10, 4, 10, 10, -5], [0, N, 3, 4, 0], [N, N, N, N, N], [-2, 1, N, N, -8]],
+     [[20, 6, 30, 400, -10], [13, N, N, N, -6.5], [10, 4, 10, 10, -5], [0, N, 3, 4, 0], [N, N, N, N, N],
+      [-2, 1, N, N, -8]], "bowfill_test.go:176-195,353-372"),
+    ("Linear refCol not sorted", "FillLinear", (4, 1), "error", "error", "bowfill_test.go:197-202,374-379"),
+]
