@@ -188,11 +188,13 @@ int launch_bounds(const BoundsLaunch &L, int sm_count, cudaStream_t stream, cuda
     const int64_t ntiles = (L.g.n + BndG::T - 1) / BndG::T;
     if (ntiles == 0) return 0;
     const int smem = BND_HEADER_BYTES + BND_STAGES * BND_STAGE_BYTES;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};  // function attributes are per device (one ctx per GPU may live in one process)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
         cudaError_t e = cudaFuncSetAttribute(bounds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        configured[dev & 63] = true;
     }
     int64_t grid = (int64_t)sm_count * 3;
     if (grid > ntiles) grid = ntiles;

@@ -556,11 +556,13 @@ int seg_launch(const SegArgs<Pol> &A, int sm_count, cudaStream_t stream, cudaEve
     static int nstages = 0, ctas = 0;
     if (!nstages) seg_knobs(nstages, ctas, 2, MIN_CTAS);
     const int smem = seg_smem_bytes(nstages);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};  // function attributes are per device (one ctx per GPU may live in one process)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        configured[dev & 63] = true;
     }
     CUtensorMap tm_time, tm_val;
     int rc = seg_make_tmap(&tm_time, A.time, A.g.n);
