@@ -1022,8 +1022,10 @@ static int32_t whole_return_type(int32_t op, int32_t input_dtype) {  // whole.go
     return op == BOWGPU_AGG_WINDOW_START ? input_dtype : bowgpu_agg_return_type(op, input_dtype);
 }
 
-extern "C" int32_t bowgpu_rolling_aggregate(bowgpu_rolling *r, const bowgpu_agg_spec *specs, int32_t nspecs,
-                                            bowgpu_out_col *outs, int32_t mem) {
+// syn_by_col: null, or one FusedSyn per frame column (fused Interpolate -> Aggregate: the aggregation runs over the
+// interpolated frame without materialising it)
+static int32_t aggregate_core(bowgpu_rolling *r, const bowgpu_agg_spec *specs, int32_t nspecs, bowgpu_out_col *outs,
+                              int32_t mem, const FusedSyn *syn_by_col) {
     if (!r || !specs || !outs || nspecs <= 0) return BOWGPU_EINVAL;
     bowgpu_frame *f = r->frame;
     bowgpu_ctx *ctx = f->ctx;
@@ -1127,6 +1129,7 @@ extern "C" int32_t bowgpu_rolling_aggregate(bowgpu_rolling *r, const bowgpu_agg_
             L.carry_head = (BasicCarry *)carry;
             L.carry_tail = (BasicCarry *)carry + seg_num_tiles(g.n);
             L.status = ctx->d_status;
+            if (syn_by_col) L.syn = syn_by_col[c];
             // the valid-row count drives every validity bitmap: Count output if it can be used as is, else scratch
             int64_t *cnt = nullptr;
             if (primary[BOWGPU_AGG_COUNT] >= 0 && specs[primary[BOWGPU_AGG_COUNT]].nfactors == 0)
@@ -1170,6 +1173,7 @@ extern "C" int32_t bowgpu_rolling_aggregate(bowgpu_rolling *r, const bowgpu_agg_
             L.carry_head = carry;
             L.carry_tail = carry + integral_carry_bytes(g.n) / 2;
             L.status = ctx->d_status;
+            if (syn_by_col) L.syn = syn_by_col[c];
             const bool want_step = count[BOWGPU_AGG_INTEGRAL_STEP] || count[BOWGPU_AGG_WAVG_STEP];
             const bool want_trap = count[BOWGPU_AGG_INTEGRAL_TRAPEZOID] || count[BOWGPU_AGG_WAVG_LINEAR];
             if (want_step) {
@@ -1279,6 +1283,11 @@ extern "C" int32_t bowgpu_rolling_aggregate(bowgpu_rolling *r, const bowgpu_agg_
         if (rc) return rc;
     }
     return check_status(ctx);
+}
+
+extern "C" int32_t bowgpu_rolling_aggregate(bowgpu_rolling *r, const bowgpu_agg_spec *specs, int32_t nspecs,
+                                            bowgpu_out_col *outs, int32_t mem) {
+    return aggregate_core(r, specs, nspecs, outs, mem, nullptr);
 }
 
 // aggregation.Aggregate(b, intervalCol, aggrs...) (rolling/aggregation/whole.go:12-93): every aggregation over ONE window
@@ -1453,4 +1462,112 @@ extern "C" int32_t bowgpu_rolling_interpolate(bowgpu_rolling *r, const int32_t *
     *out_frame = of;
     *n_out = total;
     return BOWGPU_OK;
+}
+
+// Rolling.Interpolate(ops...).Aggregate(specs...) WITHOUT materialising the interpolated frame (interpolation.go:30-161
+// followed by aggregation.go:123-238).  bounds -> per-window synthetic start rows (interp_window_kernel) -> the ordinary
+// segmented reduction with the synthetic rows injected at window boundaries (segreduce.cuh, FUSED).  Cases the fused
+// kernels do not express take the materialising chain, with identical results: Options.Inclusive set by the user,
+// rows before the first window start, range-partitioned shards, and "has start" rows that only match S_k through the
+// float64 round trip (interpolation.go:121-128).
+extern "C" int32_t bowgpu_rolling_interpolate_aggregate(bowgpu_rolling *r, const int32_t *ops, int32_t nops,
+                                                        const bowgpu_agg_spec *specs, int32_t nspecs,
+                                                        bowgpu_out_col *outs, int32_t mem) {
+    if (!r || !ops || !specs || !outs || nspecs <= 0) return BOWGPU_EINVAL;
+    bowgpu_frame *f = r->frame;
+    bowgpu_ctx *ctx = f->ctx;
+    Guard gd(ctx);
+    const int ncols = (int)f->cols.size();
+    auto unfused = [&]() -> int32_t {
+        bowgpu_frame *fi = nullptr;
+        int64_t n_out = 0;
+        int32_t rc = bowgpu_rolling_interpolate(r, ops, nops, &fi, &n_out);
+        if (rc) return rc;
+        bowgpu_rolling *r2 = nullptr;
+        rc = r->shard ? bowgpu_rolling_create_shard(fi, r->time_col, r->interval, r->s0, r->W, r->inclusive, nullptr, &r2)
+                      : bowgpu_rolling_create(fi, r->time_col, r->interval, r->offset, r->inclusive, nullptr, &r2);
+        if (rc == BOWGPU_OK) rc = aggregate_core(r2, specs, nspecs, outs, mem, nullptr);
+        if (rc == BOWGPU_OK && mem == BOWGPU_MEM_DEVICE) rc = check_status(ctx);  // the frame is about to go
+        bowgpu_rolling_destroy(r2);
+        bowgpu_frame_destroy(fi);
+        return rc;
+    };
+    if (r->inclusive || r->early_rows > 0 || r->shard || r->W == 0 || f->n == 0) return unfused();
+    // validation of the interpolations: same rules as bowgpu_rolling_interpolate
+    if (nops != ncols)
+        return fail(ctx, BOWGPU_EINVAL, "interpolations must name every column in schema order (%d given, %d columns)", nops, ncols);
+    if (ncols > INTERP_MAX_COLS) return fail(ctx, BOWGPU_EUNSUPPORTED, "interpolate supports at most %d columns", INTERP_MAX_COLS);
+    for (int j = 0; j < nops; ++j) {
+        if (ops[j] < 0 || ops[j] > BOWGPU_INTERP_NONE) return fail(ctx, BOWGPU_EUNSUPPORTED, "interpolation %d: unknown opcode %d", j, ops[j]);
+        if (ops[j] == BOWGPU_INTERP_WINDOW_START && f->cols[j].dtype != BOWGPU_INT64)
+            return fail(ctx, BOWGPU_ETYPE, "interpolation %d: WindowStart accepts types [int64], got type float64", j);
+    }
+    if (ops[r->time_col] != BOWGPU_INTERP_WINDOW_START) return unfused();  // the frame's time column must carry S_k
+    const WindowGeom g = make_geom(r, false);
+    const int64_t W = g.W;
+    // per-window arrays live in pool blocks: the aggregation core re-uses the arena
+    const size_t wv = align_up((size_t)(W + 1) * 8, 256), wb = align_up((size_t)W + 16, 256);
+    uint8_t *blk = nullptr;
+    const size_t total = wv + wb + (size_t)ncols * (wv + wb);
+    if (pool_alloc(ctx, (void **)&blk, total) != cudaSuccess) return fail(ctx, BOWGPU_ENOMEM, "fused interpolate: scratch");
+    auto bail = [&](int32_t code) {
+        pool_free(ctx, blk);
+        return code;
+    };
+    InterpLaunch L;
+    memset(&L, 0, sizeof L);
+    L.time = (const int64_t *)f->cols[r->time_col].values;
+    int64_t *d_first = (int64_t *)blk;
+    L.first = d_first;
+    L.missing = blk + wv;
+    L.status = ctx->d_status;
+    L.g = g;
+    L.inclusive = 0;
+    L.ncols = ncols;
+    if (r->has_prev) {
+        L.prev_time = (int64_t)r->prev[r->time_col].bits;
+        L.prev_time_valid = r->prev[r->time_col].valid;
+    }
+    std::vector<FusedSyn> syn(ncols);
+    uint8_t *p = blk + wv + wb;
+    for (int j = 0; j < ncols; ++j) {
+        InterpCol &c = L.cols[j];
+        c.values = f->cols[j].values;
+        c.validity = (const uint32_t *)f->cols[j].validity;
+        c.syn_val = (uint64_t *)p;
+        c.syn_ok = p + wv;
+        p += wv + wb;
+        c.op = ops[j];
+        c.is_int = f->cols[j].dtype == BOWGPU_INT64;
+        if (r->has_prev) {
+            c.prev_bits = r->prev[j].bits;
+            c.prev_valid = r->prev[j].valid;
+        }
+        syn[j].missing = L.missing;
+        syn[j].val = c.syn_val;
+        syn[j].ok = c.syn_ok;
+    }
+    // synthetic rows of windows that have a start row are never read, but keep the arrays defined
+    if (cudaMemsetAsync(blk + wv, 0, total - wv, ctx->stream) != cudaSuccess) return bail(fail(ctx, BOWGPU_ECUDA, "memset"));
+    BoundsLaunch B;
+    B.time = L.time;
+    B.g = g;
+    B.first = d_first;
+    B.status = ctx->d_status;
+    int e = launch_bounds(B, ctx->sm_count, ctx->stream, nullptr, nullptr);
+    if (!e) e = launch_interp_windows(L, ctx->stream);
+    count_launch(ctx, 2);
+    int32_t st = 0;
+    if (e || cudaMemcpyAsync(&st, ctx->d_status, 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+        return bail(fail(ctx, BOWGPU_ECUDA, "fused interpolate (windows): %s", cudaGetErrorString(cudaGetLastError())));
+    if (st & ST_INEXACT_START) {  // rare: ns timestamps whose window starts are hit only approximately
+        cudaMemsetAsync(ctx->d_status, 0, 4, ctx->stream);
+        pool_free(ctx, blk);
+        if (st & ST_UNSORTED) return fail(ctx, BOWGPU_EUNSORTED, "time column is not sorted ascending");
+        return unfused();
+    }
+    const int32_t rc = aggregate_core(r, specs, nspecs, outs, mem, syn.data());
+    pool_free(ctx, blk);  // stream ordered: released after the kernels that read it
+    return rc;
 }

@@ -64,8 +64,14 @@ __global__ void interp_window_kernel(const InterpLaunch P) {
     // interpolation.go:119-128: the comparison goes through float64
     const int64_t fcv = hi > lo ? f64_to_i64_go((double)t[lo]) : -1;
     const int missing = fcv != Sk;
-    P.off[k] = (int64_t)missing + (hi - lo);
-    P.wsrc[k] = (lo - missing) * 2 + missing;  // fixed up to "source row - output row" after the scan
+    if (P.off) {
+        P.off[k] = (int64_t)missing + (hi - lo);
+        P.wsrc[k] = (lo - missing) * 2 + missing;  // fixed up to "source row - output row" after the scan
+    }
+    if (P.missing) P.missing[k] = (uint8_t)missing;
+    // beyond 2^53 a first row NEAR S_k passes the float64 test without sitting exactly on it: the fused
+    // Interpolate -> Aggregate path cannot express that frame and falls back to the materialising one
+    if (!missing && hi > lo && t[lo] != Sk && P.status) atomicOr(P.status, ST_INEXACT_START);
     if (!missing) return;
     for (int j = 0; j < P.ncols; ++j) {
         const InterpCol &c = P.cols[j];

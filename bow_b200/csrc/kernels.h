@@ -34,7 +34,7 @@ __host__ __device__ __forceinline__ int64_t window_last_value(const WindowGeom &
 }
 
 // status word bits written by the kernels
-enum { ST_UNSORTED = 1 };
+enum { ST_UNSORTED = 1, ST_INEXACT_START = 2 };
 
 // ---- carry record of one tile edge (segreduce) ------------------------------------------------
 struct alignas(16) BasicCarry {
@@ -58,6 +58,14 @@ struct BasicOut {  // per-window outputs of one input column (any pointer may be
 // ops bit mask of the basic family
 enum { OPS_SUMCNT = 1, OPS_MINMAX = 2, OPS_FIRSTLAST = 4 };
 
+// Fused Rolling.Interpolate -> Rolling.Aggregate: the synthetic window-start rows of the interpolated frame are not
+// materialised; the reduction injects them at window boundaries from these per-window arrays (interp_window_kernel).
+struct FusedSyn {
+    const uint8_t *missing;  // [W] 1 = the interpolated frame holds a synthetic row at S_k (null = not fused)
+    const uint64_t *val;     // [W] its value in this column (raw bits)
+    const uint8_t *ok;       // [W] its validity
+};
+
 struct SegLaunch {
     const int64_t *time;
     const uint64_t *values;
@@ -69,6 +77,7 @@ struct SegLaunch {
     BasicCarry *carry_head;   // [ntiles]
     BasicCarry *carry_tail;   // [ntiles]
     int32_t *status;
+    FusedSyn syn;
 };
 
 int64_t seg_num_tiles(int64_t n);
@@ -94,6 +103,7 @@ struct IntLaunch {
     void *carry_head;  // [ntiles] of integral_carry_bytes(n) / 2
     void *carry_tail;
     int32_t *status;
+    FusedSyn syn;
 };
 size_t integral_carry_bytes(int64_t n);
 int launch_segreduce_integral(const IntLaunch &L, int sm_count, cudaStream_t stream, cudaEvent_t ev_main0,
@@ -129,8 +139,10 @@ struct InterpCol {
 struct InterpLaunch {
     const int64_t *time;
     const int64_t *first;  // [W+1] from the bounds kernel
-    int64_t *off;          // [W+1] output rows per window, scanned in place to output offsets
-    int64_t *wsrc;         // [W]
+    int64_t *off;          // [W+1] output rows per window, scanned in place to output offsets (null: fused path)
+    int64_t *wsrc;         // [W] (null: fused path)
+    uint8_t *missing;      // [W] 1 = window k gets a synthetic start row (may be null)
+    int32_t *status;       // ST_INEXACT_START is raised when a window's "has start" row is not exactly at S_k
     WindowGeom g;
     int64_t prev_time;     // Options.PrevRow time cell
     int32_t prev_time_valid;

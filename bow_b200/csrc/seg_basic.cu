@@ -86,6 +86,14 @@ struct BasicPol {
             s.cnt += __popc(mask);
         }
     }
+    // one synthetic row of the interpolated frame joins a run as its FIRST row (fused Interpolate -> Aggregate)
+    static __device__ __forceinline__ void inject(State &s, int64_t t, uint64_t raw, bool valid) {
+        if (!valid) return;
+        accumulate(s, t, raw);
+        if (s.cnt == 0) s.first = raw;
+        s.last = raw;
+        s.cnt += 1;
+    }
     static __device__ __forceinline__ State combine(const State &L, const State &R) {
         State o;
         o.sum = L.sum + R.sum;
@@ -138,6 +146,21 @@ struct BasicPol {
     static __device__ __forceinline__ int64_t carry_key(const Carry &c) { return c.key; }
     static __device__ __forceinline__ bool carry_closed(const Carry &c) { return (c.cnt & CLOSED_BIT) != 0; }
     static __device__ __forceinline__ void carry_inc_from_edge(Carry &, const Carry &, int64_t) {}
+    static __device__ __forceinline__ void carry_set_inc(Carry &, const Inc &) {}
+    static __device__ __forceinline__ uint64_t carry_edge_raw(const Carry &) { return 0; }
+    static __device__ __forceinline__ bool carry_edge_valid(const Carry &) { return false; }
+    static __device__ __forceinline__ void carry_prepend_point(Carry &a, int64_t t, uint64_t raw, bool valid) {
+        if (!valid) return;
+        State p = identity();
+        inject(p, t, raw, true);
+        const int64_t ac = a.cnt & ~CLOSED_BIT;
+        a.sum = p.sum + a.sum;
+        a.mn = (a.mn < p.mn) ? a.mn : p.mn;
+        a.mx = (a.mx > p.mx) ? a.mx : p.mx;
+        a.first = raw;
+        a.last = ac ? a.last : raw;
+        a.cnt += 1;
+    }
     static __device__ __forceinline__ void carry_clear_inc(Carry &) {}
     static __device__ __forceinline__ void carry_combine(Carry &a, const Carry &h) {
         const int64_t ac = a.cnt & ~CLOSED_BIT, hc = h.cnt & ~CLOSED_BIT;
@@ -165,6 +188,7 @@ int launch_ops(const SegLaunch &L, int sm, cudaStream_t s, cudaEvent_t e0, cudaE
         A.carry_head = L.carry_head;
         A.carry_tail = L.carry_tail;
         A.status = L.status;
+        A.syn = L.syn;
     };
     if (L.is_int) {
         SegArgs<BasicPol<OPS, true>> A;

@@ -93,6 +93,16 @@ struct IntegralPol {
             s.n += __popc(mask);
         }
     }
+    // one synthetic row of the interpolated frame joins a run as its FIRST point (fused Interpolate -> Aggregate)
+    static __device__ __forceinline__ void inject(State &s, int64_t t, uint64_t raw, bool valid) {
+        if (!valid) return;
+        accumulate(s, t, raw);
+        if (s.n == 0) {
+            s.fT = (double)t;
+            s.fV = val(raw);
+        }
+        s.n += 1;
+    }
     static __device__ __forceinline__ State combine(const State &L, const State &R) {
         State o;
         o.sS = o.sT = 0.0;  // (the sum this instantiation does not maintain)
@@ -179,6 +189,30 @@ struct IntegralPol {
         a.incT = (double)h.edge_t;
     }
     static __device__ __forceinline__ void carry_clear_inc(Carry &a) { a.inc_has = 0; }
+    static __device__ __forceinline__ void carry_set_inc(Carry &a, const Inc &inc) {
+        a.inc_has = TRAP && inc.has;
+        a.incV = inc.v;
+        a.incT = inc.T;
+    }
+    static __device__ __forceinline__ uint64_t carry_edge_raw(const Carry &c) { return c.edge_raw; }
+    static __device__ __forceinline__ bool carry_edge_valid(const Carry &c) { return c.edge_valid != 0; }
+    static __device__ __forceinline__ void carry_prepend_point(Carry &a, int64_t t, uint64_t raw, bool valid) {
+        if (!valid) return;
+        const double T = (double)t, v = val(raw);
+        const int64_t an = a.n & ~I_CLOSED_BIT;
+        if (an) {
+            const double dt = a.fT - T;
+            a.sS = (0.0 + v * dt) + a.sS;
+            a.sT = (0.0 + (v + a.fV) / 2 * dt) + a.sT;
+        } else {
+            a.sS = a.sT = 0.0;
+            a.lT = T;
+            a.lV = v;
+        }
+        a.fT = T;
+        a.fV = v;
+        a.n += 1;
+    }
     static __device__ __forceinline__ void carry_set_key(Carry &c, int64_t key) { c.key = key; }
     static __device__ __forceinline__ int64_t carry_key(const Carry &c) { return c.key; }
     static __device__ __forceinline__ bool carry_closed(const Carry &c) { return (c.n & I_CLOSED_BIT) != 0; }
@@ -220,6 +254,7 @@ int launch_mode(const IntLaunch &L, int sm, cudaStream_t s, cudaEvent_t e0, cuda
         A.carry_head = (ICarry *)L.carry_head;
         A.carry_tail = (ICarry *)L.carry_tail;
         A.status = L.status;
+        A.syn = L.syn;
     };
     if (L.is_int) {
         SegArgs<IntegralPol<STEP, TRAP, true>> A;

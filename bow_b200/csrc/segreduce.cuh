@@ -86,6 +86,7 @@ struct SegArgs {
     typename Pol::Carry *carry_head;  // [ntiles]
     typename Pol::Carry *carry_tail;  // [ntiles]
     int32_t *status;
+    FusedSyn syn;                     // fused Interpolate -> Aggregate (FUSED instantiations only)
 };
 
 template <class Pol>
@@ -112,6 +113,41 @@ __device__ __noinline__ static uint64_t div_slow(uint64_t x, uint64_t d, double 
     return div_u64(x, dv);
 }
 
+// ---- fused Interpolate -> Aggregate -------------------------------------------------------------------------------
+// In the interpolated frame (rolling/interpolation.go:118-161) window k holds [a synthetic row at S_k iff missing[k]]
+// ++ its own rows, and every EMPTY window holds exactly its synthetic row.  The inclusive row of window k is the first
+// row of window k+1 in that frame: the synthetic row at S_{k+1} when there is one, else the real first row if it sits
+// exactly on E_k.  fused_boundary() is called where window `kcur` ends and the next REAL row (x, raw, valid) - if any -
+// lies in window `knew`: it returns the inclusive row of kcur, writes the empty windows in between, and leaves in
+// `fresh` the state window knew starts from (its synthetic row, or the identity).
+template <class Pol>
+__device__ __forceinline__ typename Pol::Inc fused_boundary(const SegArgs<Pol> &A, const uint64_t kcur, const bool has_row,
+                                                            const uint64_t knew, const int64_t x, const uint64_t raw,
+                                                            const bool valid, typename Pol::State &fresh) {
+    using Inc = typename Pol::Inc;
+    const WindowGeom &g = A.g;
+    const FusedSyn &S = A.syn;
+    fresh = Pol::identity();
+    if (!has_row) return Pol::make_inc(false, false, 0, 0);  // the column ends: no window after kcur
+    const uint64_t d = g.div.d;
+    auto start_of = [&](uint64_t k) { return (int64_t)((uint64_t)g.s0 + k * d); };
+    auto real_inc = [&](uint64_t k) {  // the real row as inclusive row of window k (only if it sits exactly on E_k)
+        return Pol::make_inc(x == start_of(k + 1), valid, raw, x);
+    };
+    auto syn_inc = [&](uint64_t k) { return Pol::make_inc(true, S.ok[k] != 0, S.val[k], start_of(k)); };
+    const bool miss_new = S.missing[knew] != 0;
+    const uint64_t kn = kcur + 1;
+    const Inc inc = (knew == kn && !miss_new) ? real_inc(kcur) : syn_inc(kn);
+    for (uint64_t m = kn; m < knew; ++m) {  // empty windows: one synthetic row each (interpolation.go:83-100 golden)
+        typename Pol::State sm = Pol::identity();
+        Pol::inject(sm, start_of(m), S.val[m], S.ok[m] != 0);
+        const Inc im = (m + 1 < knew || miss_new) ? syn_inc(m + 1) : real_inc(m);
+        Pol::write(A.out, g, (int64_t)m, sm, im);
+    }
+    if (miss_new) Pol::inject(fresh, start_of(knew), S.val[knew], S.ok[knew] != 0);
+    return inc;
+}
+
 // per-thread state that lives in registers across the phases of one tile
 template <class Pol>
 struct SegThread {
@@ -130,7 +166,7 @@ struct SegThread {
 
 // One phase: P rows of every thread.  FULL: all rows of the tile exist and none lies before s0 (the common case,
 // free of per-row existence predicates).
-template <class Pol, bool HAS_NULLS, bool FULL>
+template <class Pol, bool HAS_NULLS, bool FULL, bool FUSED>
 __device__ __forceinline__ void seg_phase(SegThread<Pol> &c, const SegArgs<Pol> &A, const int64_t r0, const int phase,
                                           const uint8_t *slot, const uint32_t *bsm, bool &bad) {
     using Inc = typename Pol::Inc;
@@ -189,22 +225,44 @@ __device__ __forceinline__ void seg_phase(SegThread<Pol> &c, const SegArgs<Pol> 
             c.xlast = xj;
             if (xj >= c.eabs) {  // row j starts a later window: the open one is complete
                 Pol::note(c.st, vbits & ((1u << j) - 1u) & ~((1u << segstart) - 1u), trow, vrow);
-                const Inc inc = Pol::make_inc(xj == c.eabs, (vbits >> j) & 1u, rj, xj);
-                if (c.nclose == 0) {
-                    c.head = c.st;
-                    c.inc_head = inc;
+                if (!FUSED) {
+                    const Inc inc = Pol::make_inc(xj == c.eabs, (vbits >> j) & 1u, rj, xj);
+                    if (c.nclose == 0) {
+                        c.head = c.st;
+                        c.inc_head = inc;
+                    } else {
+                        Pol::write(A.out, g, (int64_t)c.kcur, c.st, inc);
+                    }
+                    ++c.nclose;
+                    c.st = Pol::identity();
+                    segstart = j;
+                    if ((uint64_t)xj - (uint64_t)c.eabs < d) {
+                        ++c.kcur;
+                        c.eabs = (int64_t)((uint64_t)c.eabs + d);
+                    } else {
+                        c.kcur = div_slow((uint64_t)xj - (uint64_t)g.s0, d, g.div.inv_rd);
+                        c.eabs = (int64_t)((uint64_t)g.s0 + (c.kcur + 1) * d);
+                    }
                 } else {
-                    Pol::write(A.out, g, (int64_t)c.kcur, c.st, inc);
-                }
-                ++c.nclose;
-                c.st = Pol::identity();
-                segstart = j;
-                if ((uint64_t)xj - (uint64_t)c.eabs < d) {
-                    ++c.kcur;
-                    c.eabs = (int64_t)((uint64_t)c.eabs + d);
-                } else {
-                    c.kcur = div_slow((uint64_t)xj - (uint64_t)g.s0, d, g.div.inv_rd);
-                    c.eabs = (int64_t)((uint64_t)g.s0 + (c.kcur + 1) * d);
+                    const uint64_t kold = c.kcur;
+                    if ((uint64_t)xj - (uint64_t)c.eabs < d) {
+                        ++c.kcur;
+                        c.eabs = (int64_t)((uint64_t)c.eabs + d);
+                    } else {
+                        c.kcur = div_slow((uint64_t)xj - (uint64_t)g.s0, d, g.div.inv_rd);
+                        c.eabs = (int64_t)((uint64_t)g.s0 + (c.kcur + 1) * d);
+                    }
+                    typename Pol::State fresh;
+                    const Inc inc = fused_boundary<Pol>(A, kold, true, c.kcur, xj, rj, (vbits >> j) & 1u, fresh);
+                    if (c.nclose == 0) {
+                        c.head = c.st;
+                        c.inc_head = inc;
+                    } else {
+                        Pol::write(A.out, g, (int64_t)kold, c.st, inc);
+                    }
+                    ++c.nclose;
+                    c.st = fresh;
+                    segstart = j;
                 }
             }
             if ((vbits >> j) & 1u) Pol::accumulate(c.st, xj, rj);
@@ -223,7 +281,7 @@ __device__ __forceinline__ void seg_phase(SegThread<Pol> &c, const SegArgs<Pol> 
 }
 
 // End of a tile: stitch the per-thread pieces.
-template <class Pol, bool FULL>
+template <class Pol, bool FULL, bool FUSED>
 __device__ __forceinline__ void seg_stitch(SegThread<Pol> &c, const SegArgs<Pol> &A, const int64_t tile,
                                            WarpTotal<Pol> *wtot, const WarpEdge *wedge, bool &bad) {
     using State = typename Pol::State;
@@ -237,7 +295,7 @@ __device__ __forceinline__ void seg_stitch(SegThread<Pol> &c, const SegArgs<Pol>
     // ---- the boundary at my right edge: compare with the first row of the next thread ----------------------
     uint64_t nk = __shfl_down_sync(0xffffffffu, (unsigned long long)c.kf, 1);
     int64_t nt = __shfl_down_sync(0xffffffffu, (long long)c.first_t, 1);
-    uint64_t nraw = Pol::NEXT_VALUE ? __shfl_down_sync(0xffffffffu, (unsigned long long)c.first_raw, 1) : 0;
+    uint64_t nraw = (Pol::NEXT_VALUE || FUSED) ? __shfl_down_sync(0xffffffffu, (unsigned long long)c.first_raw, 1) : 0;
     uint32_t nflags = __shfl_down_sync(0xffffffffu, c.first_flags, 1);
     if (lane == 31) {
         if (warp + 1 < SEG_NW) {
@@ -264,8 +322,13 @@ __device__ __forceinline__ void seg_stitch(SegThread<Pol> &c, const SegArgs<Pol>
     }
     bool tail_open = has_rows;  // (meaningful for the last thread of the tile only)
     if (closes_right) {
-        const Inc inc = next_has ? Pol::make_inc(nt == c.eabs, (nflags & EDGE_VALID) != 0, nraw, nt)
-                                 : Pol::make_inc(false, false, 0, 0);
+        State fresh = Pol::identity();
+        Inc inc;
+        if (FUSED)  // (also writes the empty windows between mine and the next thread's, and seeds the next window)
+            inc = fused_boundary<Pol>(A, c.kcur, next_has, nk, nt, nraw, (nflags & EDGE_VALID) != 0, fresh);
+        else
+            inc = next_has ? Pol::make_inc(nt == c.eabs, (nflags & EDGE_VALID) != 0, nraw, nt)
+                           : Pol::make_inc(false, false, 0, 0);
         if (c.nclose == 0) {
             c.head = c.st;
             c.inc_head = inc;
@@ -273,7 +336,7 @@ __device__ __forceinline__ void seg_stitch(SegThread<Pol> &c, const SegArgs<Pol>
             Pol::write(A.out, g, (int64_t)c.kcur, c.st, inc);
         }
         ++c.nclose;
-        c.st = Pol::identity();
+        c.st = fresh;  // the tail now belongs to the window the next thread starts in
         tail_open = false;
     }
 
@@ -338,7 +401,7 @@ __device__ __forceinline__ void seg_stitch(SegThread<Pol> &c, const SegArgs<Pol>
     }
 }
 
-template <class Pol, bool HAS_NULLS, int MIN_CTAS>
+template <class Pol, bool HAS_NULLS, int MIN_CTAS, bool FUSED>
 __global__ void __launch_bounds__(SEG_NT, MIN_CTAS)
     segreduce_kernel(const __grid_constant__ SegArgs<Pol> A, const __grid_constant__ CUtensorMap tm_time,
                      const __grid_constant__ CUtensorMap tm_val, const int64_t ntiles, const int nstages) {
@@ -414,7 +477,7 @@ __global__ void __launch_bounds__(SEG_NT, MIN_CTAS)
             if (fullt) {
                 mbar_wait(&full[s], (parity >> s) & 1u);
                 parity ^= 1u << s;
-                seg_phase<Pol, HAS_NULLS, true>(c, A, r0, phase, slot, bsm, bad);
+                seg_phase<Pol, HAS_NULLS, true, FUSED>(c, A, r0, phase, slot, bsm, bad);
             } else {
                 // tile at an edge of the column (or holding rows before s0): staged by plain loads with bounds checks
                 int64_t *ts = reinterpret_cast<int64_t *>(slot);
@@ -433,7 +496,7 @@ __global__ void __launch_bounds__(SEG_NT, MIN_CTAS)
                     for (int w = tid; w < SEG_BITS_COPY / 4; w += SEG_NT) bw[w] = w < words_left ? src[w] : 0u;
                 }
                 __syncthreads();
-                seg_phase<Pol, HAS_NULLS, false>(c, A, r0, phase, slot, bsm, bad);
+                seg_phase<Pol, HAS_NULLS, false, FUSED>(c, A, r0, phase, slot, bsm, bad);
             }
             if (phase == 0 && (tid & 31) == 0) {  // publish my first row for the previous warp's last lane
                 WarpEdge e;
@@ -448,9 +511,9 @@ __global__ void __launch_bounds__(SEG_NT, MIN_CTAS)
             if (tid == 0) issue_item(q + nstages);
         }
         if (fullt)
-            seg_stitch<Pol, true>(c, A, tile, wtot, wedge, bad);
+            seg_stitch<Pol, true, FUSED>(c, A, tile, wtot, wedge, bad);
         else
-            seg_stitch<Pol, false>(c, A, tile, wtot, wedge, bad);
+            seg_stitch<Pol, false, FUSED>(c, A, tile, wtot, wedge, bad);
         __syncthreads();  // wtot / wedge are reused by the next tile
     }
     if (bad) atomicOr(A.status, ST_UNSORTED);
@@ -459,7 +522,7 @@ __global__ void __launch_bounds__(SEG_NT, MIN_CTAS)
 // Joins the per-tile records, strictly left to right.  Thread j owns the windows whose first row lies in tile j
 // and that are not complete inside it: the one at the left edge of the tile (head record, unless it continues a
 // window of an earlier tile) and the one open at its right edge (tail record).
-template <class Pol>
+template <class Pol, bool FUSED>
 __global__ void seg_fixup_kernel(const __grid_constant__ SegArgs<Pol> A, const int64_t ntiles) {
     using Carry = typename Pol::Carry;
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -470,8 +533,15 @@ __global__ void seg_fixup_kernel(const __grid_constant__ SegArgs<Pol> A, const i
         for (; i < ntiles; ++i) {
             const Carry h = A.carry_head[i];
             if (Pol::carry_key(h) != key) {  // the window ended exactly at the tile boundary
-                const int64_t E = (int64_t)((uint64_t)g.s0 + ((uint64_t)key + 1) * g.div.d);
-                Pol::carry_inc_from_edge(a, h, E);
+                if (FUSED) {  // (also writes the empty windows up to the next tile's first window)
+                    typename Pol::State fresh;
+                    Pol::carry_set_inc(a, fused_boundary<Pol>(A, (uint64_t)key, true, (uint64_t)Pol::carry_key(h),
+                                                              Pol::carry_edge_t(h), Pol::carry_edge_raw(h),
+                                                              Pol::carry_edge_valid(h), fresh));
+                } else {
+                    const int64_t E = (int64_t)((uint64_t)g.s0 + ((uint64_t)key + 1) * g.div.d);
+                    Pol::carry_inc_from_edge(a, h, E);
+                }
                 Pol::write_carry(A.out, g, key, a);
                 return;
             }
@@ -484,7 +554,7 @@ __global__ void seg_fixup_kernel(const __grid_constant__ SegArgs<Pol> A, const i
         Pol::carry_clear_inc(a);
         Pol::write_carry(A.out, g, key, a);  // the column ends inside the window
     };
-    const Carry hd = A.carry_head[j];
+    Carry hd = A.carry_head[j];
     const Carry tl = A.carry_tail[j];
     bool starts = true;
     if (j > 0) {
@@ -498,6 +568,11 @@ __global__ void seg_fixup_kernel(const __grid_constant__ SegArgs<Pol> A, const i
         if (Pol::carry_edge_t(hd) < Pol::carry_edge_t(pt)) atomicOr(A.status, ST_UNSORTED);
     }
     if (starts) {
+        if (FUSED) {  // the window begins at the tile's first row: its synthetic start row comes first
+            const int64_t k = Pol::carry_key(hd);
+            if (A.syn.missing[k])
+                Pol::carry_prepend_point(hd, (int64_t)((uint64_t)g.s0 + (uint64_t)k * g.div.d), A.syn.val[k], A.syn.ok[k] != 0);
+        }
         if (Pol::carry_closed(hd))
             Pol::write_carry(A.out, g, Pol::carry_key(hd), hd);
         else
@@ -548,11 +623,11 @@ inline int seg_make_tmap(CUtensorMap *m, const void *col, int64_t n) {
     return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
-template <class Pol, bool HAS_NULLS, int MIN_CTAS>
-int seg_launch(const SegArgs<Pol> &A, int sm_count, cudaStream_t stream, cudaEvent_t e0, cudaEvent_t e1) {
+template <class Pol, bool HAS_NULLS, int MIN_CTAS, bool FUSED>
+int seg_launch_impl(const SegArgs<Pol> &A, int sm_count, cudaStream_t stream, cudaEvent_t e0, cudaEvent_t e1) {
     const int64_t ntiles = (A.g.n + SEG_T - 1) / SEG_T;
     if (ntiles == 0) return 0;
-    auto kern = segreduce_kernel<Pol, HAS_NULLS, MIN_CTAS>;
+    auto kern = segreduce_kernel<Pol, HAS_NULLS, MIN_CTAS, FUSED>;
     static int nstages = 0, ctas = 0;
     if (!nstages) seg_knobs(nstages, ctas, 2, MIN_CTAS);
     const int smem = seg_smem_bytes(nstages);
@@ -576,8 +651,14 @@ int seg_launch(const SegArgs<Pol> &A, int sm_count, cudaStream_t stream, cudaEve
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     const int fb = 128;
-    seg_fixup_kernel<Pol><<<(unsigned)((ntiles + fb - 1) / fb), fb, 0, stream>>>(A, ntiles);
+    seg_fixup_kernel<Pol, FUSED><<<(unsigned)((ntiles + fb - 1) / fb), fb, 0, stream>>>(A, ntiles);
     return (int)cudaGetLastError();
+}
+
+template <class Pol, bool HAS_NULLS, int MIN_CTAS>
+int seg_launch(const SegArgs<Pol> &A, int sm_count, cudaStream_t stream, cudaEvent_t e0, cudaEvent_t e1) {
+    return A.syn.missing ? seg_launch_impl<Pol, HAS_NULLS, MIN_CTAS, true>(A, sm_count, stream, e0, e1)
+                         : seg_launch_impl<Pol, HAS_NULLS, MIN_CTAS, false>(A, sm_count, stream, e0, e1);
 }
 
 }  // namespace bowgpu

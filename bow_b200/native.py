@@ -37,6 +37,7 @@ SYMBOLS = [
     "bowgpu_rolling_first_window_start", "bowgpu_rolling_inclusive", "bowgpu_rolling_early_rows",
     "bowgpu_rolling_bounds", "bowgpu_rolling_aggregate", "bowgpu_agg_return_type", "bowgpu_agg_needs_inclusive",
     "bowgpu_rolling_interpolate", "bowgpu_frame_aggregate_whole", "bowgpu_frame_fill", "bowgpu_frame_fill_linear",
+    "bowgpu_rolling_interpolate_aggregate",
 ]
 
 
@@ -105,6 +106,8 @@ def lib():
         L.bowgpu_rolling_bounds.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.bowgpu_rolling_aggregate.argtypes = [C.c_void_p, C.POINTER(AggSpec), C.c_int32, C.POINTER(OutCol),
                                                C.c_int32]
+        L.bowgpu_rolling_interpolate_aggregate.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.POINTER(AggSpec),
+                                                           C.c_int32, C.POINTER(OutCol), C.c_int32]
         L.bowgpu_frame_fill.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p)]
         L.bowgpu_frame_fill_linear.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
         L.bowgpu_frame_aggregate_whole.argtypes = [C.c_void_p, C.c_int32, C.POINTER(AggSpec), C.c_int32, C.POINTER(OutCol),
@@ -391,6 +394,30 @@ class Rolling:
     def aggregate_device(self, specs_arr, nspecs: int, outs) -> None:
         """Asynchronous: results stay on the device (outs: OutCol array of device pointers)."""
         self.ctx.check(lib().bowgpu_rolling_aggregate(self.h, specs_arr, nspecs, outs, MEM_DEVICE))
+
+    def interpolate_aggregate(self, ops: Sequence, specs: Sequence[tuple]):
+        """Interpolate(ops).Aggregate(specs) without materialising the interpolated frame
+        -> list of (values ndarray, valid mask ndarray), host memory"""
+        W = self.num_windows
+        codes = (C.c_int32 * len(ops))(*[INTERP[o] if isinstance(o, str) else int(o) for o in ops])
+        arr = make_specs(specs)
+        outs = (OutCol * len(specs))()
+        bufs = []
+        for j in range(len(specs)):
+            v = np.full(max(W, 1), -7, dtype=np.int64)
+            b = np.full((W + 7) // 8 + 1, 0xAA, dtype=np.uint8)
+            bufs.append((v, b))
+            outs[j].values, outs[j].validity = v.ctypes.data, b.ctypes.data
+        self.ctx.check(lib().bowgpu_rolling_interpolate_aggregate(self.h, codes, len(ops), arr, len(specs), outs, MEM_HOST))
+        res = []
+        for j, (v, b) in enumerate(bufs):
+            vals = v[:W] if outs[j].dtype == INT64 else v[:W].view(np.float64)
+            res.append((vals, unpack_bits(b, W)))
+        return res
+
+    def interpolate_aggregate_device(self, ops: Sequence, specs_arr, nspecs: int, outs) -> None:
+        codes = (C.c_int32 * len(ops))(*[INTERP[o] if isinstance(o, str) else int(o) for o in ops])
+        self.ctx.check(lib().bowgpu_rolling_interpolate_aggregate(self.h, codes, len(ops), specs_arr, nspecs, outs, MEM_DEVICE))
 
     def interpolate(self, ops: Sequence) -> Frame:
         codes = (C.c_int32 * len(ops))(*[INTERP[o] if isinstance(o, str) else int(o) for o in ops])

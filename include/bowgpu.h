@@ -247,6 +247,16 @@ int32_t bowgpu_frame_fill_linear(bowgpu_frame *frame, int32_t ref_col, int32_t t
 int32_t bowgpu_rolling_interpolate(bowgpu_rolling *r, const int32_t *ops, int32_t nops, bowgpu_frame **out_frame,
                                    int64_t *n_out);
 
+/* Rolling.Interpolate(ops...).Aggregate(specs...) in one call (interpolation.go:30-161 then aggregation.go:123-238):
+ * the result equals bowgpu_rolling_interpolate followed by bowgpu_rolling_aggregate on the interpolated frame, but
+ * the interpolated frame is not materialised (its synthetic window-start rows are injected into the reduction).
+ * ops / nops as in bowgpu_rolling_interpolate, specs / outs / mem as in bowgpu_rolling_aggregate; outs hold
+ * bowgpu_rolling_num_windows(r) entries.  This is what the Go shim calls when Aggregate follows Interpolate and the
+ * interpolated Bow itself is never asked for. */
+int32_t bowgpu_rolling_interpolate_aggregate(bowgpu_rolling *r, const int32_t *ops, int32_t nops,
+                                             const bowgpu_agg_spec *specs, int32_t nspecs, bowgpu_out_col *outs,
+                                             int32_t mem);
+
 #ifdef __cplusplus
 }
 #endif

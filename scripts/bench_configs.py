@@ -89,6 +89,11 @@ def main():
         alg = 40 * n + 4 * n // 8 + len(specs) * (8 * W + W // 8)     # fused chain, inputs read once
         report("configs[2] Interpolate(WindowStart, Linear x4) -> WeightedAverageLinear + IntegralTrapezoid x4", n, dt, alg,
                {"note": "the interpolated frame is materialised: actual traffic ~3x algorithmic"})
+        ctx.enable_timing(1)
+        dtf = timed(ctx, lambda: r.interpolate_aggregate_device(ops, arr, len(specs), outs), reps=3, warm=1)
+        report("configs[2] FUSED Interpolate -> Aggregate (bowgpu_rolling_interpolate_aggregate, no materialised frame)", n, dtf,
+               alg, {"launches_last_call": ctx.last_timing().launches})
+        ctx.enable_timing(0)
         fi = r.interpolate(ops)
         r2 = N.Rolling(fi, 0, 900 * SEC, offset=420 * SEC)
         dt2 = timed(ctx, lambda: r2.aggregate_device(arr, len(specs), outs), reps=5)
@@ -115,6 +120,12 @@ def main():
         dt = timed(ctx, chain, reps=3, warm=1)
         report("configs[3] bursty Interpolate(WindowStart, StepPrevious) -> First/Last/Min/Max", n, dt,
                16 * n + n // 8 + len(specs) * (8 * W + W // 8))
+        ctx.enable_timing(1)
+        dtf = timed(ctx, lambda: r.interpolate_aggregate_device(["WindowStart", "StepPrevious"], arr, len(specs), outs),
+                    reps=5, warm=1)
+        report("configs[3] FUSED Interpolate -> Aggregate", n, dtf, 16 * n + n // 8 + len(specs) * (8 * W + W // 8),
+               {"launches_last_call": ctx.last_timing().launches})
+        ctx.enable_timing(0)
         r.close(); fr.close(); del keep
     if "4" in which:
         n = int(5e8 * SCALE)

@@ -51,6 +51,38 @@ def device_outputs(ctx, rolling, specs):
     return vals, bits
 
 
+def fused_outputs(ctx, rolling, ops, specs):
+    """bowgpu_rolling_interpolate_aggregate with device-resident outputs"""
+    import torch
+    from bow_b200 import native as N
+    W = rolling.num_windows
+    vals = [torch.empty(max(W, 1), dtype=torch.int64, device="cuda") for _ in specs]
+    bits = [torch.zeros((W + 7) // 8 + 16, dtype=torch.uint8, device="cuda") for _ in specs]
+    outs = (N.OutCol * len(specs))()
+    for j in range(len(specs)):
+        outs[j].values, outs[j].validity = vals[j].data_ptr(), bits[j].data_ptr()
+    rolling.interpolate_aggregate_device(ops, N.make_specs(specs), len(specs), outs)
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    return vals, bits
+
+
+def assert_same_outputs(specs, a, b, W, in_dtypes, what, rel=1e-12, scale=1.0):
+    """fused vs materialising chain on the device: identical bitmaps; values bit-exact, or within `rel` of
+    max(|x|, scale) for the float64 sums"""
+    import torch
+    (va, ba), (vb, bb) = a, b
+    nb = (W + 7) // 8
+    for (op, col), x, y, p, q in zip(specs, va, vb, ba, bb):
+        assert torch.equal(p[:nb], q[:nb]), f"{what} {op}({col}): validity differs"
+        if op in TOL_OPS:
+            fx, fy = x[:W].view(torch.float64), y[:W].view(torch.float64)
+            tol = rel * torch.clamp(fy.abs(), min=scale)
+            assert bool(((fx - fy).abs() <= tol).all()), f"{what} {op}({col}): max diff {float((fx - fy).abs().max())}"
+        else:
+            assert torch.equal(x[:W], y[:W]), f"{what} {op}({col}): values differ"
+
+
 def host_window_range(vals, bits, k0, k1, is_float):
     """windows [k0, k1) of a device output -> (values ndarray, mask ndarray); k0 must be a multiple of 8"""
     from bow_b200 import native as N
@@ -148,6 +180,9 @@ def test_config2_1B_interpolate_linear_then_weighted_average(ctx):
         specs += [("WeightedAverageLinear", c), ("IntegralTrapezoid", c)]
     vals, bits = device_outputs(ctx, r2, specs)
     assert torch.equal(vals[0][:W], s0 + torch.arange(W, device="cuda") * interval)
+    # the fused chain (no materialised frame) must give the same windows
+    assert_same_outputs(specs, fused_outputs(ctx, r, ops, specs), (vals, bits), W, None, "config2 fused",
+                        scale=float(interval))
     # weighted average of values in [0,1) lies in [0,1]; integral = average * interval
     for j in range(1, len(specs), 2):
         wa = vals[j][:W - 1].view(torch.float64)
@@ -210,6 +245,8 @@ def test_config3_1B_bursty_first_last_min_max_stepprevious(ctx):
     assert r2.num_windows == W
     specs = [("WindowStart", 0), ("First", 1), ("Last", 1), ("Min", 1), ("Max", 1), ("Count", 1)]
     vals, bits = device_outputs(ctx, r2, specs)
+    assert_same_outputs(specs, fused_outputs(ctx, r, ["WindowStart", "StepPrevious"], specs), (vals, bits), W, None,
+                        "config3 fused")
     # properties over all windows: Σ Count == valid rows of the interpolated frame; min <= first,last <= max
     _, vbits = fi.device_ptrs(1)
     assert vbits, "the interpolated value column must carry nulls"

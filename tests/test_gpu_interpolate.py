@@ -182,3 +182,85 @@ def test_sharded_interpolate_matches_oracle(ctx, g):
             else:
                 scale = np.maximum(np.abs(wv[wm]), 1.0)
                 assert np.all(np.abs(gv[gm] - wv[wm]) <= 1e-12 * scale * max(1, interval)), (kind, g, sp)
+
+
+ALL_AGGS = ["Count", "Sum", "ArithmeticMean", "Min", "Max", "First", "Last", "IntegralStep", "IntegralTrapezoid",
+            "WeightedAverageStep", "WeightedAverageLinear"]
+
+
+def chain_oracle(cols, interval, offset, ops, specs, prev=None):
+    ref = R.RefRolling(R.Frame(cols), 0, interval, offset=offset, prev_row=R.Frame(prev) if prev else None)
+    icols = ref.interpolate(ops)
+    icols = [(vv, None if mm.all() else mm) for vv, mm in icols]
+    return R.RefRolling(R.Frame(icols), 0, interval, offset=offset).aggregate(specs)
+
+
+def assert_chain(got, want, specs, what, interval):
+    for sp, (gv, gm), (wv, wm) in zip(specs, got, want):
+        assert gv.dtype == wv.dtype, (what, sp)
+        assert np.array_equal(gm, wm), f"{what} {sp}: validity differs at windows {np.flatnonzero(gm != wm)[:8]}"
+        a, b = gv[gm], wv[wm]
+        if sp[0] in ("Sum", "ArithmeticMean", "IntegralStep", "IntegralTrapezoid", "WeightedAverageStep", "WeightedAverageLinear"):
+            fin = np.isfinite(b)
+            scale = 1e3 * (interval if "Integral" in sp[0] else 1.0)
+            bad = np.flatnonzero(np.abs(a[fin] - b[fin]) > 1e-12 * np.maximum(np.abs(b[fin]), scale) * 64)
+            assert bad.size == 0, f"{what} {sp}: {a[fin][bad[:3]]} vs {b[fin][bad[:3]]}"
+            assert np.array_equal(np.isnan(a), np.isnan(b)), (what, sp)
+        else:
+            same = bits(a) == bits(b)
+            if a.dtype == np.float64:
+                same |= np.isnan(a) & np.isnan(b)
+            assert same.all(), f"{what} {sp}: windows {np.flatnonzero(gm)[~same][:5]} got {a[~same][:3]} want {b[~same][:3]}"
+
+
+@pytest.mark.parametrize("kind", ["regular", "sparse", "bursty", "dense"])
+@pytest.mark.parametrize("n", [1, 40, 3000, 8192, 8193, 33000, 70000])
+def test_fused_interpolate_aggregate_vs_oracle(ctx, kind, n):
+    """bowgpu_rolling_interpolate_aggregate (no materialised frame) == oracle Interpolate -> Aggregate: synthetic start
+    rows of non-empty AND empty windows, inclusive rows taken from the next window's start row, thread / tile edges"""
+    from bow_b200 import native as N
+    rng = np.random.default_rng(H.seed_of("fused", kind, n))
+    for trial in range(2):
+        interval = int(rng.choice([3, 11, 40, 700, 5000]))
+        offset = int(rng.integers(-interval, interval))
+        t = H.random_times(rng, n, kind)
+        t = t - int(t[0]) + 1000
+        cols = [(t, None), H.random_values(rng, n, np.float64, float(rng.choice([0.0, 0.3, 0.9])), specials=n < 100),
+                H.random_values(rng, n, np.int64, float(rng.choice([0.0, 0.5]))),
+                H.random_values(rng, n, np.float64, 0.2)]
+        ops = ["WindowStart", str(rng.choice(["Linear", "StepPrevious", "None_"])), str(rng.choice(["Linear", "StepPrevious"])),
+               "Linear"]
+        prev = [(np.array([995], dtype=np.int64), None), (np.array([0.5]), None), (np.array([4], dtype=np.int64), None),
+                (np.array([-1.0]), None)] if trial else None
+        specs = [("WindowStart", 0), ("Count", 0)] + [(a, c) for c in (1, 2, 3) for a in ALL_AGGS]
+        fr = N.Frame.from_numpy(ctx, cols)
+        r = N.Rolling(fr, 0, interval, offset=offset, prev_row=prev)
+        got = r.interpolate_aggregate(ops, specs)
+        want = chain_oracle(cols, interval, offset, ops, specs, prev)
+        assert_chain(got, want, specs, f"fused {kind} n={n} I={interval} off={offset} ops={ops}", interval)
+        r.close()
+        fr.close()
+
+
+def test_fused_falls_back_when_starts_are_inexact(ctx):
+    """ns timestamps beyond 2^53: a first row 123 ns after S_k passes the reference's float64 "has start" test
+    (interpolation.go:121-128) without sitting on S_k; the fused path must hand over to the materialising one"""
+    from bow_b200 import native as N
+    n, interval = 20000, 60_000_000_000
+    t = 1_700_000_000_000_000_000 + np.arange(n, dtype=np.int64) * 1_000_000_000 + 123
+    rng = np.random.default_rng(9)
+    cols = [(t, None), H.random_values(rng, n, np.float64, 0.1)]
+    ops = ["WindowStart", "Linear"]
+    specs = [("WindowStart", 0), ("Count", 1), ("WeightedAverageLinear", 1), ("Last", 1)]
+    fr = N.Frame.from_numpy(ctx, cols)
+    r = N.Rolling(fr, 0, interval)
+    got = r.interpolate_aggregate(ops, specs)
+    want = chain_oracle(cols, interval, 0, ops, specs)
+    assert_chain(got, want, specs, "inexact starts", interval)
+    # and with Options.Inclusive (duplicated inclusive rows in the interpolated frame) -> materialising chain too
+    r2 = N.Rolling(fr, 0, interval, inclusive=True)
+    got2 = r2.interpolate_aggregate(ops, specs)
+    ref = R.RefRolling(R.Frame(cols), 0, interval, inclusive=True)
+    icols = [(vv, None if mm.all() else mm) for vv, mm in ref.interpolate(ops)]
+    want2 = R.RefRolling(R.Frame(icols), 0, interval, inclusive=True).aggregate(specs)
+    assert_chain(got2, want2, specs, "inclusive", interval)
