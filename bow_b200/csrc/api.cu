@@ -1486,6 +1486,9 @@ extern "C" int32_t bowgpu_rolling_interpolate_aggregate(bowgpu_rolling *r, const
         bowgpu_rolling *r2 = nullptr;
         rc = r->shard ? bowgpu_rolling_create_shard(fi, r->time_col, r->interval, r->s0, r->W, r->inclusive, nullptr, &r2)
                       : bowgpu_rolling_create(fi, r->time_col, r->interval, r->offset, r->inclusive, nullptr, &r2);
+        if (rc == BOWGPU_OK && r2->W != r->W)  // the caller sized `outs` for the lattice of r
+            rc = fail(ctx, BOWGPU_EUNSUPPORTED, "interpolation changes the window lattice (%lld -> %lld windows): use the two-step calls",
+                      (long long)r->W, (long long)r2->W);
         if (rc == BOWGPU_OK) rc = aggregate_core(r2, specs, nspecs, outs, mem, nullptr);
         if (rc == BOWGPU_OK && mem == BOWGPU_MEM_DEVICE) rc = check_status(ctx);  // the frame is about to go
         bowgpu_rolling_destroy(r2);

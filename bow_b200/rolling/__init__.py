@@ -220,9 +220,11 @@ class Rolling:
         self._nrows = 0
         self._bounds = None
         self._handle: Optional[N.Rolling] = None
+        self._lazy = None                          # (parent Rolling, interpolation opcodes) of a pending Interpolate
 
     # -- device plumbing ----------------------------------------------------------------------------------
     def _ensure_frame(self) -> N.Frame:
+        self._materialize()
         if self.frame is None:
             from ..runtime import default_ctx
             arr, keep = _cols_from_bow(self.bow)
@@ -230,6 +232,7 @@ class Rolling:
         return self.frame
 
     def _ensure_handle(self) -> N.Rolling:
+        self._materialize()
         if self._handle is None:
             fr = self._ensure_frame()
             prev = None
@@ -246,6 +249,7 @@ class Rolling:
         return self._handle
 
     def _ensure_bow(self) -> B.Bow:
+        self._materialize()
         if self.bow is None:
             cols = self.frame.download()
             series = [B.NewSeriesFromNumpy(n, v, m) for n, (v, m) in zip(self.names, cols)]
@@ -284,6 +288,7 @@ class Rolling:
         return self._bounds
 
     def HasNext(self) -> bool:  # rolling.go:162-173
+        self._materialize()
         return self._nrows > 0 and self.currWindowIndex < self.numWindows
 
     def Next(self):  # rolling.go:177-239 -> (windowIndex, Window | None)
@@ -360,7 +365,11 @@ class Rolling:
         self._handle = None
         self._bounds = None
         try:
-            res = self._ensure_handle().aggregate(specs)
+            if self._lazy is not None and self.currWindowIndex == 0:
+                parent, ops = self._lazy   # Aggregate right after Interpolate: fused, nothing is materialised
+                res = parent._ensure_handle().interpolate_aggregate(ops, specs)
+            else:
+                res = self._ensure_handle().aggregate(specs)
         except N.BowGpuError as e:
             raise _gpu_error(e)
         series = []
@@ -432,16 +441,27 @@ class Rolling:
             if it._kernel_op is None:
                 raise BowError(f"interpolation {i}: custom closures are not supported by the GPU backend")
             ops.append(it._kernel_op)
-        try:
-            frame = self._ensure_handle().interpolate(ops)
-        except N.BowGpuError as e:
-            raise _gpu_error(e)
         r = Rolling()
-        r.frame = frame
         r.names, r.types, r.metadata = list(self.names), list(self.types), self.metadata
         r.intervalColIndex = self.intervalColIndex
         r.interval = self.interval
         r.options = copy.copy(self.options)
+        # Lazy: when Aggregate follows directly, the interpolated frame is never materialised
+        # (bowgpu_rolling_interpolate_aggregate).  Only taken when the host can tell that the interpolated frame keeps
+        # the window lattice: no user Inclusive, first row not before the first window start, at least one window.
+        first_time = self._first_time()
+        if (not self.options.Inclusive and self.numWindows > 0 and first_time is not None
+                and self.currWindowFirstValue <= first_time and self.currWindowIndex == 0):
+            r._lazy = (self, ops)
+            r.numWindows = self.numWindows
+            r.currWindowFirstValue = self.currWindowFirstValue
+            r._nrows = -1
+            return r
+        try:
+            frame = self._ensure_handle().interpolate(ops)
+        except N.BowGpuError as e:
+            raise _gpu_error(e)
+        r.frame = frame
         r._nrows = frame.num_rows
         if r._nrows == 0:  # interpolation.go:59-61
             r.numWindows = 0
@@ -454,6 +474,23 @@ class Rolling:
         r.numWindows = h.num_windows
         r.currWindowFirstValue = h.first_window_start
         return r
+
+    def _first_time(self):
+        if self.bow is None or self.bow.NumRows() == 0:
+            return None
+        return self.bow.Column(self.intervalColIndex)[0].as_py()
+
+    def _materialize(self):
+        """runs the pending Interpolate of a lazy Rolling (the interpolated frame was asked for after all)"""
+        if self._lazy is None:
+            return
+        parent, ops = self._lazy
+        self._lazy = None
+        try:
+            self.frame = parent._ensure_handle().interpolate(ops)
+        except N.BowGpuError as e:
+            raise _gpu_error(e)
+        self._nrows = self.frame.num_rows
 
 
 def _new_interval_rolling(b: B.Bow, intervalColIndex: int, interval: int, options: Options) -> Rolling:

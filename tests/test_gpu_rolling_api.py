@@ -124,8 +124,13 @@ def test_chain_interpolate_aggregate_stays_on_device():
     assert ri.bow is None and ri.NumWindows() == 5
     out = ri.Aggregate(aggregation.WindowStart(G.TIME), aggregation.WeightedAverageLinear(G.VALUE),
                        aggregation.Count(G.VALUE).RenameOutput("n")).Bow()
-    assert ri.bow is None
+    assert ri.bow is None and ri.frame is None     # fused: the interpolated frame was not even materialised
     assert out.ToColBased()[0] == [10, 15, 20, 25, 30] and out.ToColBased()[2] == [1, 2, 2, 1, 2]
+    # asking for the interpolated Bow afterwards materialises it (and a second Aggregate runs on that frame)
+    assert ri.Bow().NumRows() == 8 and ri.frame is not None
+    out2 = ri.Aggregate(aggregation.WindowStart(G.TIME), aggregation.WeightedAverageLinear(G.VALUE),
+                        aggregation.Count(G.VALUE).RenameOutput("n")).Bow()
+    assert out2.Equal(out)
     # cross-check with the oracle on the same chain
     cols = [(np.array([10, 15, 17, 23, 31], dtype=np.int64), None), (np.array([10.0, 15.0, 17.0, 11.0, 0.5]), None)]
     ic = R.RefRolling(R.Frame(cols), 0, 5).interpolate(["WindowStart", "Linear"])
