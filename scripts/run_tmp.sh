@@ -1,5 +1,18 @@
-for l2 in 0 1 2 3; do echo -n "L2promo=$l2: "; BOWGPU_TMAP_L2=$l2 python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('ms_step %.4f  kernel_ms %.4f  GB/s %.0f' % (d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['achieved']))"; done
-ncu --set full --clock-control none --import-source on -k regex:segreduce_kernel -s 3 -c 1 -o gpurun_out/prof_seg_r1o python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > /dev/null 2>&1
+python - <<'PY'
+import sys, time, os
+sys.path.insert(0, '.')
+from bow_b200 import native as N
+ctx = N.Ctx(0)
+n = 1_000_000_000
+fr = N.Frame.generate(ctx, n, ncols=1, seed=7, null_mask=1, null_mod=10)
+r = N.Rolling(fr, 0, 900_000_000_000, offset=420_000_000_000)
+for _ in range(2): r.bounds()
+ctx.synchronize()
+ctx.enable_timing(1)
+t0 = time.perf_counter()
+for _ in range(5): r.bounds()
+ctx.synchronize()
+dt = (time.perf_counter() - t0) / 5
+tm = ctx.last_timing()
+print("bounds v1=%s: wall %.3f ms per call, kernel main_ms %.3f total_ms %.3f" % (os.environ.get("BOWGPU_BOUNDS_V1"), dt * 1e3, tm.main_ms, tm.total_ms))
+PY
