@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(EPI_NT) epilogue_group_kernel(const __grid_con
 #pragma unroll
         for (int i = 0; i < EPI_WPT; ++i) {
             const int64_t k = base + lane + 32 * i;
-            sv[j][i] = (j < G.n_div && k < g.W && c[i] > 0) ? G.div_src[j][k] : 0.0;
+            sv[j][i] = (j < G.n_div && k < g.W) ? G.div_src[j][k] : 0.0;  // (independent of the count load: both in flight)
         }
     // float64(w.LastValue - w.FirstValue), weightedmean.go:17,31 (the interval, except for the whole-Bow window)
     const double width = g.whole ? (double)(g.whole_last - g.whole_first) : (double)(int64_t)g.div.d;
