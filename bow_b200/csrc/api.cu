@@ -1495,7 +1495,8 @@ extern "C" int32_t bowgpu_rolling_interpolate_aggregate(bowgpu_rolling *r, const
         bowgpu_frame_destroy(fi);
         return rc;
     };
-    if (r->inclusive || r->early_rows > 0 || r->shard || r->W == 0 || f->n == 0) return unfused();
+    // (on a shard the rows before s0 are the left halo; elsewhere they are the negative-timestamp quirk of window 0)
+    if (r->inclusive || (r->early_rows > 0 && !r->shard) || r->W == 0 || f->n == 0) return unfused();
     // validation of the interpolations: same rules as bowgpu_rolling_interpolate
     if (nops != ncols)
         return fail(ctx, BOWGPU_EINVAL, "interpolations must name every column in schema order (%d given, %d columns)", nops, ncols);
@@ -1507,9 +1508,12 @@ extern "C" int32_t bowgpu_rolling_interpolate_aggregate(bowgpu_rolling *r, const
     }
     if (ops[r->time_col] != BOWGPU_INTERP_WINDOW_START) return unfused();  // the frame's time column must carry S_k
     const WindowGeom g = make_geom(r, false);
-    const int64_t W = g.W;
+    // a shard also interpolates the start row of the window after its last one (the inclusive row of that last window)
+    WindowGeom gx = g;
+    gx.W = g.W + (r->shard ? 1 : 0);
+    const int64_t W = gx.W;
     // per-window arrays live in pool blocks: the aggregation core re-uses the arena
-    const size_t wv = align_up((size_t)(W + 1) * 8, 256), wb = align_up((size_t)W + 16, 256);
+    const size_t wv = align_up((size_t)(W + 2) * 8, 256), wb = align_up((size_t)W + 16, 256);
     uint8_t *blk = nullptr;
     const size_t total = wv + wb + (size_t)ncols * (wv + wb);
     if (pool_alloc(ctx, (void **)&blk, total) != cudaSuccess) return fail(ctx, BOWGPU_ENOMEM, "fused interpolate: scratch");
@@ -1524,7 +1528,7 @@ extern "C" int32_t bowgpu_rolling_interpolate_aggregate(bowgpu_rolling *r, const
     L.first = d_first;
     L.missing = blk + wv;
     L.status = ctx->d_status;
-    L.g = g;
+    L.g = gx;
     L.inclusive = 0;
     L.ncols = ncols;
     if (r->has_prev) {
@@ -1549,12 +1553,13 @@ extern "C" int32_t bowgpu_rolling_interpolate_aggregate(bowgpu_rolling *r, const
         syn[j].missing = L.missing;
         syn[j].val = c.syn_val;
         syn[j].ok = c.syn_ok;
+        syn[j].len = W;
     }
     // synthetic rows of windows that have a start row are never read, but keep the arrays defined
     if (cudaMemsetAsync(blk + wv, 0, total - wv, ctx->stream) != cudaSuccess) return bail(fail(ctx, BOWGPU_ECUDA, "memset"));
     BoundsLaunch B;
     B.time = L.time;
-    B.g = g;
+    B.g = gx;
     B.first = d_first;
     B.status = ctx->d_status;
     int e = launch_bounds(B, ctx->sm_count, ctx->stream, nullptr, nullptr);

@@ -64,6 +64,7 @@ struct FusedSyn {
     const uint8_t *missing;  // [W] 1 = the interpolated frame holds a synthetic row at S_k (null = not fused)
     const uint64_t *val;     // [W] its value in this column (raw bits)
     const uint8_t *ok;       // [W] its validity
+    int64_t len;             // entries in the three arrays: W, or W + 1 on a shard (start row of the next shard's window)
 };
 
 struct SegLaunch {

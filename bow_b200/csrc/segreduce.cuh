@@ -128,17 +128,22 @@ __device__ __forceinline__ typename Pol::Inc fused_boundary(const SegArgs<Pol> &
     const WindowGeom &g = A.g;
     const FusedSyn &S = A.syn;
     fresh = Pol::identity();
-    if (!has_row) return Pol::make_inc(false, false, 0, 0);  // the column ends: no window after kcur
+    // the column ends (no window after kcur), or kcur is a halo window of a shard (not owned: nothing to produce)
+    if (!has_row || kcur >= (uint64_t)g.W) return Pol::make_inc(false, false, 0, 0);
     const uint64_t d = g.div.d;
+    const uint64_t len = (uint64_t)S.len;
     auto start_of = [&](uint64_t k) { return (int64_t)((uint64_t)g.s0 + k * d); };
     auto real_inc = [&](uint64_t k) {  // the real row as inclusive row of window k (only if it sits exactly on E_k)
         return Pol::make_inc(x == start_of(k + 1), valid, raw, x);
     };
-    auto syn_inc = [&](uint64_t k) { return Pol::make_inc(true, S.ok[k] != 0, S.val[k], start_of(k)); };
-    const bool miss_new = S.missing[knew] != 0;
+    auto syn_inc = [&](uint64_t k) {
+        return k < len ? Pol::make_inc(true, S.ok[k] != 0, S.val[k], start_of(k)) : Pol::make_inc(false, false, 0, 0);
+    };
+    const bool miss_new = knew < len && S.missing[knew] != 0;
     const uint64_t kn = kcur + 1;
     const Inc inc = (knew == kn && !miss_new) ? real_inc(kcur) : syn_inc(kn);
-    for (uint64_t m = kn; m < knew; ++m) {  // empty windows: one synthetic row each (interpolation.go:83-100 golden)
+    const uint64_t kend = knew < (uint64_t)g.W ? knew : (uint64_t)g.W;  // only owned windows are written
+    for (uint64_t m = kn; m < kend; ++m) {  // empty windows: one synthetic row each (interpolation.go:83-100 golden)
         typename Pol::State sm = Pol::identity();
         Pol::inject(sm, start_of(m), S.val[m], S.ok[m] != 0);
         const Inc im = (m + 1 < knew || miss_new) ? syn_inc(m + 1) : real_inc(m);
@@ -570,7 +575,7 @@ __global__ void seg_fixup_kernel(const __grid_constant__ SegArgs<Pol> A, const i
     if (starts) {
         if (FUSED) {  // the window begins at the tile's first row: its synthetic start row comes first
             const int64_t k = Pol::carry_key(hd);
-            if (A.syn.missing[k])
+            if (k < A.syn.len && A.syn.missing[k])
                 Pol::carry_prepend_point(hd, (int64_t)((uint64_t)g.s0 + (uint64_t)k * g.div.d), A.syn.val[k], A.syn.ok[k] != 0);
         }
         if (Pol::carry_closed(hd))

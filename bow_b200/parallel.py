@@ -172,3 +172,30 @@ def concat_frames(per_shard: Sequence[Tuple[List[NpCol], int]]) -> List[NpCol]:
     ncols = len(per_shard[0][0])
     return [(np.concatenate([o[j][0][:own] for o, own in per_shard]),
              np.concatenate([o[j][1][:own] for o, own in per_shard])) for j in range(ncols)]
+
+
+def gpu_interpolate_aggregate_executor(cols: Sequence[NpCol], time_col: int, interval: int, s0: int, num_windows: int,
+                                       ops: Sequence, specs: Sequence[tuple],
+                                       prev_row: Optional[Sequence[NpCol]]) -> Outputs:
+    """Fused Interpolate -> Aggregate of the windows [0, num_windows) of the lattice starting at s0 on this process'
+    GPU (bowgpu_rolling_interpolate_aggregate): rows before s0 are the left halo, rows after the last window the right
+    halo; the interpolated frame is never materialised."""
+    from . import native as N
+    from .runtime import default_ctx
+    fr = N.Frame.from_numpy(default_ctx(), cols)
+    r = N.Rolling(fr, time_col, interval, prev_row=prev_row, shard=(s0, num_windows))
+    try:
+        return r.interpolate_aggregate(ops, specs)
+    finally:
+        r.close()
+        fr.close()
+
+
+def interpolate_aggregate_shard(cols: Sequence[NpCol], shard: P.Shard, time_col: int, interval: int, s0_global: int,
+                                ops: Sequence, specs: Sequence[tuple], prev_row: Optional[Sequence[NpCol]] = None,
+                                executor=gpu_interpolate_aggregate_executor) -> Outputs:
+    """Rolling.Interpolate(ops).Aggregate(specs) of the windows owned by `shard` (a `plan_interpolate` shard: left halo,
+    one extra window and right halo are shipped).  Per-shard outputs concatenate to the global result."""
+    nloc = shard.halo_hi - shard.first_row
+    local = cols if len(cols[0][0]) == nloc else slice_cols(cols, shard.first_row, shard.halo_hi)
+    return executor(local, time_col, interval, s0_global + shard.k_lo * interval, shard.num_windows, ops, specs, prev_row)

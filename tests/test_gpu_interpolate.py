@@ -174,6 +174,16 @@ def test_sharded_interpolate_matches_oracle(ctx, g):
             for o in (r2, fi, r, fr):
                 o.close()
         got_agg = PP.concat_outputs(outs)
+        # the fused per-shard chain (no materialised frame) must agree with the materialising one and the oracle
+        fused = PP.concat_outputs([PP.interpolate_aggregate_shard(cols, s, 0, interval, s0, ops, specs, prev)
+                                   for s in shards if s.num_windows])
+        for sp, (fv, fm), (gv, gm) in zip(specs, fused, got_agg):
+            assert np.array_equal(fm, gm), (kind, g, sp, "fused validity")
+            if gv.dtype == np.int64 or sp[0] in ("Last", "First", "Min", "Max"):
+                assert np.array_equal(bits(fv[fm]), bits(gv[gm])), (kind, g, sp, "fused values")
+            else:
+                sc = np.maximum(np.abs(gv[gm]), 1.0)
+                assert np.all(np.abs(fv[fm] - gv[gm]) <= 1e-12 * sc * max(1, interval)), (kind, g, sp, "fused values")
         for j, sp in enumerate(specs):
             (gv, gm), (wv, wm) = got_agg[j], want_agg[j]
             assert np.array_equal(gm, wm), (kind, g, sp)
