@@ -193,6 +193,24 @@ class Bow:
             if self.ColumnType(c) not in (Type.Int64, Type.Float64):
                 raise BowError(f"column '{self.ColumnName(c)}': only Int64 / Float64 columns run on the GPU backend")
 
+    def DropNils(self, *colIndices: int) -> "Bow":  # bow.go:188-224
+        self._check_fill_types(colIndices, False)
+        return self._gpu_fill(lambda f: f.drop_nils(*colIndices))
+
+    def IsColSorted(self, colIndex: int) -> bool:  # bowassertion.go:15-81
+        from . import native as N
+        from .rolling import _cols_from_bow
+        from .runtime import default_ctx
+        if self.ColumnType(colIndex) not in (Type.Int64, Type.Float64):
+            return False
+        self._check_fill_types((), False)
+        arr, keep = _cols_from_bow(self)
+        frame = N.Frame.from_col_descs(default_ctx(), arr, self.NumCols(), N.MEM_HOST, keep)
+        try:
+            return frame.is_col_sorted(colIndex)
+        finally:
+            frame.close()
+
     def FillPrevious(self, *colIndices: int) -> "Bow":  # bowfill.go:160-164
         self._check_fill_types(colIndices, False)
         return self._gpu_fill(lambda f: f.fill("Previous", *colIndices))

@@ -832,6 +832,110 @@ extern "C" int32_t bowgpu_frame_fill_linear(bowgpu_frame *frame, int32_t ref_col
     return BOWGPU_OK;
 }
 
+// Bow.DropNils(colIndices...) (bow.go:188-224): drops every row holding a nil in one of the selected columns (all
+// columns when none is given).  Stream compaction on the device; the result is a new frame.
+extern "C" int32_t bowgpu_frame_drop_nils(bowgpu_frame *frame, const int32_t *cols, int32_t ncols, bowgpu_frame **out) {
+    if (!frame || !out || ncols < 0 || (ncols > 0 && !cols)) return BOWGPU_EINVAL;
+    *out = nullptr;
+    bowgpu_ctx *ctx = frame->ctx;
+    Guard gd(ctx);
+    const int nc = (int)frame->cols.size();
+    if (nc > 32) return fail(ctx, BOWGPU_EUNSUPPORTED, "DropNils supports at most 32 columns");
+    std::vector<char> sel(nc, ncols == 0 ? 1 : 0);  // selectCols, bowfill.go:266-288
+    for (int i = 0; i < ncols; ++i) {
+        if (cols[i] < 0 || cols[i] > nc - 1) return fail(ctx, BOWGPU_EINVAL, "selectCols: colIndex '%d' out of range", cols[i]);
+        sel[cols[i]] = 1;
+    }
+    const int64_t n = frame->n;
+    bowgpu_frame *of = new (std::nothrow) bowgpu_frame();
+    if (!of) return BOWGPU_ENOMEM;
+    of->ctx = ctx;
+    of->cols.resize(nc);
+    auto bail = [&](int32_t code) {
+        cudaStreamSynchronize(ctx->stream);
+        for (auto &c : of->cols) free_col(ctx, c);
+        delete of;
+        return code;
+    };
+    bool any = false;
+    for (int c = 0; c < nc; ++c) any |= sel[c] && frame->cols[c].validity && frame->cols[c].null_count != 0;
+    int32_t rc = BOWGPU_OK;
+    if (!any || n == 0) {  // bow.go:209-211: nothing to drop
+        of->n = n;
+        for (int c = 0; c < nc && rc == BOWGPU_OK; ++c) rc = clone_col(ctx, of->cols[c], frame->cols[c], n);
+        if (rc == BOWGPU_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, BOWGPU_ECUDA, "DropNils copy");
+        if (rc) return bail(rc);
+        *out = of;
+        return BOWGPU_OK;
+    }
+    DropLaunch L;
+    memset(&L, 0, sizeof L);
+    L.ncols = nc;
+    L.n = n;
+    for (int c = 0; c < nc; ++c) {
+        L.values[c] = frame->cols[c].values;
+        L.validity[c] = frame->cols[c].validity;
+        L.selected[c] = sel[c];
+    }
+    void *scratch = nullptr;
+    if (pool_alloc(ctx, &scratch, drop_scratch_bytes(n)) != cudaSuccess) return bail(fail(ctx, BOWGPU_ENOMEM, "DropNils scratch"));
+    timing_begin(ctx);
+    int64_t *d_total = nullptr, total = 0;
+    int e = launch_drop_mark(L, scratch, ctx->stream, &d_total);
+    if (e || cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        pool_free(ctx, scratch);
+        return bail(fail(ctx, BOWGPU_ECUDA, "DropNils (mark): %s", cudaGetErrorString(cudaGetLastError())));
+    }
+    of->n = total;
+    for (int c = 0; c < nc && rc == BOWGPU_OK; ++c) {
+        const DevCol &src = frame->cols[c];
+        const bool keeps_nulls = !sel[c] && src.validity && src.null_count != 0;
+        rc = alloc_col(ctx, of->cols[c], total, src.dtype, keeps_nulls);  // (bitmaps come zero-initialised)
+        L.out_values[c] = of->cols[c].values;
+        L.out_validity[c] = of->cols[c].validity;
+        if (!keeps_nulls) L.validity[c] = nullptr;
+    }
+    if (rc == BOWGPU_OK && total > 0) {
+        e = launch_drop_compact(L, scratch, ctx->stream);
+        if (e) rc = fail(ctx, BOWGPU_ECUDA, "DropNils (compact): %s", cudaGetErrorString((cudaError_t)e));
+    }
+    count_launch(ctx, 6);
+    timing_end(ctx);
+    pool_free(ctx, scratch);
+    for (int c = 0; c < nc && rc == BOWGPU_OK; ++c)
+        if (of->cols[c].validity) rc = count_nulls(ctx, of->cols[c], total);
+    if (rc == BOWGPU_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, BOWGPU_ECUDA, "DropNils");
+    if (rc) return bail(rc);
+    *out = of;
+    return BOWGPU_OK;
+}
+
+// Bow.IsColSorted(colIndex) (bowassertion.go:15-81): ascending or descending over the non-nil values; an empty column
+// is not sorted.
+extern "C" int32_t bowgpu_frame_is_col_sorted(bowgpu_frame *frame, int32_t col, int32_t *sorted) {
+    if (!frame || !sorted) return BOWGPU_EINVAL;
+    bowgpu_ctx *ctx = frame->ctx;
+    Guard gd(ctx);
+    if (col < 0 || col >= (int)frame->cols.size()) return fail(ctx, BOWGPU_EINVAL, "no column %d", col);
+    const DevCol &c = frame->cols[col];
+    const int64_t n = frame->n;
+    *sorted = 0;
+    if (n == 0 || (c.validity && c.null_count == n)) return BOWGPU_OK;  // IsColEmpty
+    int32_t rc = arena_reserve(ctx, fill_scratch_bytes(n) + 1024);
+    if (rc) return rc;
+    arena_reset(ctx);
+    int64_t *scratch = (int64_t *)arena_take(ctx, fill_scratch_bytes(n));
+    int32_t *d_flags = (int32_t *)arena_take(ctx, 16);
+    CK(cudaMemsetAsync(d_flags, 0, 16, ctx->stream));
+    CK(launch_sorted_flags(c.values, c.validity, c.dtype == BOWGPU_INT64, n, scratch, d_flags, ctx->stream));
+    int32_t h = 0;
+    CK(cudaMemcpyAsync(&h, d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *sorted = h != 3;
+    return BOWGPU_OK;
+}
+
 // ================================================================================================
 // rolling
 // ================================================================================================

@@ -14,6 +14,8 @@
 // Algorithmic bytes: 16 B/row (read + write values) + bitmaps; HBM bound.
 #include <math_constants.h>
 
+#include <cstring>
+
 #include "../../include/bowgpu.h"
 #include "kernels.h"
 
@@ -263,7 +265,121 @@ __global__ void __launch_bounds__(FILL_NT) sorted_flags_kernel(const uint64_t *v
     if (lane == 0 && f) atomicOr(flags, f);
 }
 
+// ---- DropNils (bow.go:188-224): stream compaction of the rows that are valid in every selected column ----------
+constexpr int DROP_MAX_COLS = 32;
+struct DropArgs {
+    const uint32_t *sel_bm[DROP_MAX_COLS];  // validity of the selected columns that have nulls
+    int32_t nsel;
+    int32_t ncols;
+    const uint64_t *values[DROP_MAX_COLS];
+    const uint32_t *bm[DROP_MAX_COLS];      // input validity of columns whose nulls SURVIVE (not selected), else null
+    uint64_t *out_values[DROP_MAX_COLS];
+    uint32_t *out_bm[DROP_MAX_COLS];        // zero-initialised, or null
+    uint32_t *keep;                          // [words] rows kept
+    int64_t *blk;                            // [nblocks + 1] kept rows per block, scanned in place
+    int64_t n;
+};
+
+__global__ void __launch_bounds__(FILL_NT) drop_mark_kernel(const DropArgs A) {
+    __shared__ int64_t sh[32];
+    const int64_t w = (int64_t)blockIdx.x * FILL_NT + threadIdx.x;
+    uint32_t keep = load_word(nullptr, w, A.n);  // all rows that exist
+    for (int j = 0; j < A.nsel; ++j) keep &= load_word(A.sel_bm[j], w, A.n);
+    if (w * 32 < A.n) A.keep[w] = keep;
+    int64_t c = __popc(keep);
+    for (int o = 16; o; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int64_t t = 0;
+        for (int i = 0; i < FILL_NT / 32; ++i) t += sh[i];
+        A.blk[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(FILL_NT) drop_compact_kernel(const DropArgs A) {
+    __shared__ uint32_t s_word[FILL_NT];
+    __shared__ int32_t s_off[FILL_NT];
+    __shared__ int32_t s_warp[FILL_NT / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t w = (int64_t)blockIdx.x * FILL_NT + tid;
+    const uint32_t word = w * 32 < A.n ? A.keep[w] : 0u;
+    s_word[tid] = word;
+    int c = __popc(word), incl = c;  // exclusive prefix of the popcounts inside the block
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int base = 0;
+    for (int i = 0; i < warp; ++i) base += s_warp[i];
+    s_off[tid] = base + incl - c;
+    __syncthreads();
+    const int64_t blk_base = A.blk[blockIdx.x];
+    for (int k = 0; k < 32; ++k) {
+        const int wi = warp * 32 + k;
+        const int64_t wg = (int64_t)blockIdx.x * FILL_NT + wi;
+        if (wg * 32 >= A.n) break;
+        const uint32_t wd = s_word[wi];
+        if (!((wd >> lane) & 1u)) continue;
+        const int64_t row = wg * 32 + lane;
+        const int64_t dst = blk_base + s_off[wi] + __popc(wd & ((1u << lane) - 1u));
+        for (int j = 0; j < A.ncols; ++j) {
+            A.out_values[j][dst] = A.values[j][row];
+            if (A.out_bm[j] && ((A.bm[j][row >> 5] >> (row & 31)) & 1u)) atomicOr(&A.out_bm[j][dst >> 5], 1u << (dst & 31));
+        }
+    }
+}
+
 }  // namespace
+
+size_t drop_scratch_bytes(int64_t n) {
+    const int64_t nb = (n + FILL_ROWS - 1) / FILL_ROWS, words = (n + 31) / 32;
+    return (size_t)words * 4 + 256 + (size_t)(nb + 2) * 8 + scan_scratch_bytes(nb) + 256;
+}
+
+// pass 1: keep mask + per-block counts scanned in place; *d_total (device int64) = rows kept
+int launch_drop_mark(const DropLaunch &L, void *scratch, cudaStream_t stream, int64_t **d_total) {
+    const int64_t nb = (L.n + FILL_ROWS - 1) / FILL_ROWS, words = (L.n + 31) / 32;
+    if (L.n <= 0 || L.ncols > DROP_MAX_COLS) return (int)cudaErrorInvalidValue;
+    DropArgs A;
+    memset(&A, 0, sizeof A);
+    uint8_t *p = (uint8_t *)scratch;
+    A.keep = (uint32_t *)p;
+    p += ((size_t)words * 4 + 255) / 256 * 256;
+    A.blk = (int64_t *)p;
+    p += (size_t)(nb + 2) * 8;
+    int64_t *scan_tmp = (int64_t *)(((uintptr_t)p + 255) / 256 * 256);
+    A.n = L.n;
+    for (int j = 0; j < L.ncols; ++j)
+        if (L.selected[j] && L.validity[j]) A.sel_bm[A.nsel++] = (const uint32_t *)L.validity[j];
+    drop_mark_kernel<<<(unsigned)nb, FILL_NT, 0, stream>>>(A);
+    int e = launch_exclusive_scan(A.blk, nb, scan_tmp, stream);
+    *d_total = A.blk + nb;
+    return e ? e : (int)cudaGetLastError();
+}
+
+// pass 2: compaction into the output columns (out_validity[j] zero-initialised, or null when the column cannot hold nulls)
+int launch_drop_compact(const DropLaunch &L, void *scratch, cudaStream_t stream) {
+    const int64_t nb = (L.n + FILL_ROWS - 1) / FILL_ROWS, words = (L.n + 31) / 32;
+    DropArgs A;
+    memset(&A, 0, sizeof A);
+    uint8_t *p = (uint8_t *)scratch;
+    A.keep = (uint32_t *)p;
+    p += ((size_t)words * 4 + 255) / 256 * 256;
+    A.blk = (int64_t *)p;
+    A.n = L.n;
+    A.ncols = L.ncols;
+    for (int j = 0; j < L.ncols; ++j) {
+        A.values[j] = L.values[j];
+        A.out_values[j] = L.out_values[j];
+        A.out_bm[j] = (uint32_t *)L.out_validity[j];
+        A.bm[j] = (const uint32_t *)L.validity[j];
+    }
+    drop_compact_kernel<<<(unsigned)nb, FILL_NT, 0, stream>>>(A);
+    return (int)cudaGetLastError();
+}
 
 size_t fill_scratch_bytes(int64_t n) {
     const int64_t nb = (n + FILL_ROWS - 1) / FILL_ROWS;

@@ -219,6 +219,21 @@ int launch_fill(int method, const FillLaunch &L, int64_t *scratch, cudaStream_t 
 int launch_sorted_flags(const uint64_t *values, const uint8_t *validity, int is_int, int64_t n, int64_t *scratch,
                         int32_t *flags, cudaStream_t stream);
 
+// ---- DropNils (fill.cu): bow.go:188-224 ----------------------------------------------------------------------------------
+struct DropLaunch {
+    int32_t ncols;
+    int32_t _pad;
+    int64_t n;
+    const uint64_t *values[32];
+    const uint8_t *validity[32];  // input bitmaps (null = no nulls)
+    uint8_t selected[32];         // rows with a null in a selected column are dropped
+    uint64_t *out_values[32];     // (second pass)
+    uint8_t *out_validity[32];    // zero-initialised bitmaps of the columns whose nulls survive, else null
+};
+size_t drop_scratch_bytes(int64_t n);
+int launch_drop_mark(const DropLaunch &L, void *scratch, cudaStream_t stream, int64_t **d_total);
+int launch_drop_compact(const DropLaunch &L, void *scratch, cudaStream_t stream);
+
 // ---- synthetic generators (generate.cu) ----------------------------------------------------------
 int launch_gen_regular(int64_t *time, int64_t n, int64_t row0, int64_t t0, int64_t step, cudaStream_t stream);
 // BURSTY: per-window row counts (to be scanned in place with launch_exclusive_scan) and the time column

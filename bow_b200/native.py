@@ -37,7 +37,7 @@ SYMBOLS = [
     "bowgpu_rolling_first_window_start", "bowgpu_rolling_inclusive", "bowgpu_rolling_early_rows",
     "bowgpu_rolling_bounds", "bowgpu_rolling_aggregate", "bowgpu_agg_return_type", "bowgpu_agg_needs_inclusive",
     "bowgpu_rolling_interpolate", "bowgpu_frame_aggregate_whole", "bowgpu_frame_fill", "bowgpu_frame_fill_linear",
-    "bowgpu_rolling_interpolate_aggregate",
+    "bowgpu_rolling_interpolate_aggregate", "bowgpu_frame_drop_nils", "bowgpu_frame_is_col_sorted",
 ]
 
 
@@ -108,6 +108,8 @@ def lib():
                                                C.c_int32]
         L.bowgpu_rolling_interpolate_aggregate.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.POINTER(AggSpec),
                                                            C.c_int32, C.POINTER(OutCol), C.c_int32]
+        L.bowgpu_frame_drop_nils.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p)]
+        L.bowgpu_frame_is_col_sorted.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
         L.bowgpu_frame_fill.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p)]
         L.bowgpu_frame_fill_linear.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
         L.bowgpu_frame_aggregate_whole.argtypes = [C.c_void_p, C.c_int32, C.POINTER(AggSpec), C.c_int32, C.POINTER(OutCol),
@@ -282,6 +284,19 @@ class Frame:
         h = C.c_void_p()
         self.ctx.check(lib().bowgpu_frame_fill(self.h, m, arr, len(cols), C.byref(h)))
         return Frame(self.ctx, h)
+
+    def drop_nils(self, *cols: int) -> "Frame":
+        """Bow.DropNils (bow.go:188-224); no column index = any column"""
+        arr = (C.c_int32 * max(1, len(cols)))(*cols)
+        h = C.c_void_p()
+        self.ctx.check(lib().bowgpu_frame_drop_nils(self.h, arr, len(cols), C.byref(h)))
+        return Frame(self.ctx, h)
+
+    def is_col_sorted(self, col: int) -> bool:
+        """Bow.IsColSorted (bowassertion.go:15-81)"""
+        out = C.c_int32()
+        self.ctx.check(lib().bowgpu_frame_is_col_sorted(self.h, col, C.byref(out)))
+        return bool(out.value)
 
     def fill_linear(self, ref_col: int, tofill_col: int) -> "Frame":
         """Bow.FillLinear (bowfill.go:14-102)"""

@@ -241,6 +241,13 @@ int32_t bowgpu_frame_fill(bowgpu_frame *frame, int32_t method, const int32_t *co
  * without nulls returns a copy. */
 int32_t bowgpu_frame_fill_linear(bowgpu_frame *frame, int32_t ref_col, int32_t tofill_col, bowgpu_frame **out);
 
+/* Bow.DropNils(colIndices...) (bow.go:188-224): drops every row holding a nil in one of cols[0..ncols) (ncols == 0:
+ * any column).  What a caller does to a time column with nils before handing it to the rolling path. */
+int32_t bowgpu_frame_drop_nils(bowgpu_frame *frame, const int32_t *cols, int32_t ncols, bowgpu_frame **out);
+/* Bow.IsColSorted(colIndex) (bowassertion.go:15-81): *sorted = 1 iff the non-nil values are ascending or descending
+ * (ties allowed); 0 for an empty column. */
+int32_t bowgpu_frame_is_col_sorted(bowgpu_frame *frame, int32_t col, int32_t *sorted);
+
 /* Rolling.Interpolate (interpolation.go:30-161).  ops[j] is the interpolation of column j (the
  * reference matches columns by position, bowappend.go:28-47, so nops must equal the number of
  * columns).  The result is a new device-resident frame with n_out rows. */

@@ -912,3 +912,10 @@ def fill_linear(b: Frame, ref: int, to_fill: int) -> Frame:     # bowfill.go:14-
         col[r] = f64_to_i64(go_round(tmp)) if is_int else tmp
     cols = [[b.get_value(c, r) for r in range(b.num_rows())] if c != to_fill else col for c in range(b.num_cols())]
     return Frame(list(b.names), list(b.types), cols)
+
+
+def drop_nils(b: Frame, *col_indices: int) -> Frame:       # bow.go:188-224
+    sel = _select_cols(b, col_indices)
+    keep = [r for r in range(b.num_rows())
+            if not any(sel[c] and b.get_value(c, r) is None for c in range(b.num_cols()))]
+    return Frame(list(b.names), list(b.types), [[b.get_value(c, r) for r in keep] for c in range(b.num_cols())])

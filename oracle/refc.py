@@ -224,3 +224,27 @@ def fill(frame: Frame, method, col: int, ref_col: int = -1):
         raise RefError(rc)
     vals = v[:n] if frame.dtypes[col] == INT64 else v[:n].view(np.float64)
     return vals, unpack_bits(b, n)
+
+
+# ---- numpy restatements (byte / index work, no C needed) ------------------------------------------------------------
+def drop_nils(cols, selected=None):
+    """Bow.DropNils (bow.go:188-224): rows with a nil in a selected column (default: any column) are dropped.
+    cols: list of (values, mask | None) -> same layout"""
+    n = len(cols[0][0]) if cols else 0
+    keep = np.ones(n, dtype=bool)
+    for j, (_, m) in enumerate(cols):
+        if (selected is None or len(selected) == 0 or j in selected) and m is not None:
+            keep &= np.asarray(m, dtype=bool)
+    return [(np.asarray(v)[keep], np.ones(int(keep.sum()), dtype=bool) if m is None else np.asarray(m, dtype=bool)[keep])
+            for v, m in cols]
+
+
+def is_col_sorted(values, mask=None) -> bool:
+    """Bow.IsColSorted (bowassertion.go:15-81): nil values skipped, ascending or descending, empty column -> False"""
+    v = np.asarray(values)
+    if mask is not None:
+        v = v[np.asarray(mask, dtype=bool)]
+    if len(v) == 0:
+        return False
+    lt, gt = bool((v[1:] < v[:-1]).any()), bool((v[1:] > v[:-1]).any())
+    return not (lt and gt)

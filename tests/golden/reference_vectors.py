@@ -312,3 +312,19 @@ FILL_CASES = [
       [-2, 1, N, N, -8]], "bowfill_test.go:176-195,353-372"),
     ("Linear refCol not sorted", "FillLinear", (4, 1), "error", "error", "bowfill_test.go:197-202,374-379"),
 ]
+
+
+# ---- Bow.DropNils: bow_test.go:165-282 ; Bow.IsColSorted: bowassertion_test.go:11-55 ------------------------------
+DROP_HOLED = [[N, 200, 300, 400], [110, N, 330, 440], [111, N, 333, N]]     # columns a, b, c
+DROP_CASES = [
+    ("empty bow", [[]], (), [[]], "bow_test.go:183-199"),
+    ("unchanged without nil", [[100, 200, 300, 400], [110, 220, 330, 440], [111, 222, 333, 444]], (),
+     [[100, 200, 300, 400], [110, 220, 330, 440], [111, 222, 333, 444]], "bow_test.go:201-206"),
+    ("drop on all columns", DROP_HOLED, (), [[300], [330], [333]], "bow_test.go:217-231"),
+    ("drop listed = default", DROP_HOLED, (1, 2, 0), [[300], [330], [333]], "bow_test.go:208-215"),
+    ("drop on one column", DROP_HOLED, (1,), [[N, 300, 400], [110, 330, 440], [111, 333, N]], "bow_test.go:233-247"),
+    ("drop consecutively at start/middle/end", [[N, N, 1, N, N, 2, N, N]], (), [[1, 2]], "bow_test.go:249-268"),
+]
+SORTED_ROWS = [[-2, 1, N, N, -8], [0, N, 3, 4, 0], [1, N, N, 120, N], [10, 4, 10, 10, -5], [13, N, N, N, N],
+               [20, 6, 30, 400, -10]]
+SORTED_EXPECTED = [True, True, True, False, False]

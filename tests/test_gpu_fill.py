@@ -113,3 +113,39 @@ def test_fill_linear_unsorted_reference(ctx):
     fr2 = N.Frame.from_numpy(ctx, [(ref, np.array([True, True, False, True])), v])
     out = fr2.fill_linear(0, 1)
     assert out.num_rows == 4
+
+
+# ---- Bow.DropNils / Bow.IsColSorted -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,cols,sel,expected,cite", G.DROP_CASES, ids=[c[0] for c in G.DROP_CASES])
+def test_drop_nils_golden_api(name, cols, sel, expected, cite):
+    names = list("abc")[:len(cols)]
+    b = B.NewBowFromColBasedInterfaces(names, [B.Int64] * len(cols), cols)
+    got = b.DropNils(*sel)
+    assert got.ToColBased() == expected, cite
+
+
+def test_is_col_sorted_golden_api():
+    for typ, conv in ((B.Int64, lambda v: v), (B.Float64, lambda v: None if v is None else float(v))):
+        b = B.NewBowFromColBasedInterfaces(list("abcde"), [typ] * 5, [[conv(r[c]) for r in G.SORTED_ROWS] for c in range(5)])
+        assert [b.IsColSorted(c) for c in range(5)] == G.SORTED_EXPECTED      # bowassertion_test.go:24-33,45-54
+
+
+@pytest.mark.parametrize("n", [1, 33, 8191, 8193, 100000])
+def test_drop_nils_random_vs_oracle(ctx, n):
+    from bow_b200 import native as N
+    rng = np.random.default_rng(H.seed_of("dropnils", n))
+    for null_p, sel in ((0.0, ()), (0.1, ()), (0.6, (1,)), (0.97, (0, 2)), (1.0, (2,))):
+        t = (np.cumsum(rng.integers(0, 4, size=n)), rng.random(n) >= null_p / 2)
+        cols = [(t[0].astype(np.int64), t[1]), H.random_values(rng, n, np.float64, null_p),
+                H.random_values(rng, n, np.int64, null_p / 3)]
+        fr = N.Frame.from_numpy(ctx, cols)
+        out = fr.drop_nils(*sel)
+        got = out.download()
+        want = R.drop_nils(cols, sel)
+        assert out.num_rows == len(want[0][0])
+        for c in range(3):
+            assert_col(got[c], (want[c][0], want[c][1]), f"DropNils n={n} p={null_p} sel={sel} col {c}")
+        # the surviving time column can go straight into the rolling path: sortedness as the reference sees it
+        assert out.is_col_sorted(0) == R.is_col_sorted(want[0][0], want[0][1]) if out.num_rows else True
+        out.close()
+        fr.close()
