@@ -65,3 +65,15 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("no CPU fallback", ""), os.path.join(dirpath, f)
+
+
+def test_c_consumer_compiles_and_links(tmp_path):
+    """the boundary is usable from plain C: tests/c/abi_demo.c builds against include/bowgpu.h and links the library
+    (it is RUN by the GPU suite, tests/test_gpu_c_abi.py)"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "abi_demo"
+    subprocess.check_call(["gcc", "-O2", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "c", "abi_demo.c"), "-o", str(exe), "-L", os.path.join(root, "bow_b200"),
+                           "-lbowgpu", "-Wl,-rpath," + os.path.join(root, "bow_b200"), "-lm"])
+    assert exe.exists()
