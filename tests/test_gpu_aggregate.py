@@ -330,3 +330,65 @@ def test_whole_random_vs_oracle(ctx, kind):
                 assert abs(a - b) <= 1e-12 * max(abs(b), scale), (kind, n, sp, a, b)
             else:
                 assert H.same_value(a.item(), b.item()), (kind, n, sp, a, b)
+
+
+@pytest.mark.parametrize("shift", [0, 1, 2])
+def test_device_resident_inputs_zero_copy(ctx, shift):
+    """BOWGPU_MEM_DEVICE frames: torch tensors already in HBM are wrapped (16-byte aligned values: zero copy; an odd
+    element offset makes them 8-byte aligned only: device-to-device copy); the Arrow bit offset of the validity bitmap
+    is honoured either way"""
+    import torch
+    from bow_b200 import native as N
+    rng = np.random.default_rng(40 + shift)
+    n, interval = 50000, 23
+    t = (np.cumsum(rng.integers(0, 4, size=n)) + 7).astype(np.int64)
+    v, m = H.random_values(rng, n, np.float64, 0.25, specials=True)
+    pad = np.zeros(shift, dtype=np.int64)
+    dt = torch.from_numpy(np.concatenate([pad, t])).cuda()
+    dv = torch.from_numpy(np.concatenate([pad.astype(np.float64), v])).cuda()
+    db = torch.from_numpy(N.pack_bits(m, shift)).cuda()
+    arr = (N.Col * 2)()
+    arr[0].values, arr[0].validity, arr[0].offset, arr[0].length, arr[0].null_count, arr[0].dtype = \
+        dt.data_ptr(), None, shift, n, 0, N.INT64
+    arr[1].values, arr[1].validity, arr[1].offset, arr[1].length, arr[1].null_count, arr[1].dtype = \
+        dv.data_ptr(), db.data_ptr(), shift, n, -1, N.FLOAT64       # null_count unknown: counted on the device
+    torch.cuda.synchronize()
+    fr = N.Frame.from_col_descs(ctx, arr, 2, N.MEM_DEVICE, keep=[dt, dv, db])
+    r = N.Rolling(fr, 0, interval, offset=5)
+    specs = [("WindowStart", 0), ("Count", 1), ("Min", 1), ("Max", 1), ("First", 1), ("Last", 1)]
+    got = r.aggregate(specs)
+    want = R.RefRolling(R.Frame([(t, None), (v, m)]), 0, interval, offset=5).aggregate(specs)
+    for sp, (gv, gm), (wv, wm) in zip(specs, got, want):
+        assert np.array_equal(gm, wm), sp
+        a, b = gv[gm], wv[wm]
+        same = a.view(np.int64) == b.view(np.int64)
+        if a.dtype == np.float64:
+            same |= np.isnan(a) & np.isnan(b)
+        assert same.all(), sp
+    r.close()
+    fr.close()
+
+
+@pytest.mark.parametrize("interval", [7, 3000, 10**7])
+def test_exact_ops_with_special_values_across_tiles(ctx, interval):
+    """Min / Max / First / Last / Count with NaN, +-0, +-Inf, 1e300 and subnormals in windows that span threads, tiles
+    (8192 rows) and the whole column: the left-wins tie rule and the sticky leading NaN survive every stitch level"""
+    from bow_b200 import native as N
+    rng = np.random.default_rng(H.seed_of("specials", interval))
+    n = 60000
+    t = (np.cumsum(rng.integers(0, 3, size=n)) + 1).astype(np.int64)
+    v, m = H.random_values(rng, n, np.float64, 0.3, specials=True)
+    specs = [("WindowStart", 0), ("Count", 1), ("Min", 1), ("Max", 1), ("First", 1), ("Last", 1)]
+    fr = N.Frame.from_numpy(ctx, [(t, None), (v, m)])
+    got = N.Rolling(fr, 0, interval).aggregate(specs)
+    want = R.RefRolling(R.Frame([(t, None), (v, m)]), 0, interval).aggregate(specs)
+    gw = fr.aggregate_whole(0, specs[1:])
+    ww = R.aggregate_whole(R.Frame([(t, None), (v, m)]), 0, specs[1:])
+    for sp, (gv, gm), (wv, wm) in list(zip(specs, got, want)) + list(zip(specs[1:], gw, ww)):
+        assert np.array_equal(gm, wm), sp
+        a, b = gv[gm], wv[wm]
+        same = a.view(np.int64) == b.view(np.int64)      # bit-exact: -0.0 and +0.0 are different answers
+        if a.dtype == np.float64:
+            same |= np.isnan(a) & np.isnan(b)
+        assert same.all(), (sp, a[~same][:3], b[~same][:3])
+    fr.close()
