@@ -10,7 +10,9 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "kernels.h"
@@ -39,6 +41,8 @@ struct bowgpu_ctx {
     uint8_t *pinned[2] = {nullptr, nullptr};
     cudaEvent_t pinned_ev[2] = {nullptr, nullptr};
     size_t pinned_bytes = 0;
+    // worker contexts of bowgpu_aggregate_host (own stream, arena, pool each), created on first use
+    std::vector<bowgpu_ctx *> workers;
     // timing
     int timing = 0;  // 0 off, 1 per call, 2 accumulate over calls
     cudaEvent_t ev_total[2] = {nullptr, nullptr};
@@ -361,6 +365,8 @@ extern "C" int32_t bowgpu_ctx_create(int32_t device, void *stream, bowgpu_ctx **
 
 extern "C" void bowgpu_ctx_destroy(bowgpu_ctx *ctx) {
     if (!ctx) return;
+    for (bowgpu_ctx *w : ctx->workers) bowgpu_ctx_destroy(w);
+    ctx->workers.clear();
     Guard gd(ctx);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->arena) cudaFree(ctx->arena);
@@ -1682,4 +1688,158 @@ extern "C" int32_t bowgpu_rolling_interpolate_aggregate(bowgpu_rolling *r, const
     const int32_t rc = aggregate_core(r, specs, nspecs, outs, mem, syn.data());
     pool_free(ctx, blk);  // stream ordered: released after the kernels that read it
     return rc;
+}
+
+// ================================================================================================
+// one-shot, pipelined host -> host aggregation
+// ================================================================================================
+// rolling.IntervalRolling(b, col, interval, opts).Aggregate(aggrs...) for a Bow that lives in HOST memory, results into
+// host buffers, in ONE call.  The window range is cut into chunks (multiples of 64 windows, so validity bitmaps land
+// byte aligned; each chunk carries the one-row halo of an inclusive window) exactly like the multi-GPU partitioning
+// (SURVEY 8e), and a few worker contexts - own stream, arena and pool each - run upload -> kernels -> download of
+// different chunks concurrently: the device-to-host copies and the kernels of one chunk hide behind the host-to-device
+// copy of the next, so the call takes the PCIe time of the inputs and little else.  Only the columns the aggregations
+// read are uploaded.
+namespace {
+
+int64_t host_time_at(const bowgpu_col &c, int64_t i) { return ((const int64_t *)c.values)[c.offset + i]; }
+
+int64_t host_lower_bound(const bowgpu_col &c, int64_t n, int64_t x) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t mid = lo + ((hi - lo) >> 1);
+        if (host_time_at(c, mid) < x)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+}  // namespace
+
+extern "C" int32_t bowgpu_aggregate_host(bowgpu_ctx *ctx, const bowgpu_col *cols, int32_t ncols, int32_t time_col,
+                                         int64_t interval, int64_t offset, int32_t inclusive,
+                                         const bowgpu_agg_spec *specs, int32_t nspecs, bowgpu_out_col *outs,
+                                         int64_t out_capacity, int64_t *num_windows) {
+    if (!ctx || !cols || !specs || !outs || ncols <= 0 || nspecs <= 0 || !num_windows) return BOWGPU_EINVAL;
+    Guard gd(ctx);
+    *num_windows = 0;
+    if (time_col < 0 || time_col >= ncols) return fail(ctx, BOWGPU_EINVAL, "time column index %d out of range", time_col);
+    const bowgpu_col &tc = cols[time_col];
+    const int64_t n = tc.length;
+    auto plain = [&]() -> int32_t {  // upload everything, one pass (small inputs and the cases chunks do not cover)
+        bowgpu_frame *f = nullptr;
+        bowgpu_rolling *r = nullptr;
+        int32_t rc = bowgpu_frame_create(ctx, cols, ncols, BOWGPU_MEM_HOST, &f);
+        if (rc == BOWGPU_OK) rc = bowgpu_rolling_create(f, time_col, interval, offset, inclusive, nullptr, &r);
+        if (rc == BOWGPU_OK) {
+            *num_windows = r->W;
+            if (r->W > out_capacity) rc = fail(ctx, BOWGPU_ECAPACITY, "%lld windows, capacity %lld", (long long)r->W, (long long)out_capacity);
+        }
+        if (rc == BOWGPU_OK) rc = bowgpu_rolling_aggregate(r, specs, nspecs, outs, BOWGPU_MEM_HOST);
+        bowgpu_rolling_destroy(r);
+        bowgpu_frame_destroy(f);
+        return rc;
+    };
+    if (tc.dtype != BOWGPU_INT64 || interval <= 0 || n < (int64_t)4 << 20 || (tc.validity && tc.null_count != 0)) return plain();
+    for (int j = 0; j < nspecs; ++j)
+        if (specs[j].col < 0 || specs[j].col >= ncols) return fail(ctx, BOWGPU_EINVAL, "aggregation %d: no column %d", j, specs[j].col);
+    // lattice, rolling.go:96-99,114-128,143-154
+    int64_t off = offset;
+    if (off >= interval || off <= -interval) off %= interval;
+    if (off < 0) off += interval;
+    const int64_t t_first = host_time_at(tc, 0), t_last = host_time_at(tc, n - 1);
+    int64_t s0 = (int64_t)((uint64_t)((t_first / interval) * interval) + (uint64_t)off);
+    if (s0 > t_first) s0 = (int64_t)((uint64_t)s0 - (uint64_t)interval);
+    if (t_first < s0 || t_last < t_first) return plain();  // rows before the first window start / obviously unsorted
+    const int64_t W = (int64_t)(((uint64_t)t_last - (uint64_t)s0) / (uint64_t)interval) + 1;
+    *num_windows = W;
+    if (W > out_capacity) return fail(ctx, BOWGPU_ECAPACITY, "%lld windows, capacity %lld", (long long)W, (long long)out_capacity);
+
+    // columns actually read, remapped to a compact frame
+    std::vector<int> used, remap(ncols, -1);
+    auto use = [&](int c) {
+        if (remap[c] < 0) {
+            remap[c] = (int)used.size();
+            used.push_back(c);
+        }
+    };
+    use(time_col);
+    for (int j = 0; j < nspecs; ++j) use(specs[j].col);
+    std::vector<bowgpu_agg_spec> sp(specs, specs + nspecs);
+    for (auto &x : sp) x.col = remap[x.col];
+    for (int j = 0; j < nspecs; ++j) outs[j].dtype = bowgpu_agg_return_type(specs[j].op, cols[specs[j].col].dtype);
+
+    // chunks of ~12M rows (a few ms of PCIe each), cut on multiples of 64 windows
+    const int64_t target_rows = (int64_t)12 << 20;
+    int64_t nchunks = (n + target_rows - 1) / target_rows;
+    if (nchunks > W / 64) nchunks = W / 64;
+    if (nchunks < 2) return plain();
+    struct Chunk {
+        int64_t k_lo, k_hi, row_lo, row_hi;
+    };
+    std::vector<Chunk> chunks;
+    int64_t k_prev = 0, row_prev = 0;
+    for (int64_t c = 1; c <= nchunks; ++c) {
+        int64_t k = c == nchunks ? W : ((c * W) / nchunks) / 64 * 64;
+        if (k <= k_prev) continue;
+        const int64_t row = c == nchunks ? n : host_lower_bound(tc, n, (int64_t)((uint64_t)s0 + (uint64_t)k * (uint64_t)interval));
+        int64_t hi = row;
+        if (c != nchunks && row < n) hi = row + 1;  // halo: the row an inclusive last window may borrow
+        chunks.push_back({k_prev, k, row_prev, hi});
+        k_prev = k;
+        row_prev = row;
+    }
+    const int nworkers = (int)std::min<size_t>(3, chunks.size());
+    while ((int)ctx->workers.size() < nworkers) {
+        bowgpu_ctx *w = nullptr;
+        int32_t rc = bowgpu_ctx_create(ctx->device, nullptr, &w);
+        if (rc) return fail(ctx, rc, "worker context");
+        ctx->workers.push_back(w);
+    }
+    std::atomic<size_t> next{0};
+    std::vector<int32_t> status(nworkers, BOWGPU_OK);
+    std::vector<std::string> errs(nworkers);
+    auto work = [&](int wi) {
+        bowgpu_ctx *wc = ctx->workers[wi];
+        cudaSetDevice(wc->device);
+        for (;;) {
+            const size_t ci = next.fetch_add(1);
+            if (ci >= chunks.size() || status[wi] != BOWGPU_OK) return;
+            const Chunk &ch = chunks[ci];
+            std::vector<bowgpu_col> cc(used.size());
+            for (size_t u = 0; u < used.size(); ++u) {
+                cc[u] = cols[used[u]];
+                cc[u].offset += ch.row_lo;
+                cc[u].length = ch.row_hi - ch.row_lo;
+                if (cc[u].validity && cc[u].null_count != 0) cc[u].null_count = -1;  // counted on the device
+            }
+            std::vector<bowgpu_out_col> oc(nspecs);
+            for (int j = 0; j < nspecs; ++j) {
+                oc[j].values = (char *)outs[j].values + ch.k_lo * 8;
+                oc[j].validity = outs[j].validity + ch.k_lo / 8;
+            }
+            bowgpu_frame *f = nullptr;
+            bowgpu_rolling *r = nullptr;
+            int32_t rc = bowgpu_frame_create(wc, cc.data(), (int32_t)cc.size(), BOWGPU_MEM_HOST, &f);
+            if (rc == BOWGPU_OK)
+                rc = bowgpu_rolling_create_shard(f, remap[time_col], interval, (int64_t)((uint64_t)s0 + (uint64_t)ch.k_lo * (uint64_t)interval),
+                                                 ch.k_hi - ch.k_lo, inclusive, nullptr, &r);
+            if (rc == BOWGPU_OK) rc = aggregate_core(r, sp.data(), nspecs, oc.data(), BOWGPU_MEM_HOST, nullptr);
+            if (rc != BOWGPU_OK) {
+                status[wi] = rc;
+                errs[wi] = wc->err;
+            }
+            bowgpu_rolling_destroy(r);
+            bowgpu_frame_destroy(f);
+        }
+    };
+    std::vector<std::thread> threads;
+    for (int wi = 1; wi < nworkers; ++wi) threads.emplace_back(work, wi);
+    work(0);
+    for (auto &t : threads) t.join();
+    for (int wi = 0; wi < nworkers; ++wi)
+        if (status[wi] != BOWGPU_OK) return fail(ctx, status[wi], "%s", errs[wi].c_str());
+    return BOWGPU_OK;
 }

@@ -38,6 +38,7 @@ SYMBOLS = [
     "bowgpu_rolling_bounds", "bowgpu_rolling_aggregate", "bowgpu_agg_return_type", "bowgpu_agg_needs_inclusive",
     "bowgpu_rolling_interpolate", "bowgpu_frame_aggregate_whole", "bowgpu_frame_fill", "bowgpu_frame_fill_linear",
     "bowgpu_rolling_interpolate_aggregate", "bowgpu_frame_drop_nils", "bowgpu_frame_is_col_sorted",
+    "bowgpu_aggregate_host",
 ]
 
 
@@ -108,6 +109,9 @@ def lib():
                                                C.c_int32]
         L.bowgpu_rolling_interpolate_aggregate.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.POINTER(AggSpec),
                                                            C.c_int32, C.POINTER(OutCol), C.c_int32]
+        L.bowgpu_aggregate_host.argtypes = [C.c_void_p, C.POINTER(Col), C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int32,
+                                            C.POINTER(AggSpec), C.c_int32, C.POINTER(OutCol), C.c_int64,
+                                            C.POINTER(C.c_int64)]
         L.bowgpu_frame_drop_nils.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p)]
         L.bowgpu_frame_is_col_sorted.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
         L.bowgpu_frame_fill.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p)]
@@ -213,6 +217,35 @@ class Ctx:
             self.close()
         except Exception:
             pass
+
+
+def aggregate_host(ctx: "Ctx", cols: Sequence[NpCol], time_col: int, interval: int, specs: Sequence[tuple],
+                   offset: int = 0, inclusive: bool = False, num_windows: Optional[int] = None):
+    """One-shot pipelined IntervalRolling -> Aggregate from host columns to host results (bowgpu_aggregate_host)
+    -> list of (values ndarray, valid mask ndarray)"""
+    arr, keep = cols_from_numpy(cols)
+    t = cols[time_col][0]
+    if num_windows is None:   # countWindows on the host (rolling.go:96-99,143-154), like the Go side
+        from . import partition as P
+        num_windows = P.num_windows(int(t[0]), int(t[-1]), interval, offset) if len(t) else 0
+    W = num_windows
+    sarr = make_specs(specs)
+    outs = (OutCol * len(specs))()
+    bufs = []
+    for j in range(len(specs)):
+        v = np.full(max(W, 1), -7, dtype=np.int64)
+        b = np.full((W + 7) // 8 + 1, 0xAA, dtype=np.uint8)
+        bufs.append((v, b))
+        outs[j].values, outs[j].validity = v.ctypes.data, b.ctypes.data
+    got = C.c_int64()
+    ctx.check(lib().bowgpu_aggregate_host(ctx.h, arr, len(cols), time_col, interval, offset, int(inclusive), sarr,
+                                          len(specs), outs, W, C.byref(got)))
+    assert got.value == W, (got.value, W)
+    res = []
+    for j, (v, b) in enumerate(bufs):
+        vals = v[:W] if outs[j].dtype == INT64 else v[:W].view(np.float64)
+        res.append((vals, unpack_bits(b, W)))
+    return res
 
 
 class Frame:

@@ -264,6 +264,16 @@ int32_t bowgpu_rolling_interpolate_aggregate(bowgpu_rolling *r, const int32_t *o
                                              const bowgpu_agg_spec *specs, int32_t nspecs, bowgpu_out_col *outs,
                                              int32_t mem);
 
+/* rolling.IntervalRolling(b, col, interval, Options{Offset, Inclusive}).Aggregate(aggrs...) for a Bow in HOST memory, in
+ * one call (rolling.go:60 + aggregation.go:123-238): the window range is processed in chunks by a few worker contexts
+ * whose uploads, kernels and downloads overlap, and only the columns the aggregations read cross the bus.  outs[j] are
+ * host buffers with room for `out_capacity` windows (values 8 bytes each, validity ceil(capacity / 8) bytes);
+ * *num_windows receives W (BOWGPU_ECAPACITY when it exceeds the capacity; the Go side knows W from countWindows,
+ * rolling.go:143-154).  Same results as bowgpu_frame_create + bowgpu_rolling_create + bowgpu_rolling_aggregate. */
+int32_t bowgpu_aggregate_host(bowgpu_ctx *ctx, const bowgpu_col *cols, int32_t ncols, int32_t time_col, int64_t interval,
+                              int64_t offset, int32_t inclusive, const bowgpu_agg_spec *specs, int32_t nspecs,
+                              bowgpu_out_col *outs, int64_t out_capacity, int64_t *num_windows);
+
 #ifdef __cplusplus
 }
 #endif

@@ -392,3 +392,31 @@ def test_exact_ops_with_special_values_across_tiles(ctx, interval):
             same |= np.isnan(a) & np.isnan(b)
         assert same.all(), (sp, a[~same][:3], b[~same][:3])
     fr.close()
+
+
+@pytest.mark.parametrize("n,kind", [(1000, "regular"), (5_000_000, "bursty"), (30_000_000, "regular"), (26_000_000, "sparse")])
+def test_pipelined_host_aggregate(ctx, n, kind):
+    """bowgpu_aggregate_host: host columns in, host results out, chunks of the window range processed by concurrent
+    worker contexts (upload / kernels / download overlap).  Must equal the plain path and the oracle, including windows
+    and inclusive rows at chunk cuts."""
+    from bow_b200 import native as N
+    rng = np.random.default_rng(H.seed_of("hostagg", n, kind))
+    t = H.random_times(rng, n, kind)
+    t = t - int(t[0]) + 12345
+    v = H.random_values(rng, n, np.float64, 0.15)
+    w = H.random_values(rng, n, np.int64, 0.0)
+    unused = (np.zeros(n), None)                     # never read by the aggregations: must not be uploaded
+    cols = [(t, None), v, unused, w]
+    interval = 37 if kind != "sparse" else 11
+    specs = [("WindowStart", 0), ("Count", 1), ("Min", 1), ("Last", 3), ("Sum", 3), ("ArithmeticMean", 1),
+             ("IntegralTrapezoid", 1), ("WeightedAverageStep", 3)]
+    got = N.aggregate_host(ctx, cols, 0, interval, specs, offset=5)
+    want = R.RefRolling(R.Frame(cols), 0, interval, offset=5).aggregate(specs)
+    for sp, (gv, gm), (wv, wm) in zip(specs, got, want):
+        assert gv.dtype == wv.dtype and np.array_equal(gm, wm), (n, kind, sp)
+        a, b = gv[gm], wv[wm]
+        if sp[0] in ("Sum", "ArithmeticMean", "IntegralTrapezoid", "WeightedAverageStep"):
+            scale = 2000.0 * (interval if sp[0].startswith("Integral") else 1.0)
+            assert np.all(np.abs(a - b) <= 1e-12 * np.maximum(np.abs(b), scale) * 8), (n, kind, sp)
+        else:
+            assert np.array_equal(a.view(np.int64), b.view(np.int64)), (n, kind, sp)
