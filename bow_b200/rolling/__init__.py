@@ -368,6 +368,8 @@ class Rolling:
             if self._lazy is not None and self.currWindowIndex == 0:
                 parent, ops = self._lazy   # Aggregate right after Interpolate: fused, nothing is materialised
                 res = parent._ensure_handle().interpolate_aggregate(ops, specs)
+            elif self.frame is None and self.bow is not None and self.currWindowIndex == 0 and self.numWindows > 0:
+                res = self._aggregate_host(specs)   # host Bow, nothing on the device yet: one pipelined call
             else:
                 res = self._ensure_handle().aggregate(specs)
         except N.BowGpuError as e:
@@ -474,6 +476,34 @@ class Rolling:
         r.numWindows = h.num_windows
         r.currWindowFirstValue = h.first_window_start
         return r
+
+    def _aggregate_host(self, specs):
+        """bowgpu_aggregate_host: upload, kernels and download of window-range chunks overlap; only the columns the
+        aggregations read cross the bus"""
+        import ctypes as C
+        from ..runtime import default_ctx
+        ctx = default_ctx()
+        arr, keep = _cols_from_bow(self.bow)
+        W = self.numWindows
+        sarr = N.make_specs(specs)
+        outs = (N.OutCol * len(specs))()
+        bufs = []
+        for j in range(len(specs)):
+            v = np.zeros(max(W, 1), dtype=np.int64)
+            b = np.zeros((W + 7) // 8 + 1, dtype=np.uint8)
+            bufs.append((v, b))
+            outs[j].values, outs[j].validity = v.ctypes.data, b.ctypes.data
+        got = C.c_int64()
+        ctx.check(N.lib().bowgpu_aggregate_host(ctx.h, arr, self.bow.NumCols(), self.intervalColIndex, self.interval,
+                                                self.options.Offset, int(self.options.Inclusive), sarr, len(specs), outs, W,
+                                                C.byref(got)))
+        if got.value != W:
+            raise BowError(f"window count mismatch: {got.value} != {W}")
+        res = []
+        for j, (v, b) in enumerate(bufs):
+            vals = v[:W] if outs[j].dtype == N.INT64 else v[:W].view(np.float64)
+            res.append((vals, N.unpack_bits(b, W)))
+        return res
 
     def _first_time(self):
         if self.bow is None or self.bow.NumRows() == 0:
