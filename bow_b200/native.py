@@ -227,7 +227,7 @@ def aggregate_host(ctx: "Ctx", cols: Sequence[NpCol], time_col: int, interval: i
     t = cols[time_col][0]
     if num_windows is None:   # countWindows on the host (rolling.go:96-99,143-154), like the Go side
         from . import partition as P
-        num_windows = P.num_windows(int(t[0]), int(t[-1]), interval, offset) if len(t) else 0
+        num_windows = P.num_windows(int(t[0]), int(t[-1]), interval, P.normalise_offset(interval, offset)) if len(t) else 0
     W = num_windows
     sarr = make_specs(specs)
     outs = (OutCol * len(specs))()
