@@ -79,10 +79,10 @@ struct BasicPol {
     }
     // cnt / first / last cost nothing per row: popcount / ffs / fls of the validity bits of the rows of one phase
     // that joined the run (bit j of mask = row j of the thread's phase, vrow = its values in shared memory)
-    static __device__ __forceinline__ void note(State &s, uint32_t mask, const int64_t *, const uint64_t *vrow) {
+    static __device__ __forceinline__ void note(State &s, uint32_t mask, const int64_t *, const uint64_t *vrow, const int swz) {
         if (mask) {
-            if (NEED_FIRST && s.cnt == 0) s.first = vrow[__ffs(mask) - 1];
-            if (NEED_LAST) s.last = vrow[31 - __clz(mask)];
+            if (NEED_FIRST && s.cnt == 0) s.first = vrow[(__ffs(mask) - 1) ^ swz];
+            if (NEED_LAST) s.last = vrow[(31 - __clz(mask)) ^ swz];
             s.cnt += __popc(mask);
         }
     }

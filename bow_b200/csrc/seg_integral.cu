@@ -83,10 +83,10 @@ struct IntegralPol {
         s.has = 1;
     }
     // the number of points and the first point of a run come from the validity bits of the rows that joined it
-    static __device__ __forceinline__ void note(State &s, uint32_t mask, const int64_t *trow, const uint64_t *vrow) {
+    static __device__ __forceinline__ void note(State &s, uint32_t mask, const int64_t *trow, const uint64_t *vrow, const int swz) {
         if (mask) {
             if (s.n == 0) {
-                const int j = __ffs(mask) - 1;
+                const int j = (__ffs(mask) - 1) ^ swz;
                 s.fT = (double)trow[j];
                 s.fV = val(vrow[j]);
             }

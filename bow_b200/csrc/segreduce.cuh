@@ -29,7 +29,7 @@
 //
 // Policy interface (all static, device):
 //   State, Carry, Out, Inc                      types (Inc = the inclusive row of a window, rolling.go:201-209)
-//   identity(), accumulate(State&, t, raw), note(State&, mask, trow, vrow), combine(L, R), shfl_up(s, d)
+//   identity(), accumulate(State&, t, raw), note(State&, mask, trow, vrow, swz), combine(L, R), shfl_up(s, d)
 //   make_inc(at_end, valid_next, raw_next, t_next)
 //   write(out, g, k, state, inc)                final values of a window
 //   make_carry(state, inc, key, closed) -> Carry; carry_* accessors; write_carry
@@ -57,13 +57,20 @@ namespace bowgpu {
 #ifndef SEG_CFG_UNROLL
 #define SEG_CFG_UNROLL 2
 #endif
+#ifndef SEG_CFG_SWZ
+#define SEG_CFG_SWZ 1
+#endif
+// SEG_SWZ: boxes are [NT][P] with TMA's 128-byte swizzle (16-byte chunk c of row r lands in chunk c ^ (r & 7)) instead of
+// [NT][P + 2] with a padded pitch: the same conflict-free LDS.128, but no padding columns through the TMA unit (the
+// staging pattern alone moves 7.1 TB/s swizzled against 6.6 TB/s padded, profiles/r1_box_stream_microbench.txt).
+constexpr bool SEG_SWZ = SEG_CFG_SWZ != 0;
 constexpr int SEG_UNROLL = SEG_CFG_UNROLL;  // row pairs per trip of the streaming loop
 constexpr int SEG_NT = SEG_CFG_NT;
 constexpr int SEG_P = 16;                     // rows per phase (box start columns must be 16-byte aligned in global memory)
 constexpr int SEG_NP = SEG_CFG_NP;            // phases per tile
 constexpr int SEG_RE = SEG_P * SEG_NP;        // consecutive rows owned by one thread in a tile
 constexpr int SEG_T = SEG_NT * SEG_RE;        // rows per tile
-constexpr int SEG_COLS = SEG_P + 2;           // box columns (the last two only pad the pitch to 144 bytes)
+constexpr int SEG_COLS = SEG_SWZ ? SEG_P : SEG_P + 2;  // box columns (unswizzled: the last two only pad the pitch to 144 bytes)
 constexpr int SEG_BOX_BYTES = SEG_NT * SEG_COLS * 8;
 constexpr int SEG_SLOT_BYTES = 2 * SEG_BOX_BYTES;  // time box + value box
 constexpr int SEG_BITS_BYTES = SEG_T / 8;
@@ -71,10 +78,15 @@ constexpr int SEG_BITS_COPY = SEG_BITS_BYTES + 16;
 constexpr int SEG_BITS_STRIDE = (SEG_BITS_COPY + 127) / 128 * 128;
 constexpr int SEG_MAX_STAGES = 4;
 constexpr int SEG_NW = SEG_NT / 32;
-constexpr int SEG_HEADER_BYTES = 640;
-static_assert((SEG_P * 8) % 16 == 0 && (SEG_COLS * 8) % 16 == 0 && (SEG_COLS * 2) % 8 == 4, "box geometry: 16-byte aligned starts, pitch = odd multiple of 16 bytes");
+constexpr int SEG_SLOT_ALIGN = SEG_SWZ ? 1024 : 128;  // the swizzle pattern is a function of the shared-memory address
+constexpr int SEG_HEADER_MIN = 640;
+constexpr int SEG_HEADER_BYTES = (SEG_HEADER_MIN + 2 * SEG_BITS_STRIDE + SEG_SLOT_ALIGN - 1) / SEG_SLOT_ALIGN * SEG_SLOT_ALIGN - 2 * SEG_BITS_STRIDE;
+static_assert((SEG_P * 8) % 16 == 0 && (SEG_COLS * 8) % 16 == 0, "box geometry: 16-byte aligned starts");
+static_assert(SEG_SWZ ? SEG_COLS * 8 == 128 : (SEG_COLS * 2) % 8 == 4, "pitch: one swizzle row, or an odd multiple of 16 bytes");
+// element j of a thread's row sits at index j ^ seg_swz(tid)
+__device__ __forceinline__ int seg_swz(int tid) { return SEG_SWZ ? (tid & 7) << 1 : 0; }
 static_assert(SEG_T % 128 == 0, "tile validity bytes must be a multiple of 16");
-static_assert(SEG_BOX_BYTES % 128 == 0, "boxes keep every slot 128-byte aligned");
+static_assert(SEG_BOX_BYTES % SEG_SLOT_ALIGN == 0, "boxes keep every slot aligned");
 
 template <class Pol>
 struct SegArgs {
@@ -181,6 +193,7 @@ __device__ __forceinline__ void seg_phase(SegThread<Pol> &c, const SegArgs<Pol> 
     const uint64_t d = g.div.d;
     const int64_t *trow = reinterpret_cast<const int64_t *>(slot) + tid * SEG_COLS;
     const uint64_t *vrow = reinterpret_cast<const uint64_t *>(slot + SEG_BOX_BYTES) + tid * SEG_COLS;
+    const int swz = seg_swz(tid);
     const int ti0 = tid * SEG_RE + phase * P;  // tile-relative index of my first row of this phase
     int nmine = P;
     if (!FULL) {
@@ -206,8 +219,8 @@ __device__ __forceinline__ void seg_phase(SegThread<Pol> &c, const SegArgs<Pol> 
 
     const longlong2 *t2 = reinterpret_cast<const longlong2 *>(trow);
     const ulonglong2 *v2 = reinterpret_cast<const ulonglong2 *>(vrow);
-    longlong2 ta = t2[0];
-    ulonglong2 va = v2[0];
+    longlong2 ta = t2[0 ^ (swz >> 1)];
+    ulonglong2 va = v2[0 ^ (swz >> 1)];
 
     if (phase == 0) {  // window of my first row and its absolute end (rows before s0 collapse onto window 0)
         const bool early0 = !FULL && early_any;
@@ -229,7 +242,7 @@ __device__ __forceinline__ void seg_phase(SegThread<Pol> &c, const SegArgs<Pol> 
             bad |= xj < c.xlast;
             c.xlast = xj;
             if (xj >= c.eabs) {  // row j starts a later window: the open one is complete
-                Pol::note(c.st, vbits & ((1u << j) - 1u) & ~((1u << segstart) - 1u), trow, vrow);
+                Pol::note(c.st, vbits & ((1u << j) - 1u) & ~((1u << segstart) - 1u), trow, vrow, swz);
                 if (!FUSED) {
                     const Inc inc = Pol::make_inc(xj == c.eabs, (vbits >> j) & 1u, rj, xj);
                     if (c.nclose == 0) {
@@ -275,14 +288,14 @@ __device__ __forceinline__ void seg_phase(SegThread<Pol> &c, const SegArgs<Pol> 
     };
 #pragma unroll(SEG_UNROLL)
     for (int q = 0; q < P / 2; ++q) {
-        const longlong2 tb = t2[q + 1 < P / 2 ? q + 1 : q];  // (the pitch pads two more columns; stay inside anyway)
-        const ulonglong2 vb = v2[q + 1 < P / 2 ? q + 1 : q];
+        const longlong2 tb = t2[(q + 1 < P / 2 ? q + 1 : q) ^ (swz >> 1)];  // (stay inside the row)
+        const ulonglong2 vb = v2[(q + 1 < P / 2 ? q + 1 : q) ^ (swz >> 1)];
         row(2 * q, ta.x, va.x);
         row(2 * q + 1, ta.y, va.y);
         ta = tb;
         va = vb;
     }
-    Pol::note(c.st, vbits & ~((1u << segstart) - 1u), trow, vrow);
+    Pol::note(c.st, vbits & ~((1u << segstart) - 1u), trow, vrow, swz);
 }
 
 // End of a tile: stitch the per-thread pieces.
@@ -410,14 +423,14 @@ template <class Pol, bool HAS_NULLS, int MIN_CTAS, bool FUSED>
 __global__ void __launch_bounds__(SEG_NT, MIN_CTAS)
     segreduce_kernel(const __grid_constant__ SegArgs<Pol> A, const __grid_constant__ CUtensorMap tm_time,
                      const __grid_constant__ CUtensorMap tm_val, const int64_t ntiles, const int nstages) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
+    extern __shared__ __align__(SEG_SLOT_ALIGN) uint8_t smem_raw[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);                    // [SEG_MAX_STAGES]
     WarpEdge *wedge = reinterpret_cast<WarpEdge *>(smem_raw + 64);              // [SEG_NW]
     WarpTotal<Pol> *wtot = reinterpret_cast<WarpTotal<Pol> *>(smem_raw + 64 + SEG_NW * sizeof(WarpEdge));
-    static_assert(64 + SEG_NW * (sizeof(WarpEdge) + sizeof(WarpTotal<Pol>)) <= SEG_HEADER_BYTES, "header layout");
+    static_assert(64 + SEG_NW * (sizeof(WarpEdge) + sizeof(WarpTotal<Pol>)) <= SEG_HEADER_MIN, "header layout");
     uint8_t *bits = smem_raw + SEG_HEADER_BYTES;                                // [2][SEG_BITS_STRIDE]
     uint8_t *slots = bits + 2 * SEG_BITS_STRIDE;
-    static_assert((SEG_HEADER_BYTES + 2 * SEG_BITS_STRIDE) % 128 == 0, "slots must be 128-byte aligned");
+    static_assert((SEG_HEADER_BYTES + 2 * SEG_BITS_STRIDE) % SEG_SLOT_ALIGN == 0, "slots must be aligned");
 
     const int tid = threadIdx.x;
     const WindowGeom &g = A.g;
@@ -491,8 +504,8 @@ __global__ void __launch_bounds__(SEG_NT, MIN_CTAS)
                     const int tt = e / SEG_P, cc = e - tt * SEG_P;
                     const int64_t row = r0 + (int64_t)tt * SEG_RE + phase * SEG_P + cc;
                     const bool in = row < g.n;
-                    ts[tt * SEG_COLS + cc] = in ? A.time[row] : 0;
-                    vs[tt * SEG_COLS + cc] = in ? A.values[row] : 0;
+                    ts[tt * SEG_COLS + (cc ^ seg_swz(tt))] = in ? A.time[row] : 0;
+                    vs[tt * SEG_COLS + (cc ^ seg_swz(tt))] = in ? A.values[row] : 0;
                 }
                 if (HAS_NULLS && phase == 0) {
                     uint32_t *bw = const_cast<uint32_t *>(bsm);
@@ -623,7 +636,7 @@ inline int seg_make_tmap(CUtensorMap *m, const void *col, int64_t n) {
         if (l2p < 0 || l2p > 3) l2p = 3;
     }
     const CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_INT64, 2, const_cast<void *>(col), dims, strides, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, (CUtensorMapL2promotion)l2p,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, SEG_SWZ ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, (CUtensorMapL2promotion)l2p,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
