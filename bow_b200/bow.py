@@ -164,6 +164,8 @@ class Bow:
             frame = N.Frame.from_col_descs(default_ctx(), arr, self.NumCols(), N.MEM_HOST, keep)
             try:
                 out = run(frame)
+                if out is None:  # nothing to do: the reference returns the receiver itself
+                    return self
                 try:
                     cols = out.download()
                 finally:
@@ -196,6 +198,12 @@ class Bow:
     def DropNils(self, *colIndices: int) -> "Bow":  # bow.go:188-224
         self._check_fill_types(colIndices, False)
         return self._gpu_fill(lambda f: f.drop_nils(*colIndices))
+
+    def SortByCol(self, colIndex: int) -> "Bow":  # bowsort.go:10-47 (equal keys keep their input order)
+        if colIndex < 0 or colIndex > self.NumCols() - 1:
+            raise BowError(f"no column {colIndex}")
+        self._check_fill_types((), False)
+        return self._gpu_fill(lambda f: f.sort_by_col(colIndex))
 
     def IsColSorted(self, colIndex: int) -> bool:  # bowassertion.go:15-81
         from . import native as N

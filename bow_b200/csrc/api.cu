@@ -942,6 +942,89 @@ extern "C" int32_t bowgpu_frame_is_col_sorted(bowgpu_frame *frame, int32_t col, 
     return BOWGPU_OK;
 }
 
+// Bow.SortByCol(colIndex) (bowsort.go:10-47): rows by ascending values of a nil-free column; *out = null when the column
+// is already sorted (the reference returns b itself, bowsort.go:18-21).  Stable radix sort on the device (sort.cu).
+extern "C" int32_t bowgpu_frame_sort_by_col(bowgpu_frame *frame, int32_t col, bowgpu_frame **out) {
+    if (!frame || !out) return BOWGPU_EINVAL;
+    *out = nullptr;
+    bowgpu_ctx *ctx = frame->ctx;
+    Guard gd(ctx);
+    const int nc = (int)frame->cols.size();
+    if (col < 0 || col >= nc) return fail(ctx, BOWGPU_EINVAL, "no column %d", col);
+    if (nc > 32) return fail(ctx, BOWGPU_EUNSUPPORTED, "SortByCol supports at most 32 columns");
+    const DevCol &kc = frame->cols[col];
+    const int64_t n = frame->n;
+    if (kc.validity && kc.null_count != 0)
+        return fail(ctx, BOWGPU_EINVAL, "column to sort by has %lld nil values", (long long)kc.null_count);  // bowsort.go:11-15
+    if (n < 2) return BOWGPU_OK;
+    if (n > 0xffffffffll) return fail(ctx, BOWGPU_EUNSUPPORTED, "SortByCol: more than 2^32-1 rows");
+    void *scratch = nullptr;
+    if (pool_alloc(ctx, &scratch, sort_scratch_bytes(n)) != cudaSuccess) return fail(ctx, BOWGPU_ENOMEM, "SortByCol scratch");
+    std::vector<unsigned long long> hist(8 * 256);
+    int32_t flags = 0;
+    timing_begin(ctx);
+    int e = launch_sort_prepare(kc.values, kc.dtype == BOWGPU_INT64, n, scratch, ctx->stream, &flags, hist.data());
+    if (e || cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        pool_free(ctx, scratch);
+        return fail(ctx, BOWGPU_ECUDA, "SortByCol (keys): %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    count_launch(ctx, 1);
+    if (!(flags & 1)) {  // sort.IsSorted: nothing to do
+        timing_end(ctx);
+        pool_free(ctx, scratch);
+        return BOWGPU_OK;
+    }
+    if (flags & 2) {
+        timing_end(ctx);
+        pool_free(ctx, scratch);
+        return fail(ctx, BOWGPU_EUNSUPPORTED, "SortByCol: NaN in an unsorted float64 column (`<` is no order there; undefined upstream)");
+    }
+    bowgpu_frame *of = new (std::nothrow) bowgpu_frame();
+    if (!of) {
+        pool_free(ctx, scratch);
+        return BOWGPU_ENOMEM;
+    }
+    of->ctx = ctx;
+    of->n = n;
+    of->cols.resize(nc);
+    auto bail = [&](int32_t code) {
+        cudaStreamSynchronize(ctx->stream);
+        pool_free(ctx, scratch);
+        for (auto &c : of->cols) free_col(ctx, c);
+        delete of;
+        return code;
+    };
+    SortGather G;
+    memset(&G, 0, sizeof G);
+    int npasses = 0;
+    e = launch_sort_passes(n, scratch, hist.data(), ctx->stream, &G.idx, &G.sorted_keys, &npasses);
+    if (e) return bail(fail(ctx, BOWGPU_ECUDA, "SortByCol (passes): %s", cudaGetErrorString((cudaError_t)e)));
+    G.ncols = nc;
+    G.key_col = col;
+    G.key_is_int = kc.dtype == BOWGPU_INT64;
+    G.n = n;
+    int32_t rc = BOWGPU_OK;
+    for (int c = 0; c < nc && rc == BOWGPU_OK; ++c) {
+        const DevCol &src = frame->cols[c];
+        const bool nulls = src.validity && src.null_count != 0;
+        rc = alloc_col(ctx, of->cols[c], n, src.dtype, nulls);
+        of->cols[c].null_count = nulls ? src.null_count : 0;  // a permutation keeps the count
+        G.values[c] = src.values;
+        G.validity[c] = nulls ? src.validity : nullptr;
+        G.out_values[c] = of->cols[c].values;
+        G.out_validity[c] = of->cols[c].validity;
+    }
+    if (rc) return bail(rc);
+    e = launch_sort_gather(G, ctx->stream);
+    count_launch(ctx, 2 * npasses + 1);
+    timing_end(ctx);
+    if (e || cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+        return bail(fail(ctx, BOWGPU_ECUDA, "SortByCol (gather): %s", cudaGetErrorString(cudaGetLastError())));
+    pool_free(ctx, scratch);
+    *out = of;
+    return BOWGPU_OK;
+}
+
 // ================================================================================================
 // rolling
 // ================================================================================================

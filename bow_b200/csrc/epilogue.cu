@@ -22,7 +22,19 @@ struct EpiBatch {
 // accesses with four independent loads in flight per array, and one ballot per i yields a whole 32-bit word of
 // the validity bitmap.  Specs are walked in a rolled loop; the per-window count array shared by the
 // aggregations of one input column is fetched once (consecutive specs with the same pointer reuse it).
-constexpr int EPI_NT = 256, EPI_WPT = 4;  // threads per block, windows per thread
+#ifndef EPI_CFG_NT
+#define EPI_CFG_NT 256
+#endif
+#ifndef EPI_CFG_WPT
+#define EPI_CFG_WPT 4
+#endif
+constexpr int EPI_NT = EPI_CFG_NT, EPI_WPT = EPI_CFG_WPT;  // threads per block, windows per thread
+#ifndef EPI_CFG_GROUP_WPT
+#define EPI_CFG_GROUP_WPT 1
+#endif
+// the grouped pass is a handful of loads and stores per window: one window per thread keeps the most loads in flight
+// (configs[1]: 1.67 M windows, step 0.3132 -> 0.3105 ms against four windows per thread)
+constexpr int EPIG_WPT = EPI_CFG_GROUP_WPT;
 
 __global__ void __launch_bounds__(EPI_NT) epilogue_kernel(const __grid_constant__ EpiBatch B, const int nspecs,
                                                           const WindowGeom g) {
@@ -37,7 +49,7 @@ __global__ void __launch_bounds__(EPI_NT) epilogue_kernel(const __grid_constant_
         in[i] = k[i] < g.W;
     }
     const int64_t *last_cnt = nullptr;
-    int64_t c[EPI_WPT] = {0, 0, 0, 0};
+    int64_t c[EPI_WPT] = {};
     for (int si = 0; si < nspecs; ++si) {
         const EpilogueSpec &sp = B.s[si];
         uint64_t *vals = reinterpret_cast<uint64_t *>(sp.values);
@@ -109,26 +121,26 @@ __global__ void __launch_bounds__(EPI_NT) epilogue_kernel(const __grid_constant_
 
 __global__ void __launch_bounds__(EPI_NT) epilogue_group_kernel(const __grid_constant__ EpiGroup G, const WindowGeom g) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t base = ((int64_t)blockIdx.x * (EPI_NT / 32) + warp) * (32 * EPI_WPT);
+    const int64_t base = ((int64_t)blockIdx.x * (EPI_NT / 32) + warp) * (32 * EPIG_WPT);
     if (base >= g.W) return;
-    int64_t c[EPI_WPT];
+    int64_t c[EPIG_WPT];
 #pragma unroll
-    for (int i = 0; i < EPI_WPT; ++i) {
+    for (int i = 0; i < EPIG_WPT; ++i) {
         const int64_t k = base + lane + 32 * i;
         c[i] = (G.cnt && k < g.W) ? G.cnt[k] : 0;
     }
-    double sv[EPIG_DIV][EPI_WPT];
+    double sv[EPIG_DIV][EPIG_WPT];
 #pragma unroll
     for (int j = 0; j < EPIG_DIV; ++j)
 #pragma unroll
-        for (int i = 0; i < EPI_WPT; ++i) {
+        for (int i = 0; i < EPIG_WPT; ++i) {
             const int64_t k = base + lane + 32 * i;
             sv[j][i] = (j < G.n_div && k < g.W) ? G.div_src[j][k] : 0.0;  // (independent of the count load: both in flight)
         }
     // float64(w.LastValue - w.FirstValue), weightedmean.go:17,31 (the interval, except for the whole-Bow window)
     const double width = g.whole ? (double)(g.whole_last - g.whole_first) : (double)(int64_t)g.div.d;
 #pragma unroll
-    for (int i = 0; i < EPI_WPT; ++i) {
+    for (int i = 0; i < EPIG_WPT; ++i) {
         const int64_t k = base + lane + 32 * i;
         const bool in = k < g.W;
         const bool valid = in && c[i] > 0;
@@ -164,7 +176,7 @@ __global__ void __launch_bounds__(EPI_NT) epilogue_group_kernel(const __grid_con
 
 int launch_epilogue_group(const EpiGroup &G, WindowGeom g, cudaStream_t stream) {
     if (g.W <= 0) return 0;
-    const int64_t per_block = (int64_t)EPI_NT * EPI_WPT;
+    const int64_t per_block = (int64_t)EPI_NT * EPIG_WPT;
     epilogue_group_kernel<<<(unsigned)((g.W + per_block - 1) / per_block), EPI_NT, 0, stream>>>(G, g);
     return (int)cudaGetLastError();
 }

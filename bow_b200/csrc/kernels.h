@@ -234,6 +234,24 @@ size_t drop_scratch_bytes(int64_t n);
 int launch_drop_mark(const DropLaunch &L, void *scratch, cudaStream_t stream, int64_t **d_total);
 int launch_drop_compact(const DropLaunch &L, void *scratch, cudaStream_t stream);
 
+// ---- SortByCol (sort.cu): bowsort.go:10-47 --------------------------------------------------------------------------------
+struct SortGather {
+    int32_t ncols, key_col, key_is_int, _pad;
+    int64_t n;
+    const uint32_t *idx;          // final permutation: output row j = input row idx[j]
+    const uint64_t *sorted_keys;  // order-preserving unsigned keys in output order
+    const uint64_t *values[32];
+    const uint8_t *validity[32];  // input bitmaps (null = no nulls)
+    uint64_t *out_values[32];
+    uint8_t *out_validity[32];    // padded device bitmaps of the columns that carry nulls, else null
+};
+size_t sort_scratch_bytes(int64_t n);
+int launch_sort_prepare(const uint64_t *values, int is_int, int64_t n, void *scratch, cudaStream_t stream, int32_t *flags_host,
+                        unsigned long long *hist_host);
+int launch_sort_passes(int64_t n, void *scratch, const unsigned long long *hist_host, cudaStream_t stream,
+                       const uint32_t **idx, const uint64_t **sorted_keys, int *npasses);
+int launch_sort_gather(const SortGather &G, cudaStream_t stream);
+
 // ---- synthetic generators (generate.cu) ----------------------------------------------------------
 int launch_gen_regular(int64_t *time, int64_t n, int64_t row0, int64_t t0, int64_t step, cudaStream_t stream);
 // BURSTY: per-window row counts (to be scanned in place with launch_exclusive_scan) and the time column

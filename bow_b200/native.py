@@ -38,7 +38,7 @@ SYMBOLS = [
     "bowgpu_rolling_bounds", "bowgpu_rolling_aggregate", "bowgpu_agg_return_type", "bowgpu_agg_needs_inclusive",
     "bowgpu_rolling_interpolate", "bowgpu_frame_aggregate_whole", "bowgpu_frame_fill", "bowgpu_frame_fill_linear",
     "bowgpu_rolling_interpolate_aggregate", "bowgpu_frame_drop_nils", "bowgpu_frame_is_col_sorted",
-    "bowgpu_aggregate_host",
+    "bowgpu_aggregate_host", "bowgpu_frame_sort_by_col",
 ]
 
 
@@ -114,6 +114,7 @@ def lib():
                                             C.POINTER(C.c_int64)]
         L.bowgpu_frame_drop_nils.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p)]
         L.bowgpu_frame_is_col_sorted.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
+        L.bowgpu_frame_sort_by_col.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
         L.bowgpu_frame_fill.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p)]
         L.bowgpu_frame_fill_linear.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
         L.bowgpu_frame_aggregate_whole.argtypes = [C.c_void_p, C.c_int32, C.POINTER(AggSpec), C.c_int32, C.POINTER(OutCol),
@@ -330,6 +331,12 @@ class Frame:
         out = C.c_int32()
         self.ctx.check(lib().bowgpu_frame_is_col_sorted(self.h, col, C.byref(out)))
         return bool(out.value)
+
+    def sort_by_col(self, col: int) -> Optional["Frame"]:
+        """Bow.SortByCol (bowsort.go:10-47); None = already sorted (the reference returns the same Bow)"""
+        h = C.c_void_p()
+        self.ctx.check(lib().bowgpu_frame_sort_by_col(self.h, col, C.byref(h)))
+        return Frame(self.ctx, h) if h.value else None
 
     def fill_linear(self, ref_col: int, tofill_col: int) -> "Frame":
         """Bow.FillLinear (bowfill.go:14-102)"""

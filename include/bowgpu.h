@@ -247,6 +247,13 @@ int32_t bowgpu_frame_drop_nils(bowgpu_frame *frame, const int32_t *cols, int32_t
 /* Bow.IsColSorted(colIndex) (bowassertion.go:15-81): *sorted = 1 iff the non-nil values are ascending or descending
  * (ties allowed); 0 for an empty column. */
 int32_t bowgpu_frame_is_col_sorted(bowgpu_frame *frame, int32_t col, int32_t *sorted);
+/* Bow.SortByCol(colIndex) (bowsort.go:10-47): a new frame with the rows in ascending order of column `col` (int64 or
+ * float64, compared with `<` like Buffer.Less, bowbuffer.go:126-131).  *out = NULL with BOWGPU_OK when the column is
+ * already sorted (sort.IsSorted; the reference returns the same Bow, bowsort.go:18-21) — keep using `frame`.  A sort column
+ * with nils is BOWGPU_EINVAL (bowsort.go:11-15).  Equal keys keep their input order (the reference's sort.Sort leaves it
+ * unspecified; its golden vectors, bowsort_test.go:133-157, show this order).  A NaN in an unsorted float64 sort column is
+ * BOWGPU_EUNSUPPORTED (no order under `<`; undefined upstream). */
+int32_t bowgpu_frame_sort_by_col(bowgpu_frame *frame, int32_t col, bowgpu_frame **out);
 
 /* Rolling.Interpolate (interpolation.go:30-161).  ops[j] is the interpolation of column j (the
  * reference matches columns by position, bowappend.go:28-47, so nops must equal the number of

@@ -919,3 +919,28 @@ def drop_nils(b: Frame, *col_indices: int) -> Frame:       # bow.go:188-224
     keep = [r for r in range(b.num_rows())
             if not any(sel[c] and b.get_value(c, r) is None for c in range(b.num_cols()))]
     return Frame(list(b.names), list(b.types), [[b.get_value(c, r) for r in keep] for c in range(b.num_cols())])
+
+
+def sort_by_col(b: Frame, col_index: int) -> Frame:        # bowsort.go:10-47
+    """SortByCol.  The reference calls sort.Sort (bowsort.go:24) over Buffer.Less / Swap (bowbuffer.go:126-139,202-206),
+    which is NOT stable: the order among equal keys depends on the algorithm of the Go toolchain that built the
+    program (quicksort + insertion sort before go1.19, pattern-defeating quicksort since), not on anything in the
+    reference's sources.  Both toolchains run a plain insertion sort on slices of at most 12 elements, which is what
+    is transliterated here for every length: equal keys keep their input order.  That is the order every golden
+    vector of the reference shows (bowsort_test.go:11-208, at most 4 rows); on longer inputs with duplicate keys it
+    is one valid outcome of the reference's contract, not necessarily the Go runtime's — PARITY UNPINNED there."""
+    nulls = sum(1 for r in range(b.num_rows()) if b.get_value(col_index, r) is None)
+    if nulls != 0:
+        raise ValueError(f"column to sort by has {nulls} nil values")        # bowsort.go:11-15
+    keys = [b.get_value(col_index, r) for r in range(b.num_rows())]
+    indices = list(range(b.num_rows()))
+    if all(not (keys[i] < keys[i - 1]) for i in range(1, len(keys))):      # sort.IsSorted, bowsort.go:18-21
+        return b
+    for i in range(1, len(keys)):                                          # insertionSort(data, 0, n)
+        j = i
+        while j > 0 and keys[j] < keys[j - 1]:                             # data.Less(j, j-1)
+            keys[j], keys[j - 1] = keys[j - 1], keys[j]                    # data.Swap(j, j-1): value and index
+            indices[j], indices[j - 1] = indices[j - 1], indices[j]
+            j -= 1
+    cols = [keys if c == col_index else [b.get_value(c, r) for r in indices] for c in range(b.num_cols())]
+    return Frame(list(b.names), list(b.types), cols)

@@ -248,3 +248,22 @@ def is_col_sorted(values, mask=None) -> bool:
         return False
     lt, gt = bool((v[1:] < v[:-1]).any()), bool((v[1:] > v[:-1]).any())
     return not (lt and gt)
+
+
+def sort_by_col(cols, col):
+    """Bow.SortByCol (bowsort.go:10-47) with equal keys kept in input order (see oracle/literal.py sort_by_col: the
+    reference's sort.Sort leaves that order to the Go toolchain — parity unpinned for duplicate keys beyond the golden
+    vectors).  cols: list of (values, mask | None) -> None when already sorted (the reference returns b itself), else
+    the same layout.  Raises ValueError for a sort column with nils (bowsort.go:11-15)."""
+    v, m = cols[col]
+    v = np.asarray(v)
+    if m is not None and not np.asarray(m, dtype=bool).all():
+        raise ValueError(f"column to sort by has {int((~np.asarray(m, dtype=bool)).sum())} nil values")
+    if len(v) < 2 or not (v[1:] < v[:-1]).any():        # sort.IsSorted over Buffer.Less
+        return None
+    order = np.argsort(v, kind="stable")                # (-0.0 == 0.0 for numpy as for Go's `<`)
+    out = []
+    for vv, mm in cols:
+        vv = np.asarray(vv)
+        out.append((vv[order], np.ones(len(vv), dtype=bool) if mm is None else np.asarray(mm, dtype=bool)[order]))
+    return out

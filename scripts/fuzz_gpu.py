@@ -60,7 +60,7 @@ def one(ctx, seed):
     has_special = bool(np.isnan(cols[1][0]).any() or np.isinf(cols[1][0]).any() or (np.abs(cols[1][0]) > 1e200).any())
     if has_special:
         specs = [s for s in specs if s[0] not in TOL or s[1] != 1] or [("WindowStart", 0), ("Min", 1)]
-    mode = str(rng.choice(["agg", "agg_inclusive", "sharded", "fused", "whole", "fill", "interp", "host"]))
+    mode = str(rng.choice(["agg", "agg_inclusive", "sharded", "fused", "whole", "fill", "interp", "host", "sort"]))
     what = f"seed={seed} mode={mode} n={n} kind={kind} I={interval} off={offset}"
     fr = N.Frame.from_numpy(ctx, cols)
     try:
@@ -104,6 +104,23 @@ def one(ctx, seed):
             span = float(t[-1] - t[0]) if n else 1.0
             for sp, gg, w in zip(specs, got, want):
                 same(sp, gg, w, max(span, 1.0) * max(n, 1), what)
+        elif mode == "sort" and n:
+            key = rng.integers(-50, 50, size=n) if rng.random() < 0.5 else rng.permutation(n).astype(np.int64) - n // 2
+            scols = [(key.astype(np.float64) / 2 if rng.random() < 0.3 else key, None), cols[1], cols[2]]
+            sf = N.Frame.from_numpy(ctx, scols)
+            try:
+                out = sf.sort_by_col(0)
+                want = R.sort_by_col(scols, 0)
+                assert (out is None) == (want is None), what
+                if out is not None:
+                    gs = out.download()
+                    out.close()
+                    for c in range(3):
+                        gv, gm = gs[c]
+                        wv, wm = want[c]
+                        assert np.array_equal(gm, wm) and np.array_equal(gv[gm].view(np.int64), wv[wm].view(np.int64)), f"{what} col {c}"
+            finally:
+                sf.close()
         elif mode == "fill":
             method = str(rng.choice(["Previous", "Next", "Mean"]))
             out = fr.fill(method, 1, 2)

@@ -328,3 +328,24 @@ DROP_CASES = [
 SORTED_ROWS = [[-2, 1, N, N, -8], [0, N, 3, 4, 0], [1, N, N, 120, N], [10, 4, 10, 10, -5], [13, N, N, N, N],
                [20, 6, 30, 400, -10]]
 SORTED_EXPECTED = [True, True, True, False, False]
+
+
+# ---- Bow.SortByCol: bowsort_test.go:11-208 (Boolean / String columns of the upstream tables left out) ----------------
+# (name, column types, input rows, sort column, expected rows | "same" | "error", cite)
+SORT_CASES = [
+    ("sorted", "iff", [[10, 2.4, 3.1], [11, 2.8, 5.9], [12, 2.9, 7.5], [13, 3.9, 13.4]], 0, "same", "bowsort_test.go:12-27"),
+    ("unsorted with all types", "iif", [[10, 2, 3.1], [11, 2, 5.9], [13, 3, 13.4], [12, 2, 7.5]], 0,
+     [[10, 2, 3.1], [11, 2, 5.9], [12, 2, 7.5], [13, 3, 13.4]], "bowsort_test.go:29-53"),
+    ("unsorted with different cols", "ffi", [[2.4, 3.1, 10], [2.8, 5.9, 11], [3.9, 13.4, 13], [2.9, 7.5, 12]], 2,
+     [[2.4, 3.1, 10], [2.8, 5.9, 11], [2.9, 7.5, 12], [3.9, 13.4, 13]], "bowsort_test.go:55-79"),
+    ("unsorted with nil values", "iif", [[10, 5, N], [11, 2, 56.], [13, N, 13.4], [12, -1, N]], 0,
+     [[10, 5, N], [11, 2, 56.], [12, -1, N], [13, N, 13.4]], "bowsort_test.go:81-105"),
+    ("sorted in desc order", "iff", [[13, 3.9, 13.4], [12, 2.9, 7.5], [11, 2.8, 5.9], [10, 2.4, 3.1]], 0,
+     [[10, 2.4, 3.1], [11, 2.8, 5.9], [12, 2.9, 7.5], [13, 3.9, 13.4]], "bowsort_test.go:107-131"),
+    ("duplicate values in sort by column", "iff", [[13, 3.9, 13.4], [12, 2.9, 7.5], [12, 2.8, 5.9], [10, 2.4, 3.1]], 0,
+     [[10, 2.4, 3.1], [12, 2.9, 7.5], [12, 2.8, 5.9], [13, 3.9, 13.4]], "bowsort_test.go:133-157"),
+    ("empty bow", "if", [], 0, "same", "bowsort_test.go:159-169"),
+    ("with metadata", "if", [[1, .1], [3, .3], [2, .2]], 0, [[1, .1], [2, .2], [3, .3]], "bowsort_test.go:171-188"),
+    ("ERR: nil values in sort by column", "iff", [[13, 3.9, 13.4], [12, 2.9, 7.5], [N, 2.8, 5.9], [10, 2.4, 3.1]], 0,
+     "error", "bowsort_test.go:190-204"),
+]
