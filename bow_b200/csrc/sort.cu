@@ -20,7 +20,13 @@ namespace bowgpu {
 namespace {
 
 constexpr int SORT_NT = 256, SORT_NW = SORT_NT / 32;
-constexpr int SORT_ITEMS = 16;
+#ifndef SORT_CFG_ITEMS
+#define SORT_CFG_ITEMS 16
+#endif
+#ifndef SORT_CFG_MINB
+#define SORT_CFG_MINB 2
+#endif
+constexpr int SORT_ITEMS = SORT_CFG_ITEMS;
 constexpr int SORT_TILE = SORT_NT * SORT_ITEMS;
 constexpr uint64_t SORT_AGG = 1ull << 62, SORT_INCL = 1ull << 63, SORT_VAL = SORT_AGG - 1;
 constexpr uint64_t SIGN = 0x8000000000000000ull;
@@ -78,34 +84,50 @@ __global__ void __launch_bounds__(SORT_NT) sort_prepare_kernel(const uint64_t *v
 
 // One digit.  kin/vin -> kout/vout; vin == null means the identity permutation (first pass).  digit_base[256] is the
 // exclusive prefix of this digit's histogram; status[ntiles][256] (zeroed) carries the per-tile digit counts.
-__global__ void __launch_bounds__(SORT_NT) sort_pass_kernel(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
+// The tile is put in digit order in shared memory first, so that a warp's stores cover a few contiguous runs of the
+// output instead of 32 different buckets (and pages).
+__global__ void __launch_bounds__(SORT_NT, SORT_CFG_MINB) sort_pass_kernel(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
                                                             uint64_t *__restrict__ kout, uint32_t *__restrict__ vout,
                                                             const int64_t n, const int shift,
                                                             const unsigned long long *__restrict__ digit_base,
                                                             volatile unsigned long long *status, uint32_t *ticket) {
     __shared__ uint32_t cnt[SORT_NW][257];  // (slot 256: rows beyond the end of the column)
-    __shared__ uint64_t gbase[256];
+    __shared__ uint64_t gadj[256];          // output position of tile slot s holding digit d = gadj[d] + s
+    __shared__ uint32_t tile_off[256];      // first tile slot of digit d
+    __shared__ uint32_t wsum[SORT_NW];
     __shared__ uint32_t s_tile;
+    __shared__ uint64_t xch[SORT_TILE];     // the tile in digit order: keys, then the permutation entries
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);
     for (int i = tid; i < SORT_NW * 257; i += SORT_NT) (&cnt[0][0])[i] = 0;
     __syncthreads();
     const int64_t tile = s_tile;
     const int64_t base = tile * SORT_TILE + (int64_t)warp * (32 * SORT_ITEMS) + lane;
+    const int64_t left = n - tile * SORT_TILE;
+    const int nvalid = left < SORT_TILE ? (int)left : SORT_TILE;
 
+    // keys and the permutation entries that travel with them: all loads of the tile in flight before the ranking starts
     uint64_t key[SORT_ITEMS];
-    uint32_t rank[SORT_ITEMS];
+    uint32_t val[SORT_ITEMS];
+    uint32_t rank[SORT_ITEMS];  // the warp peers of the row (same digit), then its rank among the tile's rows of that digit, then its slot
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; ++i) {
         const int64_t idx = base + i * 32;
         key[i] = idx < n ? kin[idx] : ~0ull;
+        val[i] = vin ? (idx < n ? vin[idx] : 0u) : (uint32_t)idx;
     }
     const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {  // (independent of each other: the matches pipeline)
+        const int64_t idx = base + i * 32;
+        const uint32_t d = idx < n ? (uint32_t)(key[i] >> shift) & 255u : 256u;
+        rank[i] = __match_any_sync(0xffffffffu, d);
+    }
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; ++i) {
         const int64_t idx = base + i * 32;
         const uint32_t d = idx < n ? (uint32_t)(key[i] >> shift) & 255u : 256u;
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t peers = rank[i];
         const int leader = __ffs(peers) - 1;
         uint32_t old = 0;
         if (lane == leader) {
@@ -118,31 +140,30 @@ __global__ void __launch_bounds__(SORT_NT) sort_pass_kernel(const uint64_t *__re
     }
     __syncthreads();
 
-    {   // thread t owns digit t: exclusive scan over the warps, then the tile's place among the tiles
-        const int t = tid;
-        uint32_t run = 0;
+    // thread t owns digit t: exclusive scan over the warps (-> cnt), over the digits (-> tile_off), publish the tile's count
+    const int t = tid;
+    uint32_t run = 0;
 #pragma unroll
-        for (int w = 0; w < SORT_NW; ++w) {
-            const uint32_t c = cnt[w][t];
-            cnt[w][t] = run;
-            run += c;
-        }
-        volatile unsigned long long *mine = status + tile * 256 + t;
-        uint64_t excl = 0;
-        if (tile > 0) {
-            *mine = SORT_AGG | run;
-            for (int64_t p = tile - 1;; --p) {
-                volatile unsigned long long *q = status + p * 256 + t;
-                unsigned long long s;
-                while ((s = *q) == 0) {
-                }
-                excl += s & SORT_VAL;
-                if (s & SORT_INCL) break;
-            }
-        }
-        *mine = SORT_INCL | (excl + run);
-        gbase[t] = digit_base[t] + excl;
+    for (int w = 0; w < SORT_NW; ++w) {
+        const uint32_t c = cnt[w][t];
+        cnt[w][t] = run;
+        run += c;
     }
+    volatile unsigned long long *mine = status + tile * 256 + t;
+    if (tile > 0) *mine = SORT_AGG | run;
+    uint32_t incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    uint32_t toff = incl - run;
+#pragma unroll
+    for (int w = 0; w < SORT_NW; ++w)
+        if (w < warp) toff += wsum[w];
+    tile_off[t] = toff;
     __syncthreads();
 
 #pragma unroll
@@ -150,10 +171,46 @@ __global__ void __launch_bounds__(SORT_NT) sort_pass_kernel(const uint64_t *__re
         const int64_t idx = base + i * 32;
         if (idx < n) {
             const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
-            const uint64_t pos = gbase[d] + cnt[warp][d] + rank[i];
-            kout[pos] = key[i];
-            vout[pos] = vin ? vin[idx] : (uint32_t)idx;
+            rank[i] += tile_off[d] + cnt[warp][d];
+            xch[rank[i]] = key[i];
         }
+    }
+
+    {   // the tile's place among the tiles: decoupled look-back over the counts of digit t
+        uint64_t excl = 0;
+        if (tile > 0) {
+            for (int64_t p = tile - 1;; --p) {
+                volatile unsigned long long *q = status + p * 256 + t;
+                unsigned long long sv;
+                while ((sv = *q) == 0) {
+                }
+                excl += sv & SORT_VAL;
+                if (sv & SORT_INCL) break;
+            }
+        }
+        *mine = SORT_INCL | (excl + run);
+        gadj[t] = digit_base[t] + excl - toff;
+    }
+    __syncthreads();
+
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        const int sl = tid + SORT_NT * i;
+        if (sl < nvalid) {
+            key[i] = xch[sl];
+            kout[gadj[(uint32_t)(key[i] >> shift) & 255u] + sl] = key[i];
+        }
+    }
+    __syncthreads();
+    uint32_t *xv = reinterpret_cast<uint32_t *>(xch);
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i)
+        if (base + i * 32 < n) xv[rank[i]] = val[i];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        const int sl = tid + SORT_NT * i;
+        if (sl < nvalid) vout[gadj[(uint32_t)(key[i] >> shift) & 255u] + sl] = xv[sl];
     }
 }
 

@@ -53,7 +53,7 @@ def report(name, n, secs, alg_bytes, extra=None):
 
 def main():
     ctx = N.Ctx(0)
-    which = sys.argv[1:] or ["1", "1b", "2", "3", "4", "fill"]
+    which = sys.argv[1:] or ["1", "1b", "2", "3", "4", "fill", "sort"]
     if "1" in which or "1b" in which:
         for tag, n in (("1", int(1e8 * SCALE)), ("1b", int(1e9 * SCALE))):
             if tag not in which:
@@ -158,6 +158,34 @@ def main():
         dt = timed(ctx, run_lin, reps=3, warm=1)
         report("FillLinear(time, value) incl. IsColSorted of the reference column", n, dt, 8 * n + 16 * n + 2 * n // 8 + 2 * 16 * n)
         fr.close()
+    if "sort" in which:   # Bow.SortByCol (bowsort.go) — shuffled ns timestamps + 2 value columns
+        n = int(1e8 * SCALE)
+        perm = torch.randperm(n, device="cuda")
+        t = 1_700_000_000_000_000_000 + perm * SEC
+        v0 = torch.rand(n, dtype=torch.float64, device="cuda")
+        v1 = torch.randint(0, 1 << 20, (n,), dtype=torch.int64, device="cuda")
+        del perm
+        arr = (N.Col * 3)()
+        for j, (x, dt_) in enumerate(((t, N.INT64), (v0, N.FLOAT64), (v1, N.INT64))):
+            arr[j].values, arr[j].validity, arr[j].offset, arr[j].length, arr[j].null_count, arr[j].dtype = \
+                x.data_ptr(), None, 0, n, 0, dt_
+        torch.cuda.synchronize()
+        fr = N.Frame.from_col_descs(ctx, arr, 3, N.MEM_DEVICE, keep=[t, v0, v1])
+        for col, what in ((0, "shuffled int64 ns timestamps (5 varying digits)"), (1, "uniform float64 keys (8 digits)"),
+                          (2, "20-bit int64 keys (3 digits)")):
+            def run():
+                out = fr.sort_by_col(col)
+                out.close()
+            dt = timed(ctx, run, reps=3, warm=1)
+            report(f"SortByCol, 3 columns, by {what}", n, dt, 2 * 3 * 8 * n)
+        fr.close()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            ks, order = torch.sort(t, stable=True)
+            g0, g1 = v0[order], v1[order]
+        torch.cuda.synchronize()
+        report("(context) torch.sort(stable) + 2 gathers of the same timestamps", n, (time.perf_counter() - t0) / 3, 2 * 3 * 8 * n)
 
 
 if __name__ == "__main__":
