@@ -21,10 +21,10 @@ namespace {
 
 constexpr int SORT_NT = 256, SORT_NW = SORT_NT / 32;
 #ifndef SORT_CFG_ITEMS
-#define SORT_CFG_ITEMS 16
+#define SORT_CFG_ITEMS 12
 #endif
 #ifndef SORT_CFG_MINB
-#define SORT_CFG_MINB 2
+#define SORT_CFG_MINB 3
 #endif
 constexpr int SORT_ITEMS = SORT_CFG_ITEMS;
 constexpr int SORT_TILE = SORT_NT * SORT_ITEMS;
