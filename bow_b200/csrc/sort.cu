@@ -214,6 +214,24 @@ __global__ void __launch_bounds__(SORT_NT, SORT_CFG_MINB) sort_pass_kernel(const
     }
 }
 
+// 8-byte load of a randomly placed element; SORT_CFG_GATHER_HINT selects the L2 prefetch-size qualifier (0 = plain load)
+#ifndef SORT_CFG_GATHER_HINT
+#define SORT_CFG_GATHER_HINT 64
+#endif
+__device__ __forceinline__ uint64_t gather_u64(const uint64_t *p) {
+#if SORT_CFG_GATHER_HINT == 64
+    uint64_t v;
+    asm volatile("ld.global.L2::64B.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+#elif SORT_CFG_GATHER_HINT == 1
+    return __ldcs(p);
+#elif SORT_CFG_GATHER_HINT == 2
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
 // Every column through the permutation.  A warp owns 64 consecutive output rows (two per lane), so each ballot is one
 // whole 32-bit word of an output bitmap; the permutation entry is loaded once for all columns.
 __global__ void __launch_bounds__(256) sort_gather_kernel(const __grid_constant__ SortGather G) {
@@ -238,7 +256,7 @@ __global__ void __launch_bounds__(256) sort_gather_kernel(const __grid_constant_
             const int64_t j = wbase + 32 * u + lane;
             bool ok = in[u];
             if (in[u]) {
-                dv[j] = from_keys ? G.sorted_keys[j] ^ SIGN : sv[src[u]];
+                dv[j] = from_keys ? G.sorted_keys[j] ^ SIGN : gather_u64(sv + src[u]);
                 if (sm) ok = (sm[src[u] >> 3] >> (src[u] & 7)) & 1;
             }
             if (G.out_validity[c]) {  // padded device bitmap: whole words
