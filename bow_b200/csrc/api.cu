@@ -1541,7 +1541,7 @@ extern "C" int32_t bowgpu_rolling_interpolate(bowgpu_rolling *r, const int32_t *
         return fail(ctx, BOWGPU_EINVAL, "interpolations must name every column in schema order (%d given, %d columns)", nops, ncols);
     if (ncols > INTERP_MAX_COLS) return fail(ctx, BOWGPU_EUNSUPPORTED, "interpolate supports at most %d columns", INTERP_MAX_COLS);
     for (int j = 0; j < nops; ++j) {  // validateInterpolation, interpolation.go:71-96
-        if (ops[j] < 0 || ops[j] > BOWGPU_INTERP_NONE) return fail(ctx, BOWGPU_EUNSUPPORTED, "interpolation %d: unknown opcode %d", j, ops[j]);
+        if (ops[j] < 0 || ops[j] > BOWGPU_INTERP_STEP_NEXT) return fail(ctx, BOWGPU_EUNSUPPORTED, "interpolation %d: unknown opcode %d", j, ops[j]);
         if (ops[j] == BOWGPU_INTERP_WINDOW_START && f->cols[j].dtype != BOWGPU_INT64)
             return fail(ctx, BOWGPU_ETYPE, "interpolation %d: WindowStart accepts types [int64], got type float64", j);
     }
@@ -1695,7 +1695,7 @@ extern "C" int32_t bowgpu_rolling_interpolate_aggregate(bowgpu_rolling *r, const
         return fail(ctx, BOWGPU_EINVAL, "interpolations must name every column in schema order (%d given, %d columns)", nops, ncols);
     if (ncols > INTERP_MAX_COLS) return fail(ctx, BOWGPU_EUNSUPPORTED, "interpolate supports at most %d columns", INTERP_MAX_COLS);
     for (int j = 0; j < nops; ++j) {
-        if (ops[j] < 0 || ops[j] > BOWGPU_INTERP_NONE) return fail(ctx, BOWGPU_EUNSUPPORTED, "interpolation %d: unknown opcode %d", j, ops[j]);
+        if (ops[j] < 0 || ops[j] > BOWGPU_INTERP_STEP_NEXT) return fail(ctx, BOWGPU_EUNSUPPORTED, "interpolation %d: unknown opcode %d", j, ops[j]);
         if (ops[j] == BOWGPU_INTERP_WINDOW_START && f->cols[j].dtype != BOWGPU_INT64)
             return fail(ctx, BOWGPU_ETYPE, "interpolation %d: WindowStart accepts types [int64], got type float64", j);
     }

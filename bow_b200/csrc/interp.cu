@@ -95,6 +95,14 @@ __global__ void interp_window_kernel(const InterpLaunch P) {
             }
             break;
         }
+        case BOWGPU_INTERP_STEP_NEXT: {  // not upstream: StepPrevious mirrored over GetNextValues (bowgetters.go:111-123)
+            const int64_t nx = next_valid(c.validity, first_index, g.n);
+            if (nx >= 0) {
+                bits = c.values[nx];
+                valid = true;
+            }
+            break;
+        }
         case BOWGPU_INTERP_LINEAR: {  // interpolation/linear.go:8-38
             double t0, v0;
             const int64_t p = prev_valid(c.validity, first_index - 1);

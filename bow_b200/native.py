@@ -21,7 +21,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 
 AGG = dict(WindowStart=0, Count=1, Sum=2, ArithmeticMean=3, Min=4, Max=5, First=6, Last=7,
            IntegralStep=8, IntegralTrapezoid=9, WeightedAverageStep=10, WeightedAverageLinear=11)
-INTERP = dict(WindowStart=0, Linear=1, StepPrevious=2, None_=3)
+INTERP = dict(WindowStart=0, Linear=1, StepPrevious=2, None_=3, StepNext=4)
 FILL = dict(Previous=0, Next=1, Mean=2, Linear=3)
 STATUS = {0: "OK", 1: "EINVAL", 2: "ETYPE", 3: "EFIRSTNULL", 4: "EPREVROW", 5: "ENOINTERVALCOL", 6: "ECAPACITY",
           7: "EUNSORTED", 8: "ENULLTIME", 9: "ECUDA", 10: "ENOMEM", 11: "EUNSUPPORTED"}

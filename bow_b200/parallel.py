@@ -120,7 +120,7 @@ def plan_interpolate_for_columns(cols: Sequence[NpCol], time_col: int, interval:
     n = len(time)
     if n == 0:
         return P.plan(0, 0, 0, interval, offset, n_shards, lambda x: 0), 0
-    need = [j for j, o in enumerate(ops) if str(o) in ("Linear", "StepPrevious", "1", "2")]
+    need = [j for j, o in enumerate(ops) if str(o) in ("Linear", "StepPrevious", "StepNext", "1", "2", "4")]
     pv, nv = halo_searches(cols, need)
     off = P.normalise_offset(interval, offset)
     s0 = P.first_window_start(int(time[0]), interval, off)

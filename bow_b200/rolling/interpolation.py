@@ -1,6 +1,7 @@
 """rolling/interpolation: the built-in ColInterpolation constructors (reference rolling/interpolation/*.go).
 `None` is spelled `None_` (Python keyword).  The north-star's `StepNext` does not exist upstream
- and is not provided: its parity would be unpinned."""
+(SURVEY section 0); it is provided as the mirror image of StepPrevious over the reference's GetNextValues getter,
+with its parity marked unpinned."""
 from __future__ import annotations
 
 from .. import bow as B
@@ -10,6 +11,12 @@ from . import ColInterpolation
 
 def WindowStart(colName: str) -> ColInterpolation:     # windowstart.go:8-14
     return ColInterpolation(colName, [B.Int64], None, kernel_op=N.INTERP["WindowStart"])
+
+
+def StepNext(colName: str) -> ColInterpolation:
+    """Named by the north-star, not in the reference: StepPrevious mirrored over Bow.GetNextValues
+    (bowgetters.go:111-123) - the next valid value at or after the window's first row, else nil.  Parity unpinned."""
+    return ColInterpolation(colName, [B.Int64, B.Float64, B.Boolean, B.String], None, kernel_op=N.INTERP["StepNext"])
 
 
 def Linear(colName: str) -> ColInterpolation:          # linear.go:8-38

@@ -71,7 +71,11 @@ enum {
     BOWGPU_INTERP_WINDOW_START = 0,  /* interpolation.WindowStart   windowstart.go:8-14   */
     BOWGPU_INTERP_LINEAR = 1,        /* interpolation.Linear        linear.go:8-38        */
     BOWGPU_INTERP_STEP_PREVIOUS = 2, /* interpolation.StepPrevious  stepprevious.go:8-26  */
-    BOWGPU_INTERP_NONE = 3           /* interpolation.None          none.go:8-14          */
+    BOWGPU_INTERP_NONE = 3,          /* interpolation.None          none.go:8-14          */
+    BOWGPU_INTERP_STEP_NEXT = 4      /* named by the north-star, NOT in the reference: the mirror image of StepPrevious over
+                                      * the reference's own getter Bow.GetNextValues (bowgetters.go:111-123) — the value of
+                                      * the first row at or after the window's first row whose time and value are both valid,
+                                      * else nil.  Parity unpinned (no upstream implementation, no golden vectors). */
 };
 
 /* ---- memory spaces of the pointers inside a bowgpu_col / bowgpu_out_col --------------- */

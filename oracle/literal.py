@@ -11,8 +11,9 @@ import anything under `oracle/`.  The product (`bow_b200/`) never does.
 
 Parity status: PINNED — replays every in-scope golden vector of the reference's
 own tests (see tests/golden/reference_vectors.py and tests/test_oracle_golden.py).
-`interpolation.StepNext` named by the north-star does not exist upstream; it is
-not implemented here (parity would be unpinned).
+`interpolation.StepNext` named by the north-star does not exist upstream; InterpStepNext
+restates it as StepPrevious mirrored over Bow.GetNextValues — PARITY UNPINNED for that one
+function (no upstream code, no golden vectors).
 
 Arithmetic conventions restated from Go/amd64:
   * int64 `/` and `%` truncate toward zero                (go spec; rolling.go:96,119)
@@ -175,6 +176,15 @@ class Frame:
                 return v, r
             r -= 1
         return None, -1
+
+    def get_next_values(self, c1: int, c2: int, r: int):     # bowgetters.go:111-123
+        while 0 <= r < self.num_rows():
+            v1, r = self.get_next_value(c1, r)
+            v2, r2 = self.get_next_value(c2, r)
+            if r == r2:
+                return v1, v2, r
+            r += 1
+        return None, None, -1
 
     def get_prev_values(self, c1: int, c2: int, r: int):     # bowgetters.go:93-107
         while 0 <= r < self.num_rows():
@@ -707,6 +717,17 @@ def InterpStepPrevious(col: str) -> ColInterpolation:     # interpolation/steppr
         if v is not None:
             state["prev"] = v
         return state["prev"]
+    return ColInterpolation(col, [INT64, FLOAT64, "bool", "utf8"], fn)
+
+
+def InterpStepNext(col: str) -> ColInterpolation:
+    """NOT in the reference (rolling/interpolation/ holds Linear, None, StepPrevious, WindowStart): named by the
+    north-star.  Defined as the mirror image of StepPrevious (stepprevious.go:8-26) over the reference's own getter
+    Bow.GetNextValues (bowgetters.go:111-123): the value of the first row at or after the window's first row where
+    interval column and value are both valid, else nil; PrevRow plays no part.  PARITY UNPINNED (no golden vectors)."""
+    def fn(c, w, full, prev_row):
+        _, v, _ = full.get_next_values(w.interval_col_index, c, w.first_index)
+        return v
     return ColInterpolation(col, [INT64, FLOAT64, "bool", "utf8"], fn)
 
 

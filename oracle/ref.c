@@ -49,6 +49,7 @@ enum {
     BOWREF_INTERP_LINEAR = 1,
     BOWREF_INTERP_STEP_PREVIOUS = 2,
     BOWREF_INTERP_NONE = 3,
+    BOWREF_INTERP_STEP_NEXT = 4, /* not upstream (north-star): StepPrevious mirrored over GetNextValues */
 };
 enum {
     BOWREF_OK = 0,
@@ -572,6 +573,11 @@ static ref_value interp_closure(const bowref_rolling *r, int op, int col, const 
             return pc->dtype == BOWREF_INT64 ? int_value(col_raw(pc, 0)) : float_value(raw_as_f64(col_raw(pc, 0)));
         }
         return nil_value();
+    }
+    case BOWREF_INTERP_STEP_NEXT: { /* no upstream closure: Bow.GetNextValues(intervalCol, col, w.FirstIndex), bowgetters.go:111-123 */
+        int64_t nx = next_both_valid(t, c, w->first_index, r->nrows);
+        if (nx < 0) return nil_value();
+        return c->dtype == BOWREF_INT64 ? int_value(col_raw(c, nx)) : float_value(raw_as_f64(col_raw(c, nx)));
     }
     case BOWREF_INTERP_LINEAR: { /* interpolation/linear.go:8-38 (stateless equivalent) */
         double t0, v0;

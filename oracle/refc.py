@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(HERE, "libbowref.so")
 FLOAT64, INT64 = 1, 2
 AGG = dict(WindowStart=0, Count=1, Sum=2, ArithmeticMean=3, Min=4, Max=5, First=6, Last=7,
            IntegralStep=8, IntegralTrapezoid=9, WeightedAverageStep=10, WeightedAverageLinear=11)
-INTERP = dict(WindowStart=0, Linear=1, StepPrevious=2, None_=3)
+INTERP = dict(WindowStart=0, Linear=1, StepPrevious=2, None_=3, StepNext=4)
 ERRORS = {1: "EINVAL", 2: "ETYPE", 3: "EFIRSTNULL", 4: "EPREVROW", 5: "ENOINTERVALCOL", 6: "ECAPACITY"}
 
 

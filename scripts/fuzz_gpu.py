@@ -83,7 +83,7 @@ def one(ctx, seed):
             for sp, gg, w in zip(specs, PP.concat_outputs(per), want):
                 same(sp, gg, w, interval, what)
         elif mode in ("fused", "interp") and n:
-            ops = ["WindowStart", str(rng.choice(["Linear", "StepPrevious", "None_"])), str(rng.choice(["Linear", "StepPrevious"]))]
+            ops = ["WindowStart", str(rng.choice(["Linear", "StepPrevious", "None_", "StepNext"])), str(rng.choice(["Linear", "StepPrevious", "StepNext"]))]
             ref = R.RefRolling(R.Frame(cols), 0, interval, offset=offset)
             icols = ref.interpolate(ops)
             r = N.Rolling(fr, 0, interval, offset=offset)

@@ -218,6 +218,17 @@ INTERPOLATIONS = [
     ("none no options", "None", _TWO, 0, [(10, 1.0), (12, N), (13, 1.3)], "none_test.go:24-42"),
     ("none with offset", "None", _TWO, 1, [(9, N), (10, 1.0), (11, N), (13, 1.3)], "none_test.go:44-63"),
 ]
+# NOT from the reference: interpolation.StepNext does not exist upstream (the north-star names it).  Tables derived
+# BY HAND from the StepPrevious tables above under the definition "value of the first row at or after the window's
+# first row where time and value are valid" (Bow.GetNextValues, bowgetters.go:111-123) — they pin our own three
+# implementations (literal, C, CUDA) on each other, not on the reference.
+INTERPOLATIONS_STEPNEXT = [
+    ("stepnext no options", "StepNext", _TWO, 0, [(10, 1.0), (12, 1.3), (13, 1.3)], "hand-derived"),
+    ("stepnext with offset", "StepNext", _TWO, 1, [(9, 1.0), (10, 1.0), (11, 1.3), (13, 1.3)], "hand-derived"),
+    ("stepnext with nils", "StepNext", [(10, 1.0), (11, N), (13, N), (15, 1.5)], 0,
+     [(10, 1.0), (11, N), (12, 1.5), (13, N), (14, 1.5), (15, 1.5)], "hand-derived"),
+    ("stepnext nothing after", "StepNext", [(10, 1.0), (13, N)], 0, [(10, 1.0), (12, N), (13, N)], "hand-derived"),
+]
 # rolling/interpolation/windowstart_test.go:13-64 — single-column bow {10,13}
 INTERP_WINDOWSTART = [
     ("windowstart no options", [10, 13], 0, [10, 12, 13]),

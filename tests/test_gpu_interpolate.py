@@ -69,7 +69,7 @@ def test_random_interpolate_vs_oracle(ctx, kind, n):
         b = H.random_values(rng, n, np.int64, [0.2, 0.0, 0.6, 0.0, 0.97][trial])
         c = H.random_values(rng, n, np.float64, 0.4)
         cols = [a, (t, None), b, c]           # interval column in the middle
-        ops = ["Linear", "WindowStart", ["StepPrevious", "Linear"][trial % 2], ["None_", "StepPrevious"][trial % 2]]
+        ops = ["Linear", "WindowStart", ["StepPrevious", "Linear", "StepNext"][trial % 3], ["None_", "StepPrevious", "StepNext"][(trial + 1) % 3]]
         interval = int(rng.choice([1, 2, 5, 10, 60, 1000]))
         offset = int(rng.integers(-2 * interval, 2 * interval))
         inclusive = trial == 3
@@ -238,8 +238,8 @@ def test_fused_interpolate_aggregate_vs_oracle(ctx, kind, n):
         cols = [(t, None), H.random_values(rng, n, np.float64, float(rng.choice([0.0, 0.3, 0.9])), specials=n < 100),
                 H.random_values(rng, n, np.int64, float(rng.choice([0.0, 0.5]))),
                 H.random_values(rng, n, np.float64, 0.2)]
-        ops = ["WindowStart", str(rng.choice(["Linear", "StepPrevious", "None_"])), str(rng.choice(["Linear", "StepPrevious"])),
-               "Linear"]
+        ops = ["WindowStart", str(rng.choice(["Linear", "StepPrevious", "None_", "StepNext"])),
+               str(rng.choice(["Linear", "StepPrevious", "StepNext"])), "Linear"]
         prev = [(np.array([995], dtype=np.int64), None), (np.array([0.5]), None), (np.array([4], dtype=np.int64), None),
                 (np.array([-1.0]), None)] if trial else None
         specs = [("WindowStart", 0), ("Count", 0)] + [(a, c) for c in (1, 2, 3) for a in ALL_AGGS]

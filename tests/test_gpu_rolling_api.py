@@ -94,7 +94,8 @@ def test_aggregate_host_transformation_and_cursor():
                             "got <nil>")
 
 
-@pytest.mark.parametrize("name,kind,rows,offset,expected,cite", G.INTERPOLATIONS, ids=[c[0] for c in G.INTERPOLATIONS])
+@pytest.mark.parametrize("name,kind,rows,offset,expected,cite", G.INTERPOLATIONS + G.INTERPOLATIONS_STEPNEXT,
+                         ids=[c[0] for c in G.INTERPOLATIONS + G.INTERPOLATIONS_STEPNEXT])
 def test_interpolations(name, kind, rows, offset, expected, cite):  # interpolation/*_test.go
     fn = interpolation.None_ if kind == "None" else getattr(interpolation, kind)
     r = rolling.IntervalRolling(rows_bow(rows), G.TIME, 2, rolling.Options(Offset=offset))

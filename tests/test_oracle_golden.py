@@ -123,8 +123,8 @@ def test_interpolate_driver_errors():
     assert e.value.args[0] == G.INTERP_DRIVER_ERRORS[1][1]
 
 
-@pytest.mark.parametrize("name,kind,rows,offset,expected,cite", G.INTERPOLATIONS,
-                         ids=[c[0] for c in G.INTERPOLATIONS])
+@pytest.mark.parametrize("name,kind,rows,offset,expected,cite", G.INTERPOLATIONS + G.INTERPOLATIONS_STEPNEXT,
+                         ids=[c[0] for c in G.INTERPOLATIONS + G.INTERPOLATIONS_STEPNEXT])
 def test_interpolations(name, kind, rows, offset, expected, cite):
     r = L.IntervalRolling.create(frame_rows(rows), G.TIME, 2, L.Options(offset=offset))
     out = r.interpolate(L.InterpWindowStart(G.TIME), getattr(L, "Interp" + kind)(G.VALUE)).bow

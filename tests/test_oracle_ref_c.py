@@ -13,7 +13,8 @@ from tests.golden import reference_vectors as G
 AGG_NAMES = ["WindowStart", "Count", "Sum", "ArithmeticMean", "Min", "Max", "First", "Last",
              "IntegralStep", "IntegralTrapezoid", "WeightedAverageStep", "WeightedAverageLinear"]
 LIT_INTERP = {"WindowStart": L.InterpWindowStart, "Linear": L.InterpLinear,
-              "StepPrevious": L.InterpStepPrevious, "None_": L.InterpNone}
+              "StepPrevious": L.InterpStepPrevious, "None_": L.InterpNone,
+              "StepNext": L.InterpStepNext}
 
 
 def ref_rows(frame_cols, interval, aggs, **opts):
@@ -59,8 +60,8 @@ def test_aggregations_golden(agg, fixture, factor, vtype, expected, cite):
     H.assert_cols_equal(out, [[r[0] for r in expected], [r[1] for r in expected]], cite)
 
 
-@pytest.mark.parametrize("name,kind,rows,offset,expected,cite", G.INTERPOLATIONS,
-                         ids=[c[0] for c in G.INTERPOLATIONS])
+@pytest.mark.parametrize("name,kind,rows,offset,expected,cite", G.INTERPOLATIONS + G.INTERPOLATIONS_STEPNEXT,
+                         ids=[c[0] for c in G.INTERPOLATIONS + G.INTERPOLATIONS_STEPNEXT])
 def test_interpolations_golden(name, kind, rows, offset, expected, cite):
     cols = H.np_cols_from_lists([[r[0] for r in rows], [r[1] for r in rows]], [L.INT64, L.FLOAT64])
     r = R.RefRolling(R.Frame(cols), 0, 2, offset=offset)
@@ -153,8 +154,8 @@ def test_interpolate_vs_literal(seed):
     if cols[0][1] is not None and not cols[0][1][-1]:
         pytest.skip("trailing null timestamp: the reference panics in AppendBows on the nil window bows")
     rng = np.random.default_rng(1000 + seed)
-    ops = ["WindowStart", str(rng.choice(["Linear", "StepPrevious", "None_"])),
-           str(rng.choice(["Linear", "StepPrevious", "None_"]))]
+    ops = ["WindowStart", str(rng.choice(["Linear", "StepPrevious", "None_", "StepNext"])),
+           str(rng.choice(["Linear", "StepPrevious", "None_", "StepNext"]))]
     r = R.RefRolling(R.Frame(cols, offset=seed % 2 * 3), 0, interval, offset=offset, inclusive=inclusive,
                      prev_row=R.Frame(prev) if prev else None)
     got = H.lists_from_np(r.interpolate(ops))

@@ -145,6 +145,7 @@ def test_two_rank_gloo_gather():
 
 # ---- Rolling.Interpolate across shards -------------------------------------------------------------------------
 OPS = ["WindowStart", "Linear", "StepPrevious"]
+OPS_NEXT = ["WindowStart", "StepNext", "Linear"]
 
 
 def oracle_interp_executor(cols, time_col, interval, s0, num_windows, inclusive, ops, prev_row):
@@ -171,9 +172,10 @@ def oracle_interp_executor(cols, time_col, interval, s0, num_windows, inclusive,
     return [(v[lo:hi], m[lo:hi]) for v, m in out]
 
 
+@pytest.mark.parametrize("OPS", [OPS, OPS_NEXT], ids=["prev", "next"])
 @pytest.mark.parametrize("kind", ["regular", "sparse", "bursty"])
 @pytest.mark.parametrize("g", [1, 2, 5])
-def test_sharded_interpolate_matches_unsharded(kind, g):
+def test_sharded_interpolate_matches_unsharded(kind, g, OPS):
     rng = np.random.default_rng(H.seed_of((kind, g, "i")))
     for n, interval in ((1, 5), (40, 3), (6000, 7), (20000, 300)):
         t = H.random_times(rng, n, kind)
