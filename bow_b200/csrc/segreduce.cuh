@@ -64,6 +64,15 @@ namespace bowgpu {
 // [NT][P + 2] with a padded pitch: the same conflict-free LDS.128, but no padding columns through the TMA unit (the
 // staging pattern alone moves 7.1 TB/s swizzled against 6.6 TB/s padded, profiles/r1_box_stream_microbench.txt).
 constexpr bool SEG_SWZ = SEG_CFG_SWZ != 0;
+#ifndef SEG_CFG_FUSED_COLD
+#define SEG_CFG_FUSED_COLD 2
+#endif
+#ifndef SEG_CFG_FUSED_EXPECT
+#define SEG_CFG_FUSED_EXPECT 1
+#endif
+#ifndef SEG_CFG_FUSED_PREFETCH
+#define SEG_CFG_FUSED_PREFETCH 1
+#endif
 constexpr int SEG_UNROLL = SEG_CFG_UNROLL;  // row pairs per trip of the streaming loop
 constexpr int SEG_NT = SEG_CFG_NT;
 constexpr int SEG_P = 16;                     // rows per phase (box start columns must be 16-byte aligned in global memory)
@@ -165,6 +174,47 @@ __device__ __forceinline__ typename Pol::Inc fused_boundary(const SegArgs<Pol> &
     return inc;
 }
 
+// Out-of-line copy for the streaming loop: a window boundary is a rare event there (once per window), and the inlined
+// body in each of the loop's four row slots pushed the fused kernel out of the instruction cache (configs[2]: 1.025 ms
+// per column pass at 2.5e8 rows against 0.787 ms for the unfused kernel).
+template <class Pol>
+__device__ __noinline__ typename Pol::Inc fused_boundary_cold(const SegArgs<Pol> &A, const uint64_t kcur, const uint64_t knew,
+                                                              const int64_t x, const uint64_t raw, const bool valid,
+                                                              typename Pol::State &fresh) {
+    return fused_boundary<Pol>(A, kcur, true, knew, x, raw, valid, fresh);
+}
+
+// SEG_CFG_FUSED_COLD == 2: the whole close of a window in the streaming loop out of line — inclusive row, empty windows,
+// and the head capture / window write.  The head window and its inclusive row are handed over by address, which parks
+// them in local memory while the rows stream: they are written once per thread and tile and read once before the stitch,
+// but as registers they cost the fused streaming loop 14 register moves PER ROW (ptxas ping-pongs the merged copies
+// around the branch; ncu: 27 % of the kernel's instructions on the line of the boundary test).
+template <class Pol>
+__device__ __noinline__ typename Pol::State fused_close_cold(const SegArgs<Pol> &A, const uint64_t kold, const uint64_t knew,
+                                                             const int64_t x, const uint64_t raw, const bool valid,
+                                                             const typename Pol::State st, typename Pol::State *head,
+                                                             typename Pol::Inc *inc_head, const int nclose) {
+    typename Pol::State fresh;
+    const typename Pol::Inc inc = fused_boundary<Pol>(A, kold, true, knew, x, raw, valid, fresh);
+    if (nclose == 0) {
+        *head = st;
+        *inc_head = inc;
+    } else {
+        Pol::write(A.out, A.g, (int64_t)kold, st, inc);
+    }
+    return fresh;
+}
+
+// In the fused kernel the state a new window starts from comes out of the boundary path (its synthetic row); without a
+// hint ptxas keeps the merge cheap on THAT side and pays ~17 register moves per row on the side where nothing happens.
+template <bool FUSED>
+__device__ __forceinline__ bool seg_rare(bool b) {
+#if SEG_CFG_FUSED_EXPECT
+    if (FUSED) return __builtin_expect(b, 0);
+#endif
+    return b;
+}
+
 // per-thread state that lives in registers across the phases of one tile
 template <class Pol>
 struct SegThread {
@@ -185,7 +235,8 @@ struct SegThread {
 // free of per-row existence predicates).
 template <class Pol, bool HAS_NULLS, bool FULL, bool FUSED>
 __device__ __forceinline__ void seg_phase(SegThread<Pol> &c, const SegArgs<Pol> &A, const int64_t r0, const int phase,
-                                          const uint8_t *slot, const uint32_t *bsm, bool &bad) {
+                                          const uint8_t *slot, const uint32_t *bsm, bool &bad,
+                                          typename Pol::State *fhead, typename Pol::Inc *finc) {
     using Inc = typename Pol::Inc;
     constexpr int P = SEG_P;
     const int tid = threadIdx.x;
@@ -231,6 +282,16 @@ __device__ __forceinline__ void seg_phase(SegThread<Pol> &c, const SegArgs<Pol> 
         c.first_raw = va.x;
         c.first_flags = EDGE_HAS | ((vbits & 1u) ? EDGE_VALID : 0u);
         c.xlast = ta.x;
+#if SEG_CFG_FUSED_PREFETCH
+        if (FUSED) {  // the synthetic row of the next window: what the boundary path will ask for, pulled towards the SM now
+            const uint64_t kn = c.kf + 1;
+            if (kn < (uint64_t)A.syn.len) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(A.syn.missing + kn));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(A.syn.val + kn));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(A.syn.ok + kn));
+            }
+        }
+#endif
     }
 
     int segstart = 0;  // first row of this phase that belongs to the open window
@@ -241,7 +302,7 @@ __device__ __forceinline__ void seg_phase(SegThread<Pol> &c, const SegArgs<Pol> 
         if (FULL || j < nmine) {
             bad |= xj < c.xlast;
             c.xlast = xj;
-            if (xj >= c.eabs) {  // row j starts a later window: the open one is complete
+            if (seg_rare<FUSED>(xj >= c.eabs)) {  // row j starts a later window: the open one is complete
                 Pol::note(c.st, vbits & ((1u << j) - 1u) & ~((1u << segstart) - 1u), trow, vrow, swz);
                 if (!FUSED) {
                     const Inc inc = Pol::make_inc(xj == c.eabs, (vbits >> j) & 1u, rj, xj);
@@ -270,8 +331,17 @@ __device__ __forceinline__ void seg_phase(SegThread<Pol> &c, const SegArgs<Pol> 
                         c.kcur = div_slow((uint64_t)xj - (uint64_t)g.s0, d, g.div.inv_rd);
                         c.eabs = (int64_t)((uint64_t)g.s0 + (c.kcur + 1) * d);
                     }
+#if SEG_CFG_FUSED_COLD == 2
+                    c.st = fused_close_cold<Pol>(A, kold, c.kcur, xj, rj, (vbits >> j) & 1u, c.st, fhead, finc, c.nclose);
+                    ++c.nclose;
+                    segstart = j;
+#else
                     typename Pol::State fresh;
+#if SEG_CFG_FUSED_COLD
+                    const Inc inc = fused_boundary_cold<Pol>(A, kold, c.kcur, xj, rj, (vbits >> j) & 1u, fresh);
+#else
                     const Inc inc = fused_boundary<Pol>(A, kold, true, c.kcur, xj, rj, (vbits >> j) & 1u, fresh);
+#endif
                     if (c.nclose == 0) {
                         c.head = c.st;
                         c.inc_head = inc;
@@ -281,6 +351,7 @@ __device__ __forceinline__ void seg_phase(SegThread<Pol> &c, const SegArgs<Pol> 
                     ++c.nclose;
                     c.st = fresh;
                     segstart = j;
+#endif
                 }
             }
             if ((vbits >> j) & 1u) Pol::accumulate(c.st, xj, rj);
@@ -488,6 +559,9 @@ __global__ void __launch_bounds__(SEG_NT, MIN_CTAS)
         c.kf = c.kcur = 0;
         c.eabs = 0;
         c.xlast = 0;
+        // fused kernel: the head window of the thread is parked in local memory while the rows stream (fused_close_cold)
+        typename Pol::State fhead = Pol::identity();
+        typename Pol::Inc finc = Pol::make_inc(false, false, 0, 0);
 #pragma unroll 1
         for (int phase = 0; phase < SEG_NP; ++phase, ++q) {
             const int s = (int)(q % nstages);
@@ -495,7 +569,7 @@ __global__ void __launch_bounds__(SEG_NT, MIN_CTAS)
             if (fullt) {
                 mbar_wait(&full[s], (parity >> s) & 1u);
                 parity ^= 1u << s;
-                seg_phase<Pol, HAS_NULLS, true, FUSED>(c, A, r0, phase, slot, bsm, bad);
+                seg_phase<Pol, HAS_NULLS, true, FUSED>(c, A, r0, phase, slot, bsm, bad, &fhead, &finc);
             } else {
                 // tile at an edge of the column (or holding rows before s0): staged by plain loads with bounds checks
                 int64_t *ts = reinterpret_cast<int64_t *>(slot);
@@ -514,7 +588,7 @@ __global__ void __launch_bounds__(SEG_NT, MIN_CTAS)
                     for (int w = tid; w < SEG_BITS_COPY / 4; w += SEG_NT) bw[w] = w < words_left ? src[w] : 0u;
                 }
                 __syncthreads();
-                seg_phase<Pol, HAS_NULLS, false, FUSED>(c, A, r0, phase, slot, bsm, bad);
+                seg_phase<Pol, HAS_NULLS, false, FUSED>(c, A, r0, phase, slot, bsm, bad, &fhead, &finc);
             }
             if (phase == 0 && (tid & 31) == 0) {  // publish my first row for the previous warp's last lane
                 WarpEdge e;
@@ -527,6 +601,10 @@ __global__ void __launch_bounds__(SEG_NT, MIN_CTAS)
             }
             __syncthreads();  // every read of this slot is done
             if (tid == 0) issue_item(q + nstages);
+        }
+        if (FUSED && SEG_CFG_FUSED_COLD == 2) {
+            c.head = fhead;
+            c.inc_head = finc;
         }
         if (fullt)
             seg_stitch<Pol, true, FUSED>(c, A, tile, wtot, wedge, bad);
