@@ -942,6 +942,30 @@ extern "C" int32_t bowgpu_frame_is_col_sorted(bowgpu_frame *frame, int32_t col, 
     return BOWGPU_OK;
 }
 
+// scratch for the validity pyramids of the columns whose interpolation looks up previous / next valid rows
+// (interp.cu); one stream-ordered block, released by the caller once the window kernel is enqueued
+static void *attach_pyramids(bowgpu_ctx *ctx, InterpLaunch &L, int64_t n) {
+    const size_t per = align_up(interp_pyramid_bytes(n), 256);
+    int need = 0;
+    for (int j = 0; j < L.ncols; ++j) {
+        const InterpCol &c = L.cols[j];
+        need += c.validity && (c.op == BOWGPU_INTERP_STEP_PREVIOUS || c.op == BOWGPU_INTERP_LINEAR || c.op == BOWGPU_INTERP_STEP_NEXT);
+    }
+    if (!need || n <= 4096) return nullptr;  // short columns: the word-by-word walk is bounded anyway
+    uint8_t *blk = nullptr;
+    if (pool_alloc(ctx, (void **)&blk, per * need) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;  // (the lookups fall back to walking the words)
+    }
+    int k = 0;
+    for (int j = 0; j < L.ncols; ++j) {
+        InterpCol &c = L.cols[j];
+        if (c.validity && (c.op == BOWGPU_INTERP_STEP_PREVIOUS || c.op == BOWGPU_INTERP_LINEAR || c.op == BOWGPU_INTERP_STEP_NEXT))
+            c.summary = (uint32_t *)(blk + per * k++);
+    }
+    return blk;
+}
+
 // Bow.SortByCol(colIndex) (bowsort.go:10-47): rows by ascending values of a nil-free column; *out = null when the column
 // is already sorted (the reference returns b itself, bowsort.go:18-21).  Stable radix sort on the device (sort.cu).
 extern "C" int32_t bowgpu_frame_sort_by_col(bowgpu_frame *frame, int32_t col, bowgpu_frame **out) {
@@ -1602,7 +1626,9 @@ extern "C" int32_t bowgpu_rolling_interpolate(bowgpu_rolling *r, const int32_t *
     B.first = d_first;
     B.status = ctx->d_status;
     int e = launch_bounds(B, ctx->sm_count, ctx->stream, nullptr, nullptr);
+    void *pyr = attach_pyramids(ctx, L, g.n);
     if (!e) e = launch_interp_windows(L, ctx->stream);
+    pool_free(ctx, pyr);
     if (!e) e = launch_exclusive_scan(L.off, W, scan_tmp, ctx->stream);
     count_launch(ctx, 5);
     int64_t total = 0;
@@ -1756,7 +1782,9 @@ extern "C" int32_t bowgpu_rolling_interpolate_aggregate(bowgpu_rolling *r, const
     B.first = d_first;
     B.status = ctx->d_status;
     int e = launch_bounds(B, ctx->sm_count, ctx->stream, nullptr, nullptr);
+    void *pyr = attach_pyramids(ctx, L, gx.n);
     if (!e) e = launch_interp_windows(L, ctx->stream);
+    pool_free(ctx, pyr);
     count_launch(ctx, 2);
     int32_t st = 0;
     if (e || cudaMemcpyAsync(&st, ctx->d_status, 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||

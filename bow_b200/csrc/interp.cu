@@ -19,32 +19,79 @@ namespace bowgpu {
 
 namespace {
 
-// ---- word-wise validity scans (GetPrev* / GetNext* of the reference, bowgetters.go:65-107,282-311) ------
-__device__ __forceinline__ int64_t prev_valid(const uint32_t *bm, int64_t i) {  // last valid row <= i, or -1
-    if (i < 0) return -1;
-    if (!bm) return i;
-    int64_t w = i >> 5;
-    uint32_t m = bm[w] & (0xFFFFFFFFu >> (31 - (int)(i & 31)));
-    while (true) {
-        if (m) return w * 32 + 31 - __clz(m);
-        if (--w < 0) return -1;
-        m = bm[w];
-    }
+// ---- validity lookups (GetPrev* / GetNext* of the reference, bowgetters.go:65-107,282-311) -------------
+// Word-wise on the bitmap; when the word of the row holds no answer the lookup climbs the summary pyramid (one word
+// per level) to the nearest non-empty word and descends again: O(levels) however long the null run is.  Without a
+// pyramid (summary == null) the words are walked one by one.
+struct Bits {
+    const uint32_t *bm;       // level 0
+    const uint32_t *summary;  // levels 1.. or null
+};
+__device__ __forceinline__ const uint32_t *pyr_level(const Bits &b, const ValidityPyramid &py, int l) {  // l >= 1
+    return b.summary + py.off[l - 1];
 }
-__device__ __forceinline__ int64_t next_valid(const uint32_t *bm, int64_t i, int64_t n) {  // first valid row >= i
-    if (i >= n) return -1;
-    if (!bm) return i;
-    const int64_t nw = (n + 31) >> 5;
-    int64_t w = i >> 5;
-    uint32_t m = bm[w] & (0xFFFFFFFFu << (int)(i & 31));
-    while (true) {
-        if (m) {
-            const int64_t r = w * 32 + __ffs(m) - 1;
-            return r < n ? r : -1;
-        }
-        if (++w >= nw) return -1;
-        m = bm[w];
+__device__ __noinline__ int64_t prev_valid_far(const Bits &b, const ValidityPyramid &py, int64_t w) {  // last non-zero word < w
+    if (!b.summary) {
+        while (--w >= 0)
+            if (b.bm[w]) return w * 32 + 31 - __clz(b.bm[w]);
+        return -1;
     }
+    int64_t idx = w;
+    for (int l = 1; l <= py.nlev; ++l) {
+        const int64_t ww = idx >> 5;
+        const int bit = (int)(idx & 31);
+        const uint32_t m = bit ? pyr_level(b, py, l)[ww] & ((1u << bit) - 1u) : 0u;
+        if (m) {
+            int64_t j = ww * 32 + 31 - __clz(m);
+            for (int ll = l - 1; ll >= 1; --ll) j = j * 32 + 31 - __clz(pyr_level(b, py, ll)[j]);
+            return j * 32 + 31 - __clz(b.bm[j]);
+        }
+        idx = ww;
+    }
+    return -1;
+}
+__device__ __noinline__ int64_t next_valid_far(const Bits &b, const ValidityPyramid &py, int64_t w, int64_t nw) {  // first non-zero word > w
+    if (!b.summary) {
+        while (++w < nw)
+            if (b.bm[w]) return w * 32 + __ffs(b.bm[w]) - 1;
+        return -1;
+    }
+    int64_t idx = w;
+    for (int l = 1; l <= py.nlev; ++l) {
+        const int64_t ww = idx >> 5;
+        const int bit = (int)(idx & 31);
+        const uint32_t m = bit < 31 ? pyr_level(b, py, l)[ww] & (0xFFFFFFFFu << (bit + 1)) : 0u;
+        if (m) {
+            int64_t j = ww * 32 + __ffs(m) - 1;
+            for (int ll = l - 1; ll >= 1; --ll) j = j * 32 + __ffs(pyr_level(b, py, ll)[j]) - 1;
+            return j * 32 + __ffs(b.bm[j]) - 1;
+        }
+        idx = ww;
+    }
+    return -1;
+}
+__device__ __forceinline__ int64_t prev_valid(const Bits &b, const ValidityPyramid &py, int64_t i) {  // last valid row <= i, or -1
+    if (i < 0) return -1;
+    if (!b.bm) return i;
+    const int64_t w = i >> 5;
+    const uint32_t m = b.bm[w] & (0xFFFFFFFFu >> (31 - (int)(i & 31)));
+    if (m) return w * 32 + 31 - __clz(m);
+    return prev_valid_far(b, py, w);
+}
+__device__ __forceinline__ int64_t next_valid(const Bits &b, const ValidityPyramid &py, int64_t i, int64_t n) {  // first valid row >= i
+    if (i >= n) return -1;
+    if (!b.bm) return i;
+    const int64_t w = i >> 5;
+    const uint32_t m = b.bm[w] & (0xFFFFFFFFu << (int)(i & 31));
+    const int64_t r = m ? w * 32 + __ffs(m) - 1 : next_valid_far(b, py, w, (n + 31) >> 5);
+    return r < n ? r : -1;
+}
+
+// level l+1 from level l: one ballot per 32 input words
+__global__ void pyramid_level_kernel(const uint32_t *in, const int64_t nin, uint32_t *out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t ball = __ballot_sync(0xffffffffu, i < nin && in[i] != 0);
+    if ((threadIdx.x & 31) == 0 && i < nin) out[i >> 5] = ball;
 }
 
 __global__ void interp_window_kernel(const InterpLaunch P) {
@@ -85,7 +132,7 @@ __global__ void interp_window_kernel(const InterpLaunch P) {
         case BOWGPU_INTERP_NONE:  // interpolation/none.go:8-14
             break;
         case BOWGPU_INTERP_STEP_PREVIOUS: {  // interpolation/stepprevious.go:8-26
-            const int64_t p = prev_valid(c.validity, first_index - 1);
+            const int64_t p = prev_valid(Bits{c.validity, c.summary}, P.pyr, first_index - 1);
             if (p >= 0) {
                 bits = c.values[p];
                 valid = true;
@@ -96,7 +143,7 @@ __global__ void interp_window_kernel(const InterpLaunch P) {
             break;
         }
         case BOWGPU_INTERP_STEP_NEXT: {  // not upstream: StepPrevious mirrored over GetNextValues (bowgetters.go:111-123)
-            const int64_t nx = next_valid(c.validity, first_index, g.n);
+            const int64_t nx = next_valid(Bits{c.validity, c.summary}, P.pyr, first_index, g.n);
             if (nx >= 0) {
                 bits = c.values[nx];
                 valid = true;
@@ -105,7 +152,7 @@ __global__ void interp_window_kernel(const InterpLaunch P) {
         }
         case BOWGPU_INTERP_LINEAR: {  // interpolation/linear.go:8-38
             double t0, v0;
-            const int64_t p = prev_valid(c.validity, first_index - 1);
+            const int64_t p = prev_valid(Bits{c.validity, c.summary}, P.pyr, first_index - 1);
             if (p >= 0) {
                 t0 = (double)t[p];
                 v0 = c.is_int ? (double)(int64_t)c.values[p] : bits_as_f64(c.values[p]);
@@ -115,7 +162,7 @@ __global__ void interp_window_kernel(const InterpLaunch P) {
             } else {
                 break;
             }
-            const int64_t nx = next_valid(c.validity, first_index, g.n);
+            const int64_t nx = next_valid(Bits{c.validity, c.summary}, P.pyr, first_index, g.n);
             if (nx < 0) break;
             const double t2 = (double)t[nx];
             const double v2 = c.is_int ? (double)(int64_t)c.values[nx] : bits_as_f64(c.values[nx]);
@@ -325,8 +372,45 @@ __global__ void __launch_bounds__(GA_NT, 4)
 
 }  // namespace
 
-int launch_interp_windows(const InterpLaunch &L, cudaStream_t stream) {
-    if (L.g.W <= 0) return 0;
+ValidityPyramid make_pyramid(int64_t n) {
+    ValidityPyramid py;
+    memset(&py, 0, sizeof py);
+    int64_t words = (n + 31) / 32, off = 0;
+    while (words > 1 && py.nlev < PYR_MAXLEV) {
+        words = (words + 31) / 32;
+        py.off[py.nlev] = off;
+        py.words[py.nlev] = words;
+        off += (words + 3) / 4 * 4;  // levels stay 16-byte aligned
+        ++py.nlev;
+    }
+    return py;
+}
+
+size_t interp_pyramid_bytes(int64_t n) {
+    const ValidityPyramid py = make_pyramid(n);
+    return py.nlev ? (size_t)(py.off[py.nlev - 1] + (py.words[py.nlev - 1] + 3) / 4 * 4) * 4 : 16;
+}
+
+int launch_interp_windows(const InterpLaunch &L0, cudaStream_t stream) {
+    if (L0.g.W <= 0) return 0;
+    InterpLaunch L = L0;
+    L.pyr = make_pyramid(L.g.n);
+    for (int j = 0; j < L.ncols; ++j) {
+        InterpCol &c = L.cols[j];
+        const bool looks = c.op == BOWGPU_INTERP_STEP_PREVIOUS || c.op == BOWGPU_INTERP_LINEAR || c.op == BOWGPU_INTERP_STEP_NEXT;
+        if (!looks || !c.validity || !c.summary || L.pyr.nlev == 0) {
+            c.summary = nullptr;
+            continue;
+        }
+        const uint32_t *in = c.validity;
+        int64_t nin = (L.g.n + 31) / 32;
+        for (int l = 0; l < L.pyr.nlev; ++l) {
+            uint32_t *out = c.summary + L.pyr.off[l];
+            pyramid_level_kernel<<<(unsigned)((nin + 255) / 256), 256, 0, stream>>>(in, nin, out);
+            in = out;
+            nin = L.pyr.words[l];
+        }
+    }
     const int nt = 128;
     interp_window_kernel<<<(unsigned)((L.g.W + nt - 1) / nt), nt, 0, stream>>>(L);
     return (int)cudaGetLastError();

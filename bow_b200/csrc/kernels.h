@@ -124,9 +124,23 @@ int launch_inclusive_bitmap(const int64_t *time, const int64_t *first, WindowGeo
 
 // ---- interpolate (interp.cu) ------------------------------------------------------------------------
 constexpr int INTERP_MAX_COLS = 32;
+// Summary pyramid over a validity bitmap: bit i of level l (l >= 1) = word i of level l-1 is non-zero (level 0 = the
+// bitmap).  Bounds the prev-valid / next-valid lookups of StepPrevious / Linear / StepNext to one word per level even
+// when a column holds null runs of millions of rows.  All levels of one column live in one buffer.
+constexpr int PYR_MAXLEV = 8;
+struct ValidityPyramid {
+    int32_t nlev;               // summary levels (0 = none: bitmaps of at most one word)
+    int32_t _pad;
+    int64_t off[PYR_MAXLEV];    // word offset of level l+1 inside the column's summary buffer
+    int64_t words[PYR_MAXLEV];  // its length in words
+};
+ValidityPyramid make_pyramid(int64_t n);
+size_t interp_pyramid_bytes(int64_t n);  // summary buffer of one column
 struct InterpCol {
     const uint64_t *values;    // input column
     const uint32_t *validity;  // input validity (bit offset 0) or null
+    uint32_t *summary;         // pyramid levels 1.. of `validity` (scratch of interp_pyramid_bytes(n), filled by
+                               // launch_interp_windows) or null = plain word-by-word scans
     uint64_t *syn_val;         // [W] value of the synthetic window-start row (scratch)
     uint8_t *syn_ok;           // [W] its validity
     uint64_t *out_values;      // [n_out]
@@ -150,6 +164,7 @@ struct InterpLaunch {
     int32_t inclusive;
     int32_t ncols;
     int32_t _pad;
+    ValidityPyramid pyr;   // (filled by launch_interp_windows)
     InterpCol cols[INTERP_MAX_COLS];
 };
 int launch_interp_windows(const InterpLaunch &L, cudaStream_t stream);

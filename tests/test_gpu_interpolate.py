@@ -274,3 +274,68 @@ def test_fused_falls_back_when_starts_are_inexact(ctx):
     icols = [(vv, None if mm.all() else mm) for vv, mm in ref.interpolate(ops)]
     want2 = R.RefRolling(R.Frame(icols), 0, interval, inclusive=True).aggregate(specs)
     assert_chain(got2, want2, specs, "inclusive", interval)
+
+
+# ---- long null runs: the prev-valid / next-valid lookups climb a summary pyramid instead of walking the bitmap ----------
+@pytest.mark.parametrize("pattern", ["ends", "middle", "none", "sparse"])
+def test_interpolate_long_null_runs_vs_oracle(ctx, pattern):
+    from bow_b200 import native as N
+    n, interval = 300_000, 100
+    rng = np.random.default_rng(H.seed_of("nullruns", pattern))
+    t = np.arange(n, dtype=np.int64) * 3 + 7          # no row sits on a window start: every window gets a start row
+    m = np.zeros(n, dtype=bool)
+    if pattern == "ends":
+        m[[0, n - 1]] = True
+    elif pattern == "middle":
+        m[n // 2 - 1] = m[n // 2 + 40_000] = True
+    elif pattern == "sparse":
+        m[rng.integers(0, n, size=12)] = True
+    a = (rng.standard_normal(n), m)
+    b = (rng.integers(-99, 99, size=n).astype(np.int64), m.copy())
+    c = (rng.standard_normal(n), np.roll(m, 12345))
+    cols = [(t, None), a, b, c]
+    ops = ["WindowStart", "StepPrevious", "Linear", "StepNext"]
+    fr = N.Frame.from_numpy(ctx, cols)
+    r = N.Rolling(fr, 0, interval)
+    out = r.interpolate(ops)
+    got = out.download()
+    out.close()
+    want = R.RefRolling(R.Frame(cols), 0, interval).interpolate(ops)
+    for j in range(4):
+        assert np.array_equal(got[j][1], want[j][1]), (pattern, j)
+        assert np.array_equal(got[j][0][got[j][1]].view(np.int64), want[j][0][want[j][1]].view(np.int64)), (pattern, j)
+    r.close()
+    fr.close()
+
+
+def test_interpolate_all_null_column_is_not_quadratic(ctx):
+    """5e7 rows, one valid value at each end, 5e5 windows: walking the bitmap word by word would read ~4e11 words"""
+    import os
+    import time
+    from bow_b200 import native as N
+    n = int(5e7 * float(os.environ.get("BOW_TEST_SCALE", "1")))
+    interval = 100
+    vals = np.zeros(n)
+    vals[0], vals[-1] = 0.25, 9.5
+    m = np.zeros(n, dtype=bool)
+    m[0] = m[-1] = True
+    time_col = np.arange(n, dtype=np.int64) * 2 + 7      # odd timestamps: no row sits on a window start
+    fr = N.Frame.from_numpy(ctx, [(time_col, None), (vals, m), (vals, m.copy()), (vals, m.copy())])
+    r = N.Rolling(fr, 0, interval)
+    ctx.synchronize()
+    t0 = time.perf_counter()
+    out = r.interpolate(["WindowStart", "StepPrevious", "StepNext", "Linear"])
+    ctx.synchronize()
+    dt = time.perf_counter() - t0
+    assert dt < 5.0, f"interpolate took {dt:.1f} s"
+    W = r.num_windows
+    n_out = out.num_rows
+    assert n_out == n + W               # every window gets a start row
+    got = out.download(n_out - 200, 200)
+    out.close()
+    r.close()
+    fr.close()
+    # the last window's start row: StepPrevious = the first value, StepNext = the last one, Linear in between
+    ts, (sp, spm), (sn, snm), (li, lim) = got[0][0], got[1], got[2], got[3]
+    k = np.flatnonzero(ts % interval == 0)[-1]
+    assert spm[k] and sp[k] == 0.25 and snm[k] and sn[k] == 9.5 and lim[k] and 0.25 < li[k] < 9.5
