@@ -135,7 +135,9 @@ __global__ void __launch_bounds__(EPI_NT) epilogue_group_kernel(const __grid_con
 #pragma unroll
         for (int i = 0; i < EPIG_WPT; ++i) {
             const int64_t k = base + lane + 32 * i;
-            sv[j][i] = (j < G.n_div && k < g.W) ? G.div_src[j][k] : 0.0;  // (independent of the count load: both in flight)
+            sv[j][i] = (j < G.n_div && k < g.W) ? G.div_src[j][k] : 0.0;  // (independent of the count load: both in flight;
+                                                                         // slots of windows without valid rows were never written - initcheck
+                                                                         // reports the read - and are discarded below: valid == false)
         }
     // float64(w.LastValue - w.FirstValue), weightedmean.go:17,31 (the interval, except for the whole-Bow window)
     const double width = g.whole ? (double)(g.whole_last - g.whole_first) : (double)(int64_t)g.div.d;
