@@ -201,7 +201,7 @@ def run_ours(args):
         for _ in range(max(args.warmup, 3)):
             step()
         ctx.synchronize()
-        ctx.enable_timing(2)
+        ctx.enable_timing(2)   # CUDA events around every 4th launch of the dominant kernel, on its own stream
         sampler = ClockSampler(local_rank if os.environ.get("CUDA_VISIBLE_DEVICES") is None else
                                int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
         sampler.start()
@@ -237,6 +237,7 @@ def run_ours(args):
                 traffic = None
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "kernel": "segreduce_basic_kernel", "kernel_ms": main_ms,
+                    "kernel_launches_timed": int(tm.main_launches),
                     "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                     "frac_of_nominal_8TBs": achieved / 8000.0}
 

@@ -134,8 +134,9 @@ void bowgpu_ctx_destroy(bowgpu_ctx *ctx);
 const char *bowgpu_last_error(const bowgpu_ctx *ctx);
 const char *bowgpu_status_string(int32_t status);
 int32_t bowgpu_ctx_synchronize(bowgpu_ctx *ctx);
-/* enable: 0 off, 1 = events of the last call, 2 = accumulate (main_ms, launches) over calls until
- * bowgpu_ctx_last_timing reads and resets them */
+/* enable: 0 off, 1 = events of the last call (total_ms, main_ms over all its main launches), 2 = accumulate over calls
+ * until bowgpu_ctx_last_timing reads and resets: `launches` counts every kernel, main_ms / main_launches cover every
+ * 4th launch of the dominant kernel only (events inside a timed loop are not free), total_ms is 0 */
 int32_t bowgpu_ctx_enable_timing(bowgpu_ctx *ctx, int32_t enable);
 int32_t bowgpu_ctx_last_timing(bowgpu_ctx *ctx, bowgpu_timing *out); /* synchronizes */
 int32_t bowgpu_ctx_sm_count(const bowgpu_ctx *ctx);
