@@ -140,7 +140,11 @@ __global__ void __launch_bounds__(EPI_NT) epilogue_group_kernel(const __grid_con
                                                                          // reports the read - and are discarded below: valid == false)
         }
     // float64(w.LastValue - w.FirstValue), weightedmean.go:17,31 (the interval, except for the whole-Bow window)
-    const double width = g.whole ? (double)(g.whole_last - g.whole_first) : (double)(int64_t)g.div.d;
+    bool by_width = false;
+#pragma unroll
+    for (int j = 0; j < EPIG_DIV; ++j) by_width |= j < G.n_div && !G.div_by_cnt[j];
+    double width = 1.0;  // (64-bit integer -> double conversions are not cheap: only when an output divides by the interval)
+    if (by_width) width = g.whole ? (double)(g.whole_last - g.whole_first) : (double)(int64_t)g.div.d;
 #pragma unroll
     for (int i = 0; i < EPIG_WPT; ++i) {
         const int64_t k = base + lane + 32 * i;
@@ -160,16 +164,14 @@ __global__ void __launch_bounds__(EPI_NT) epilogue_group_kernel(const __grid_con
         const uint32_t ball = __ballot_sync(0xffffffffu, valid);
         const uint32_t ball_in = __ballot_sync(0xffffffffu, in);
         const int64_t w0 = base + 32 * i;
-        if (lane == 0 && w0 < g.W) {
+        if (lane < G.n_bm_cnt + G.n_bm_all && w0 < g.W) {  // lane j stores the word of bitmap j
             const bool whole = w0 + 32 <= g.W;
-            for (int j = 0; j < G.n_bm_cnt + G.n_bm_all; ++j) {
-                uint8_t *bm = j < G.n_bm_cnt ? G.bm_cnt[j] : G.bm_all[j - G.n_bm_cnt];
-                const uint32_t word = j < G.n_bm_cnt ? ball : ball_in;
-                if (whole)
-                    *reinterpret_cast<uint32_t *>(bm + (w0 >> 3)) = word;
-                else
-                    for (int64_t b = 0; w0 + 8 * b < g.W; ++b) bm[(w0 >> 3) + b] = (uint8_t)(word >> (8 * b));
-            }
+            uint8_t *bm = lane < G.n_bm_cnt ? G.bm_cnt[lane] : G.bm_all[lane - G.n_bm_cnt];
+            const uint32_t word = lane < G.n_bm_cnt ? ball : ball_in;
+            if (whole)
+                *reinterpret_cast<uint32_t *>(bm + (w0 >> 3)) = word;
+            else
+                for (int64_t b = 0; w0 + 8 * b < g.W; ++b) bm[(w0 >> 3) + b] = (uint8_t)(word >> (8 * b));
         }
     }
 }
