@@ -81,9 +81,36 @@ int main(void) {
     ibad |= !(((ib[1][1] >> 0) & 1) && fabs(iv[8] - 11.0) < 1e-12);
     printf("interpolate: %s (%lld rows)\n", ibad ? "MISMATCH" : "ok", (long long)n_out);
 
+    /* Bow.SortByCol(0) on the reference's duplicate-key table (bowsort_test.go:133-157); NULL = already sorted */
+    int64_t st_[4] = {13, 12, 12, 10};
+    double sa[4] = {3.9, 2.9, 2.8, 2.4};
+    bowgpu_col scols[2];
+    memset(scols, 0, sizeof scols);
+    scols[0].values = st_, scols[0].length = 4, scols[0].dtype = BOWGPU_INT64;
+    scols[1].values = sa, scols[1].length = 4, scols[1].dtype = BOWGPU_FLOAT64;
+    bowgpu_frame *unsorted = NULL, *sorted = NULL, *again = NULL;
+    CHECK(bowgpu_frame_create(ctx, scols, 2, BOWGPU_MEM_HOST, &unsorted));
+    CHECK(bowgpu_frame_sort_by_col(unsorted, 0, &sorted));
+    int sbad = sorted == NULL;
+    if (!sbad) {
+        int64_t ot[4];
+        double oa[4];
+        uint8_t ob[2][1];
+        bowgpu_out_col sd[2] = {{ot, ob[0], 0, 0}, {oa, ob[1], 0, 0}};
+        CHECK(bowgpu_frame_download(sorted, sd, 2));
+        const int64_t want_st[4] = {10, 12, 12, 13};
+        const double want_sa[4] = {2.4, 2.9, 2.8, 3.9};
+        for (int i = 0; i < 4; ++i) sbad |= ot[i] != want_st[i] || oa[i] != want_sa[i];
+        CHECK(bowgpu_frame_sort_by_col(sorted, 0, &again));
+        sbad |= again != NULL;
+    }
+    printf("sort: %s\n", sbad ? "MISMATCH" : "ok");
+
+    bowgpu_frame_destroy(sorted);
+    bowgpu_frame_destroy(unsorted);
     bowgpu_frame_destroy(fi);
     bowgpu_rolling_destroy(r);
     bowgpu_frame_destroy(frame);
     bowgpu_ctx_destroy(ctx);
-    return (bad || ibad) ? 1 : 0;
+    return (bad || ibad || sbad) ? 1 : 0;
 }

@@ -16,4 +16,4 @@ def test_c_consumer_runs(tmp_path):
                            "-Wl,-rpath," + os.path.join(ROOT, "bow_b200"), "-lm"])
     p = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert p.returncode == 0, p.stdout + p.stderr
-    assert "aggregate: ok" in p.stdout and "interpolate: ok" in p.stdout
+    assert "aggregate: ok" in p.stdout and "interpolate: ok" in p.stdout and "sort: ok" in p.stdout
