@@ -1510,9 +1510,211 @@ static int32_t aggregate_core(bowgpu_rolling *r, const bowgpu_agg_spec *specs, i
     return check_status(ctx);
 }
 
+// Rolling.Aggregate on the segmc kernels (segmc.cuh): the input columns are grouped by (dtype, has nulls), every group is
+// ONE streaming launch that reads the time column once and each of its value columns once and writes the final values of
+// all their aggregations; launch_finish then derives the validity bitmap of every output, the WindowStart columns and the
+// zeros of windows without rows.
+static int32_t aggregate_core_mc(bowgpu_rolling *r, const bowgpu_agg_spec *specs, int32_t nspecs, bowgpu_out_col *outs,
+                                 int32_t mem, const FusedSyn *syn_by_col) {
+    if (!r || !specs || !outs || nspecs <= 0) return BOWGPU_EINVAL;
+    bowgpu_frame *f = r->frame;
+    bowgpu_ctx *ctx = f->ctx;
+    Guard gd(ctx);
+    const int ncols = (int)f->cols.size();
+    bool keeps_interval = false, inclusive_eff = r->inclusive != 0;
+    for (int j = 0; j < nspecs; ++j) {  // validateAggregation, aggregation.go:171-188
+        if (specs[j].col < 0 || specs[j].col >= ncols) return fail(ctx, BOWGPU_EINVAL, "aggregation %d: no column %d", j, specs[j].col);
+        if (specs[j].op < 0 || specs[j].op >= BOWGPU_AGG__COUNT) return fail(ctx, BOWGPU_EUNSUPPORTED, "aggregation %d: unknown opcode %d", j, specs[j].op);
+        if (specs[j].nfactors < 0 || specs[j].nfactors > 4) return fail(ctx, BOWGPU_EINVAL, "aggregation %d: at most 4 factors", j);
+        if (bowgpu_agg_needs_inclusive(specs[j].op)) inclusive_eff = true;
+        if (specs[j].col == r->time_col) keeps_interval = true;
+    }
+    if (!keeps_interval && !r->whole)
+        return fail(ctx, BOWGPU_ENOINTERVALCOL, "must keep interval column");  // aggregation.go:163-166
+    for (int j = 0; j < nspecs; ++j)
+        outs[j].dtype = r->whole ? whole_return_type(specs[j].op, f->cols[specs[j].col].dtype)
+                                 : bowgpu_agg_return_type(specs[j].op, f->cols[specs[j].col].dtype);
+    const WindowGeom g = make_geom(r, inclusive_eff);
+    const int64_t W = g.W;
+    if (W == 0) return BOWGPU_OK;
+
+    // ---- plan -------------------------------------------------------------------------------------------------------------
+    std::vector<int> cols_used;
+    for (int j = 0; j < nspecs; ++j) {
+        if (specs[j].op == BOWGPU_AGG_WINDOW_START) continue;
+        if (std::find(cols_used.begin(), cols_used.end(), specs[j].col) == cols_used.end()) cols_used.push_back(specs[j].col);
+    }
+    const size_t wv = align_up((size_t)W * 8, 256), wb = align_up((size_t)((W + 7) / 8) + 16, 256);
+    const size_t ww = align_up((size_t)((W + 31) / 32) * 4 + 16, 256);  // one bitmap, in words
+    const size_t rec_bytes = align_up((size_t)2 * mc_max_chunks(ctx->sm_count) * sizeof(McCarry), 256);
+    size_t need = 8192 + (1 + 2 * cols_used.size()) * (ww + 256) + cols_used.size() * (rec_bytes + 256);
+    if (mem == BOWGPU_MEM_HOST) need += (size_t)nspecs * (wv + wb + 512);
+    int32_t rc = arena_reserve(ctx, need);
+    if (rc) return rc;
+    arena_reset(ctx);
+    std::vector<void *> dvals(nspecs);
+    std::vector<uint8_t *> dbits(nspecs);
+    for (int j = 0; j < nspecs; ++j) {
+        if (mem == BOWGPU_MEM_DEVICE) {
+            dvals[j] = outs[j].values;
+            dbits[j] = outs[j].validity;
+        } else {
+            dvals[j] = arena_take(ctx, wv);
+            dbits[j] = (uint8_t *)arena_take(ctx, wb);
+        }
+        if (!dvals[j] || !dbits[j]) return fail(ctx, BOWGPU_EINVAL, "aggregation %d: null output buffer", j);
+    }
+    // bitmaps set by the streaming kernels: touched, then (valid rows, trapezoid defined) per used column - one memset
+    uint8_t *bm_base = (uint8_t *)arena_take(ctx, (1 + 2 * cols_used.size()) * ww);
+    if (!bm_base) return fail(ctx, BOWGPU_ENOMEM, "aggregate: scratch");
+    uint32_t *touched = (uint32_t *)bm_base;
+    timing_begin(ctx);
+    CK(cudaMemsetAsync(bm_base, 0, (1 + 2 * cols_used.size()) * ww, ctx->stream));
+
+    struct ColPlan {
+        int col;
+        McColArgs a;
+        uint32_t bops, iops;
+        int primary[BOWGPU_AGG__COUNT];
+    };
+    std::vector<ColPlan> plans(cols_used.size());
+    for (size_t u = 0; u < cols_used.size(); ++u) {
+        ColPlan &P = plans[u];
+        const int c = cols_used[u];
+        const DevCol &dc = f->cols[c];
+        P.col = c;
+        memset(&P.a, 0, sizeof P.a);
+        P.bops = P.iops = 0;
+        for (int o = 0; o < BOWGPU_AGG__COUNT; ++o) P.primary[o] = -1;
+        for (int j = 0; j < nspecs; ++j)  // the first spec of each op on this column receives the kernel output
+            if (specs[j].col == c && specs[j].op != BOWGPU_AGG_WINDOW_START && P.primary[specs[j].op] < 0) P.primary[specs[j].op] = j;
+        auto prim = [&](int op) -> void * { return P.primary[op] >= 0 ? dvals[P.primary[op]] : nullptr; };
+        P.a.values = dc.values;
+        P.a.validity = dc.validity;
+        McColOut &o = P.a.out;
+        o.cnt = (int64_t *)prim(BOWGPU_AGG_COUNT);
+        o.sum = (double *)prim(BOWGPU_AGG_SUM);
+        o.mean = (double *)prim(BOWGPU_AGG_MEAN);
+        o.mn = (double *)prim(BOWGPU_AGG_MIN);
+        o.mx = (double *)prim(BOWGPU_AGG_MAX);
+        o.first = (uint64_t *)prim(BOWGPU_AGG_FIRST);
+        o.last = (uint64_t *)prim(BOWGPU_AGG_LAST);
+        o.step = (double *)prim(BOWGPU_AGG_INTEGRAL_STEP);
+        o.wstep = (double *)prim(BOWGPU_AGG_WAVG_STEP);
+        o.trap = (double *)prim(BOWGPU_AGG_INTEGRAL_TRAPEZOID);
+        o.wlin = (double *)prim(BOWGPU_AGG_WAVG_LINEAR);
+        o.vb_cnt = (uint32_t *)(bm_base + (1 + 2 * u) * ww);
+        o.vb_trap = (uint32_t *)(bm_base + (2 + 2 * u) * ww);
+        if (o.cnt || o.sum || o.mean) P.bops |= MC_SUM;
+        if (o.mn || o.mx) P.bops |= MC_SUM | MC_MINMAX;
+        if (o.first || o.last) P.bops |= MC_SUM | MC_MINMAX | MC_FIRSTLAST;
+        if (o.step || o.wstep) P.iops |= MC_STEP;
+        if (o.trap || o.wlin) P.iops |= MC_TRAP;
+        if (syn_by_col) P.a.syn = syn_by_col[c];
+        P.a.rec = (McCarry *)arena_take(ctx, rec_bytes);
+        if (!P.a.rec) return fail(ctx, BOWGPU_ENOMEM, "aggregate: scratch");
+    }
+    // ---- one streaming launch per (dtype, nulls) group of at most MC_MAXC columns ------------------------------------------
+    {
+        std::vector<bool> done(plans.size(), false);
+        for (size_t u = 0; u < plans.size(); ++u) {
+            if (done[u]) continue;
+            const DevCol &d0 = f->cols[plans[u].col];
+            McLaunch L;
+            memset(&L, 0, sizeof L);
+            L.time = (const int64_t *)f->cols[r->time_col].values;
+            L.g = g;
+            L.is_int = d0.dtype == BOWGPU_INT64;
+            L.touched = touched;
+            L.status = ctx->d_status;
+            for (size_t v = u; v < plans.size() && L.ncols < MC_MAXC; ++v) {
+                const DevCol &dv = f->cols[plans[v].col];
+                if (done[v] || (dv.dtype == BOWGPU_INT64) != (L.is_int != 0) || (dv.validity != nullptr) != (d0.validity != nullptr)) continue;
+                L.col[L.ncols++] = plans[v].a;
+                L.bops |= plans[v].bops;
+                L.iops |= plans[v].iops;
+                done[v] = true;
+            }
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            timing_main_pair(ctx, &e0, &e1);
+            CK(launch_segmc(L, ctx->sm_count, ctx->stream, e0, e1));
+            count_launch(ctx, 1, true);
+            count_launch(ctx, 1);
+        }
+    }
+    // ---- per-output finishing: validity bitmaps, WindowStart, zeros of windows without rows ---------------------------------
+    {
+        std::vector<FinishDst> dst;
+        for (int j = 0; j < nspecs; ++j) {
+            const int op = specs[j].op;
+            if (r->whole && op == BOWGPU_AGG_WINDOW_START && f->cols[specs[j].col].dtype != BOWGPU_INT64) {
+                // whole.go:87 SetOrDropStrict: the int64 window start does not fit the Float64 buffer -> null
+                CK(cudaMemsetAsync(dvals[j], 0, (size_t)W * 8, ctx->stream));
+                CK(cudaMemsetAsync(dbits[j], 0, (size_t)((W + 7) / 8), ctx->stream));
+                continue;
+            }
+            FinishDst D;
+            memset(&D, 0, sizeof D);
+            D.values = (uint64_t *)dvals[j];
+            D.validity = dbits[j];
+            if (op == BOWGPU_AGG_WINDOW_START) {
+                D.kind = FIN_WINDOW_START;
+            } else {
+                size_t u = std::find(cols_used.begin(), cols_used.end(), specs[j].col) - cols_used.begin();
+                const ColPlan &P = plans[u];
+                D.zero_empty = syn_by_col == nullptr;
+                if (op == BOWGPU_AGG_COUNT || op == BOWGPU_AGG_SUM) {
+                    D.kind = FIN_ALWAYS;
+                } else {
+                    D.kind = FIN_SRC;
+                    D.src = (op == BOWGPU_AGG_INTEGRAL_TRAPEZOID || op == BOWGPU_AGG_WAVG_LINEAR) ? P.a.out.vb_trap : P.a.out.vb_cnt;
+                }
+                // duplicates of an (op, column) pair: copies of the first one
+                if (P.primary[op] != j)
+                    CK(cudaMemcpyAsync(dvals[j], dvals[P.primary[op]], (size_t)W * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+            dst.push_back(D);
+        }
+        int nl = 0;
+        if (!dst.empty()) CK(launch_finish(dst.data(), (int)dst.size(), touched, g, ctx->stream, &nl));
+        count_launch(ctx, nl);
+        for (int j = 0; j < nspecs; ++j)
+            if (specs[j].nfactors > 0) {  // transformation.Factor, in place on the valid slots
+                CK(launch_factor((uint64_t *)dvals[j], dbits[j], W, outs[j].dtype == BOWGPU_INT64, specs[j].nfactors, specs[j].factors,
+                                 ctx->stream));
+                count_launch(ctx);
+            }
+    }
+    timing_end(ctx);
+    if (mem == BOWGPU_MEM_DEVICE) return BOWGPU_OK;  // asynchronous: errors surface in bowgpu_ctx_synchronize
+    for (int j = 0; j < nspecs; ++j) {
+        rc = copy_d2h(ctx, outs[j].values, dvals[j], (size_t)W * 8);
+        if (rc) return rc;
+        rc = copy_d2h(ctx, outs[j].validity, dbits[j], (size_t)((W + 7) / 8));
+        if (rc) return rc;
+    }
+    return check_status(ctx);
+}
+
+// Two implementations of Rolling.Aggregate live side by side (same results, same ABI):
+//   v1 (default)  one streaming launch per input column and kernel family (segreduce.cuh) + epilogue pass
+//   mc            BOWGPU_SEG_IMPL=mc: the multi-column kernels of segmc.cuh (time read once per launch, final values
+//                 written in place).  Parity-green, but measured slower than v1 on B200: opt-in only.
+static bool use_mc() {
+    static const bool mc = [] {
+        const char *e = getenv("BOWGPU_SEG_IMPL");
+        return e && strcmp(e, "mc") == 0;
+    }();
+    return mc;
+}
+static int32_t aggregate_dispatch(bowgpu_rolling *r, const bowgpu_agg_spec *specs, int32_t nspecs, bowgpu_out_col *outs,
+                                  int32_t mem, const FusedSyn *syn_by_col) {
+    return use_mc() ? aggregate_core_mc(r, specs, nspecs, outs, mem, syn_by_col) : aggregate_core(r, specs, nspecs, outs, mem, syn_by_col);
+}
+
 extern "C" int32_t bowgpu_rolling_aggregate(bowgpu_rolling *r, const bowgpu_agg_spec *specs, int32_t nspecs,
                                             bowgpu_out_col *outs, int32_t mem) {
-    return aggregate_core(r, specs, nspecs, outs, mem, nullptr);
+    return aggregate_dispatch(r, specs, nspecs, outs, mem, nullptr);
 }
 
 // aggregation.Aggregate(b, intervalCol, aggrs...) (rolling/aggregation/whole.go:12-93): every aggregation over ONE window
@@ -1716,7 +1918,7 @@ extern "C" int32_t bowgpu_rolling_interpolate_aggregate(bowgpu_rolling *r, const
         if (rc == BOWGPU_OK && r2->W != r->W)  // the caller sized `outs` for the lattice of r
             rc = fail(ctx, BOWGPU_EUNSUPPORTED, "interpolation changes the window lattice (%lld -> %lld windows): use the two-step calls",
                       (long long)r->W, (long long)r2->W);
-        if (rc == BOWGPU_OK) rc = aggregate_core(r2, specs, nspecs, outs, mem, nullptr);
+        if (rc == BOWGPU_OK) rc = aggregate_dispatch(r2, specs, nspecs, outs, mem, nullptr);
         if (rc == BOWGPU_OK && mem == BOWGPU_MEM_DEVICE) rc = check_status(ctx);  // the frame is about to go
         bowgpu_rolling_destroy(r2);
         bowgpu_frame_destroy(fi);
@@ -1781,6 +1983,7 @@ extern "C" int32_t bowgpu_rolling_interpolate_aggregate(bowgpu_rolling *r, const
         syn[j].val = c.syn_val;
         syn[j].ok = c.syn_ok;
         syn[j].len = W;
+        syn[j].first = d_first;
     }
     // synthetic rows of windows that have a start row are never read, but keep the arrays defined
     if (cudaMemsetAsync(blk + wv, 0, total - wv, ctx->stream) != cudaSuccess) return bail(fail(ctx, BOWGPU_ECUDA, "memset"));
@@ -1804,7 +2007,7 @@ extern "C" int32_t bowgpu_rolling_interpolate_aggregate(bowgpu_rolling *r, const
         if (st & ST_UNSORTED) return fail(ctx, BOWGPU_EUNSORTED, "time column is not sorted ascending");
         return unfused();
     }
-    const int32_t rc = aggregate_core(r, specs, nspecs, outs, mem, syn.data());
+    const int32_t rc = aggregate_dispatch(r, specs, nspecs, outs, mem, syn.data());
     pool_free(ctx, blk);  // stream ordered: released after the kernels that read it
     return rc;
 }
@@ -1945,7 +2148,7 @@ extern "C" int32_t bowgpu_aggregate_host(bowgpu_ctx *ctx, const bowgpu_col *cols
             if (rc == BOWGPU_OK)
                 rc = bowgpu_rolling_create_shard(f, remap[time_col], interval, (int64_t)((uint64_t)s0 + (uint64_t)ch.k_lo * (uint64_t)interval),
                                                  ch.k_hi - ch.k_lo, inclusive, nullptr, &r);
-            if (rc == BOWGPU_OK) rc = aggregate_core(r, sp.data(), nspecs, oc.data(), BOWGPU_MEM_HOST, nullptr);
+            if (rc == BOWGPU_OK) rc = aggregate_dispatch(r, sp.data(), nspecs, oc.data(), BOWGPU_MEM_HOST, nullptr);
             if (rc != BOWGPU_OK) {
                 status[wi] = rc;
                 errs[wi] = wc->err;

@@ -65,6 +65,7 @@ struct FusedSyn {
     const uint64_t *val;     // [W] its value in this column (raw bits)
     const uint8_t *ok;       // [W] its validity
     int64_t len;             // entries in the three arrays: W, or W + 1 on a shard (start row of the next shard's window)
+    const int64_t *first;    // [len + 1] window boundaries (bounds kernel): first row of window k (segmc: empty windows)
 };
 
 struct SegLaunch {
@@ -109,6 +110,72 @@ struct IntLaunch {
 size_t integral_carry_bytes(int64_t n);
 int launch_segreduce_integral(const IntLaunch &L, int sm_count, cudaStream_t stream, cudaEvent_t ev_main0,
                               cudaEvent_t ev_main1);
+
+// ---- segmc: multi-column, multi-family streaming segmented reduction (segmc.cuh) ----------------------------------
+// One launch stages the time column ONCE per tile and streams up to MC_MAXC value columns past it; every aggregation of
+// a column (basic and integral family together) comes out of that one pass, and the FINAL output values are written by
+// whoever completes a window (no per-window intermediate arrays, no epilogue pass over values).
+constexpr int MC_MAXC = 8;
+enum { MC_SUM = 1, MC_MINMAX = 2, MC_FIRSTLAST = 4 };  // basic family (the valid-row count is always kept)
+enum { MC_STEP = 1, MC_TRAP = 2 };                      // integral family
+struct McColOut {  // final outputs of one input column; null = not requested
+    int64_t *cnt;
+    double *sum, *mean, *mn, *mx;
+    uint64_t *first, *last;
+    double *step, *trap, *wstep, *wlin;
+    uint32_t *vb_cnt;   // zero-initialised validity words: bit k set iff window k holds a valid row (atomicOr)
+    uint32_t *vb_trap;  // ... iff the trapezoid integral of window k is defined (>= 2 points, integral.go:33-35)
+};
+struct alignas(16) McCarry {  // one edge record of a chunk of tiles (joined by mc_fixup_kernel)
+    int64_t key;              // window index, -1 = none
+    int64_t cnt;              // valid rows; bit 62 = the window closed inside the chunk (head records)
+    double sum, mn, mx;
+    uint64_t first, last;     // raw bits of the first / last valid value
+    double fT, lT, lV, sS, sT;
+    double incV, incT;
+    int64_t inc_has;
+    int64_t edge_t;           // head records: first row of the chunk (time, raw value bits, validity);
+    uint64_t edge_raw;        // tail records: edge_t = time of the chunk's last row
+    int64_t edge_valid;
+    int64_t _pad;
+};
+static_assert(sizeof(McCarry) == 160, "record layout");
+struct McColArgs {
+    const uint64_t *values;
+    const uint8_t *validity;  // null = all valid (a launch is homogeneous: all columns with, or all without, nulls)
+    McColOut out;
+    FusedSyn syn;
+    McCarry *rec;             // [2 * nchunks]: head, tail of every chunk
+};
+struct McLaunch {
+    const int64_t *time;
+    WindowGeom g;
+    int32_t ncols;
+    int32_t is_int;    // value columns are int64 (a launch is homogeneous)
+    uint32_t bops;     // MC_SUM | MC_MINMAX | MC_FIRSTLAST needed by some column (0 = none)
+    uint32_t iops;     // MC_STEP | MC_TRAP
+    uint32_t *touched; // zero-initialised bitmap words: bit k set iff window k holds at least one row
+    int32_t *status;
+    McColArgs col[MC_MAXC];
+};
+int mc_max_chunks(int sm_count);              // upper bound of chunks (records per column = 2 * this)
+int launch_segmc(const McLaunch &L, int sm_count, cudaStream_t stream, cudaEvent_t ev_main0, cudaEvent_t ev_main1);
+
+// Per-window finishing pass (finish.cu): validity bitmaps of every output from the few bitmaps the streaming kernel
+// set, WindowStart columns, and value 0 in the slots of windows that hold no row at all.
+enum { FIN_SRC = 0, FIN_ALWAYS = 1, FIN_WINDOW_START = 2 };
+struct FinishDst {
+    uint64_t *values;     // [W]
+    uint8_t *validity;    // [ceil(W/8)] bytes
+    const uint32_t *src;  // FIN_SRC: validity words to copy
+    int32_t kind;
+    int32_t zero_empty;   // write value 0 for windows without rows (not on the fused path: those hold a synthetic row)
+};
+int launch_finish(const FinishDst *dst_host, int ndst, const uint32_t *touched, WindowGeom g, cudaStream_t stream,
+                  int *launches);
+// transformation.Factor (factor.go:7-20) applied in place to the valid slots of a finished output column
+int launch_factor(uint64_t *values, const uint8_t *validity, int64_t W, int out_is_int, int nfactors,
+                  const double *factors, cudaStream_t stream);
 
 // ---- bounds ------------------------------------------------------------------------------------
 struct BoundsLaunch {
