@@ -8,6 +8,7 @@
 // there is one exact 64-bit division per thread and tile, not per row.  The thread that owns the
 // last row of a window writes the start index of every window up to the next non-empty one, so
 // empty windows need no second pass.
+#include <atomic>
 #include "kernels.h"
 #include "tile_pipe.cuh"
 
@@ -188,13 +189,13 @@ int launch_bounds(const BoundsLaunch &L, int sm_count, cudaStream_t stream, cuda
     const int64_t ntiles = (L.g.n + BndG::T - 1) / BndG::T;
     if (ntiles == 0) return 0;
     const int smem = BND_HEADER_BYTES + BND_STAGES * BND_STAGE_BYTES;
-    static bool configured[64] = {};  // function attributes are per device (one ctx per GPU may live in one process)
+    static std::atomic<bool> configured[64];  // function attributes are per device (one ctx per GPU may live in one process)
     int dev = 0;
     cudaGetDevice(&dev);
-    if (!configured[dev & 63]) {
+    if (!configured[dev & 63].load(std::memory_order_acquire)) {  // (host threads may launch concurrently)
         cudaError_t e = cudaFuncSetAttribute(bounds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        configured[dev & 63] = true;
+        configured[dev & 63].store(true, std::memory_order_release);
     }
     int64_t grid = (int64_t)sm_count * 3;
     if (grid > ntiles) grid = ntiles;

@@ -37,8 +37,10 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "kernels.h"
 
@@ -691,31 +693,40 @@ inline void seg_knobs(int &nstages, int &ctas, int def_stages, int def_ctas) {
 
 // Tensor map viewing a column of n 8-byte elements as [n / RE][RE]; box = [NT][P+2].  Only whole rows of the view
 // are addressable, which is all the kernel asks for (tiles that are not complete are staged by plain loads).
+// process-wide launch knobs, resolved once (bowgpu_aggregate_host drives the kernels from several host threads)
+struct SegKnobs {
+    PFN_cuTensorMapEncodeTiled_v12000 encode;
+    int l2p;  // L2 promotion of the box fetches (tuning knob; 0 none, 1 64B, 2 128B, 3 256B)
+};
+inline const SegKnobs &seg_global_knobs() {
+    static SegKnobs k;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        k.encode = nullptr;
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            k.encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+        const char *e = getenv("BOWGPU_TMAP_L2");
+        k.l2p = e ? atoi(e) : 1;
+        if (k.l2p < 0 || k.l2p > 3) k.l2p = 3;
+    });
+    return k;
+}
 inline int seg_make_tmap(CUtensorMap *m, const void *col, int64_t n) {
     memset(m, 0, sizeof *m);
     const int64_t outer = n / SEG_RE;
     if (outer == 0) return 0;
-    static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
-    if (!encode) {
-        void *fn = nullptr;
-        cudaDriverEntryPointQueryResult qr;
-        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr);
-        if (e != cudaSuccess || qr != cudaDriverEntryPointSuccess || !fn) return (int)cudaErrorNotSupported;
-        encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
-    }
+    const SegKnobs &K = seg_global_knobs();
+    if (!K.encode) return (int)cudaErrorNotSupported;
     const cuuint64_t dims[2] = {(cuuint64_t)SEG_RE, (cuuint64_t)outer};
     const cuuint64_t strides[1] = {(cuuint64_t)SEG_RE * 8};
     const cuuint32_t box[2] = {(cuuint32_t)SEG_COLS, (cuuint32_t)SEG_NT};
     const cuuint32_t estr[2] = {1, 1};
-    static int l2p = -1;  // L2 promotion of the box fetches (tuning knob; 0 none, 1 64B, 2 128B, 3 256B)
-    if (l2p < 0) {
-        const char *e = getenv("BOWGPU_TMAP_L2");
-        l2p = e ? atoi(e) : 1;
-        if (l2p < 0 || l2p > 3) l2p = 3;
-    }
-    const CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_INT64, 2, const_cast<void *>(col), dims, strides, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, SEG_SWZ ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, (CUtensorMapL2promotion)l2p,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult r = K.encode(m, CU_TENSOR_MAP_DATA_TYPE_INT64, 2, const_cast<void *>(col), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, SEG_SWZ ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                                (CUtensorMapL2promotion)K.l2p, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
@@ -724,16 +735,18 @@ int seg_launch_impl(const SegArgs<Pol> &A, int sm_count, cudaStream_t stream, cu
     const int64_t ntiles = (A.g.n + SEG_T - 1) / SEG_T;
     if (ntiles == 0) return 0;
     auto kern = segreduce_kernel<Pol, HAS_NULLS, MIN_CTAS, FUSED>;
+    // resolved once per instantiation, under std::call_once: several host threads launch concurrently
     static int nstages = 0, ctas = 0;
-    if (!nstages) seg_knobs(nstages, ctas, 2, MIN_CTAS);
+    static std::once_flag once;
+    std::call_once(once, [] { seg_knobs(nstages, ctas, 2, MIN_CTAS); });
     const int smem = seg_smem_bytes(nstages);
-    static bool configured[64] = {};  // function attributes are per device (one ctx per GPU may live in one process)
+    static std::atomic<bool> configured[64];  // function attributes are per device (one ctx per GPU may live in one process)
     int dev = 0;
     cudaGetDevice(&dev);
-    if (!configured[dev & 63]) {
+    if (!configured[dev & 63].load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        configured[dev & 63] = true;
+        configured[dev & 63].store(true, std::memory_order_release);
     }
     CUtensorMap tm_time, tm_val;
     int rc = seg_make_tmap(&tm_time, A.time, A.g.n);

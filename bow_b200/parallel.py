@@ -27,7 +27,10 @@ def gpu_executor(cols: Sequence[NpCol], time_col: int, interval: int, s0: int, n
     from . import native as N
     from .runtime import default_ctx
     fr = N.Frame.from_numpy(default_ctx(), cols)
-    r = N.Rolling(fr, time_col, interval, inclusive=inclusive, shard=(s0, num_windows))
+    if num_windows < 0:   # a `plain` shard (partition.plan): the whole frame as an ordinary rolling
+        r = N.Rolling(fr, time_col, interval, offset=s0 % interval, inclusive=inclusive)
+    else:
+        r = N.Rolling(fr, time_col, interval, inclusive=inclusive, shard=(s0, num_windows))
     try:
         return r.aggregate(specs)
     finally:
@@ -57,6 +60,8 @@ def aggregate_shard(cols: Sequence[NpCol], shard: P.Shard, time_col: int, interv
     rows [row_lo, halo_hi) when `len(cols[0][0]) == halo_hi - row_lo`."""
     nloc = shard.halo_hi - shard.row_lo
     local = cols if len(cols[0][0]) == nloc else slice_cols(cols, shard.row_lo, shard.halo_hi)
+    if shard.plain:       # (num_windows < 0 tells the executor to run an ordinary rolling with offset s0 mod interval)
+        return executor(local, time_col, interval, s0_global, -1, inclusive, specs)
     return executor(local, time_col, interval, s0_global + shard.k_lo * interval, shard.num_windows, inclusive, specs)
 
 
@@ -136,7 +141,10 @@ def gpu_interpolate_executor(cols: Sequence[NpCol], time_col: int, interval: int
     from . import native as N
     from .runtime import default_ctx
     fr = N.Frame.from_numpy(default_ctx(), cols)
-    r = N.Rolling(fr, time_col, interval, inclusive=inclusive, prev_row=prev_row, shard=(s0, num_windows))
+    if num_windows < 0:   # a `plain` shard
+        r = N.Rolling(fr, time_col, interval, offset=s0 % interval, inclusive=inclusive, prev_row=prev_row)
+    else:
+        r = N.Rolling(fr, time_col, interval, inclusive=inclusive, prev_row=prev_row, shard=(s0, num_windows))
     try:
         out = r.interpolate(ops)
         try:
@@ -160,6 +168,9 @@ def interpolate_shard(cols: Sequence[NpCol], shard: P.Shard, time_col: int, inte
         return [(np.zeros(0, dtype=v.dtype), np.zeros(0, dtype=bool)) for v, _ in cols], 0
     nloc = shard.halo_hi - shard.first_row
     local = cols if len(cols[0][0]) == nloc else slice_cols(cols, shard.first_row, shard.halo_hi)
+    if shard.plain:
+        out = executor(local, time_col, interval, s0_global, -1, inclusive, ops, prev_row)
+        return out, len(out[time_col][0])
     s0 = s0_global + shard.k_lo * interval
     out = executor(local, time_col, interval, s0, shard.num_windows + shard.extra_windows, inclusive, ops, prev_row)
     assert len(out) == ncols
@@ -183,7 +194,10 @@ def gpu_interpolate_aggregate_executor(cols: Sequence[NpCol], time_col: int, int
     from . import native as N
     from .runtime import default_ctx
     fr = N.Frame.from_numpy(default_ctx(), cols)
-    r = N.Rolling(fr, time_col, interval, prev_row=prev_row, shard=(s0, num_windows))
+    if num_windows < 0:   # a `plain` shard
+        r = N.Rolling(fr, time_col, interval, offset=s0 % interval, prev_row=prev_row)
+    else:
+        r = N.Rolling(fr, time_col, interval, prev_row=prev_row, shard=(s0, num_windows))
     try:
         return r.interpolate_aggregate(ops, specs)
     finally:
@@ -198,4 +212,6 @@ def interpolate_aggregate_shard(cols: Sequence[NpCol], shard: P.Shard, time_col:
     one extra window and right halo are shipped).  Per-shard outputs concatenate to the global result."""
     nloc = shard.halo_hi - shard.first_row
     local = cols if len(cols[0][0]) == nloc else slice_cols(cols, shard.first_row, shard.halo_hi)
+    if shard.plain:
+        return executor(local, time_col, interval, s0_global, -1, ops, specs, prev_row)
     return executor(local, time_col, interval, s0_global + shard.k_lo * interval, shard.num_windows, ops, specs, prev_row)

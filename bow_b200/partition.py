@@ -27,6 +27,7 @@ class Shard:
     halo_hi: int   # rows [row_hi, halo_hi) are shipped too (inclusive row of the last window)
     frame_lo: int = -1   # first row shipped: rows [frame_lo, row_lo) are the LEFT halo (Interpolate only)
     extra_windows: int = 0   # Interpolate only: 1 if the start row of window k_hi is produced here as well
+    plain: bool = False  # the whole frame, to be run as an ordinary (unsharded) rolling: see `plan`
 
     @property
     def num_windows(self) -> int:
@@ -88,6 +89,13 @@ def plan(n_rows: int, t_first: int, t_last: int, interval: int, offset: int, n_s
         return [Shard(g, 0, 0, 0, 0, 0) for g in range(n_shards)]
     s0 = first_window_start(t_first, interval, offset)
     W = num_windows(t_first, t_last, interval, offset)
+    if t_first < s0:
+        # Negative timestamps with an offset: Go's truncating division can leave the first window start AFTER the
+        # first row (rolling.go:96-99; t_first = -15, interval 10, offset 7 -> s0 = -13).  Those leading rows belong to
+        # window 0 iff that window holds a row of its own (rolling.go:194-211) - a rule of the unsharded iterator that a
+        # shard (whose rows before its first window start are a halo) does not apply.  The frame is not cut: shard 0
+        # takes all of it and runs as an ordinary rolling, the other shards are empty.
+        return [Shard(0, 0, W, 0, n_rows, n_rows, plain=True)] + [Shard(g, W, W, n_rows, n_rows, n_rows) for g in range(1, n_shards)]
     cuts = [0]
     for g in range(1, n_shards):
         k = (g * W + n_shards // 2) // n_shards
@@ -132,7 +140,7 @@ def plan_interpolate(n_rows: int, t_first: int, t_last: int, interval: int, offs
         interpolated here (linear.go:20-27 looks beyond the window).
     """
     base = plan(n_rows, t_first, t_last, interval, offset, n_shards, lower_bound, align)
-    if n_rows == 0:
+    if n_rows == 0 or base[0].plain:
         return base
     off = normalise_offset(interval, offset)
     s0 = first_window_start(t_first, interval, off)

@@ -239,6 +239,10 @@ class Rolling:
             if self.options.PrevRow is not None:
                 prev = []
                 pr = self.options.PrevRow
+                # the C ABI reads one PrevRow cell per frame column, by position: same columns, same types
+                if pr.NumCols() != len(self.types) or any(pr.ColumnType(j) != self.types[j] for j in range(pr.NumCols())):
+                    raise BowError("newIntervalRolling: prevRow must have the same columns (number, order and types) "
+                                   "as the bow")
                 for j in range(pr.NumCols()):
                     a = pr.Column(j)
                     dt = np.int64 if pr.ColumnType(j) == B.Int64 else np.float64
@@ -452,8 +456,12 @@ class Rolling:
         # (bowgpu_rolling_interpolate_aggregate).  Only taken when the host can tell that the interpolated frame keeps
         # the window lattice: no user Inclusive, first row not before the first window start, at least one window.
         first_time = self._first_time()
+        # ... and the interval column is interpolated by WindowStart (the condition of the fused C entry point): any other
+        # interpolation of it (None leaves null timestamps, newIntervalRolling then fails, rolling.go:91-94) goes
+        # through the eager path so that NumWindows / Bow / the deferred error behave like the reference's.
         if (not self.options.Inclusive and self.numWindows > 0 and first_time is not None
-                and self.currWindowFirstValue <= first_time and self.currWindowIndex == 0):
+                and self.currWindowFirstValue <= first_time and self.currWindowIndex == 0
+                and ops[self.intervalColIndex] == N.INTERP["WindowStart"]):
             r._lazy = (self, ops)
             r.numWindows = self.numWindows
             r.currWindowFirstValue = self.currWindowFirstValue

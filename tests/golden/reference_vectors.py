@@ -229,6 +229,14 @@ INTERPOLATIONS_STEPNEXT = [
      [(10, 1.0), (11, N), (12, 1.5), (13, N), (14, 1.5), (15, 1.5)], "hand-derived"),
     ("stepnext nothing after", "StepNext", [(10, 1.0), (13, N)], 0, [(10, 1.0), (12, N), (13, N)], "hand-derived"),
 ]
+# StepNext ANCHORED ON THE REFERENCE: the value StepNext gives a synthetic window-start row is, by definition, what
+# Bow.FillNext (bowfill.go:154-158) leaves at the window's first row — "the next valid value at or after it".  Over the
+# time column t = 0, 10, .. 50 with interval 10 and offset 5 (first window start -5) window k holds exactly row k and no
+# row sits on a window start, so EVERY window gets a synthetic row and its StepNext values must be row k of the
+# reference's own FillNext golden table (bowfill_test.go:93-112 Int64, :269-288 Float64: FILL_CASES "Next all columns",
+# whose input is FILL_ROWS; column `a` included - it is filled like the others).
+STEPNEXT_VS_FILLNEXT = dict(times=[0, 10, 20, 30, 40, 50], interval=10, offset=5, rows="FILL_ROWS",
+                            expected_case="Next all columns", cite="bowfill_test.go:93-112,269-288")
 # rolling/interpolation/windowstart_test.go:13-64 — single-column bow {10,13}
 INTERP_WINDOWSTART = [
     ("windowstart no options", [10, 13], 0, [10, 12, 13]),

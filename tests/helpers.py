@@ -93,3 +93,36 @@ def seed_of(*key) -> int:
     """deterministic seed from a test's parameters (Python's hash() of strings changes from run to run)"""
     import zlib
     return zlib.crc32(repr(key).encode())
+
+
+# ---- the stated tolerance class of the float reductions -------------------------------------------------------------
+TOL = 1e-12
+TOL_OPS = ("Sum", "ArithmeticMean", "IntegralStep", "IntegralTrapezoid", "WeightedAverageStep", "WeightedAverageLinear")
+
+
+def term_scales(cols, vcol, interval, offset=0, inclusive=False, time_col=0):
+    """sum of |term_i| per window for every float reduction of column `vcol` (the second argument of the parity bar
+    |gpu - ref| <= 1e-12 * max(|ref|, sum|term_i|)): the oracle run on |v|.  Sum: sum|v|; ArithmeticMean: sum|v| / count;
+    integrals: the integral of |v|; weighted averages: that over the window width."""
+    from oracle import refc as R
+    v, m = cols[vcol]
+    av = np.abs(v.astype(np.float64))
+    av = np.where(np.isfinite(av), av, 0.0)
+    ref = R.RefRolling(R.Frame([cols[time_col], (av, m)]), 0, interval, offset=offset, inclusive=inclusive)
+    out = ref.aggregate([("WindowStart", 0), ("Sum", 1), ("Count", 1), ("IntegralStep", 1), ("IntegralTrapezoid", 1)])
+    s = out[1][0]
+    cnt = np.maximum(out[2][0], 1).astype(np.float64)
+    integ = np.maximum(np.where(out[3][1], np.abs(out[3][0]), 0.0), np.where(out[4][1], np.abs(out[4][0]), 0.0))
+    return {"Sum": s, "ArithmeticMean": s / cnt, "IntegralStep": integ, "IntegralTrapezoid": integ,
+            "WeightedAverageStep": integ / float(interval), "WeightedAverageLinear": integ / float(interval)}
+
+
+def assert_in_tolerance_class(gv, wv, scale, what="", factor=1.0):
+    """|gpu - ref| <= 1e-12 * max(|ref|, scale) elementwise (bit-identical values, incl. NaN / Inf, always pass);
+    `factor`: product of the |transformation.Factor|s applied to the output"""
+    gv, wv = np.asarray(gv, dtype=np.float64), np.asarray(wv, dtype=np.float64)
+    same = (gv.view(np.int64) == wv.view(np.int64)) | (np.isnan(gv) & np.isnan(wv))
+    with np.errstate(invalid="ignore"):
+        ok = np.abs(gv - wv) <= TOL * np.maximum(np.abs(wv), np.asarray(scale, dtype=np.float64) * factor)
+    bad = np.flatnonzero(~same & ~ok)
+    assert bad.size == 0, f"{what}: {bad[:10]} got {gv[bad[:10]]} want {wv[bad[:10]]}"

@@ -29,25 +29,22 @@ def bits(a):
     return np.asarray(a).view(np.int64) if np.asarray(a).dtype == np.float64 else np.asarray(a)
 
 
-def compare_aggs(names, got, want, abs_sums=None, what=""):
+def compare_aggs(names, got, want, abs_sums=None, what="", int_input=False):
+    """int_input: the aggregated column is int64 (|v| < 2^53 / n in these tests): every partial sum is an exactly
+    representable integer, so Sum is order independent and must be BIT-EXACT (north star: "int64 Sum bit-exact")"""
     assert len(got) == len(want)
     for j, name in enumerate(names):
         (gv, gm), (wv, wm) = got[j], want[j]
         assert gv.dtype == wv.dtype, (what, name, gv.dtype, wv.dtype)
         assert np.array_equal(gm, wm), f"{what} {name}: validity differs at {np.flatnonzero(gm != wm)[:10]}"
-        if name in EXACT:
+        if name in EXACT or (int_input and name == "Sum"):
             bad = np.flatnonzero(bits(gv) != bits(wv))
             # NaN payloads are not compared (see tests/helpers.same_value)
             if gv.dtype == np.float64:
                 bad = bad[~(np.isnan(gv[bad]) & np.isnan(wv[bad]))]
             assert bad.size == 0, f"{what} {name}: {bad[:10]} got {gv[bad[:10]]} want {wv[bad[:10]]}"
         else:
-            scale = np.maximum(np.abs(wv), abs_sums if abs_sums is not None else 0.0)
-            with np.errstate(invalid="ignore"):
-                err = np.abs(gv - wv)
-            same = (bits(gv) == bits(wv)) | (np.isnan(gv) & np.isnan(wv))
-            bad = np.flatnonzero(~same & ~(err <= TOL * scale))
-            assert bad.size == 0, f"{what} {name}: {bad[:10]} got {gv[bad[:10]]} want {wv[bad[:10]]}"
+            H.assert_in_tolerance_class(gv, wv, abs_sums[name] if abs_sums is not None else 0.0, f"{what} {name}")
         # null slots hold value 0 (bowbuffer.go:22-40)
         assert not np.any(bits(gv)[~gm]), f"{what} {name}: non-zero value in a null slot"
 
@@ -61,15 +58,8 @@ def run_both(ctx, cols, interval, specs, offset=0, inclusive=False, slice_offset
     assert r.num_windows == ref.num_windows
     assert r.first_window_start == ref.first_window_start or len(cols[0][0]) == 0
     want = ref.aggregate(specs)
-    # sum |v| per window for the tolerance of the float reductions
-    abs_sums = None
-    vcol = specs[-1][1]
-    if cols[vcol][0].dtype == np.float64 or True:
-        v, m = cols[vcol]
-        av = np.abs(v.astype(np.float64))
-        av = np.where(np.isfinite(av), av, 0.0)
-        abs_ref = R.RefRolling(R.Frame([cols[0], (av, m)]), 0, interval, offset=offset, inclusive=inclusive)
-        abs_sums = abs_ref.aggregate([("WindowStart", 0), ("Sum", 1)])[1][0]
+    # sum |term| per window for the tolerance class of the float reductions
+    abs_sums = H.term_scales(cols, specs[-1][1], interval, offset=offset, inclusive=inclusive)
     r.close()
     fr.close()
     return got, want, abs_sums
@@ -124,7 +114,8 @@ def test_random_vs_oracle(ctx, kind, n):
         specs = [("WindowStart", 0)] + [(a, 1) for a in BASIC[1:]]
         got, want, abs_sums = run_both(ctx, cols, interval, specs, offset=offset, inclusive=inclusive,
                                        slice_offset=int(rng.integers(0, 70)) if trial == 3 else 0)
-        compare_aggs(BASIC, got, want, abs_sums, what=f"{kind} n={n} I={interval} off={offset} inc={inclusive}")
+        compare_aggs(BASIC, got, want, abs_sums, what=f"{kind} n={n} I={interval} off={offset} inc={inclusive}",
+                     int_input=dtype == np.int64)
 
 
 INTEGRALS = ["IntegralStep", "IntegralTrapezoid", "WeightedAverageStep", "WeightedAverageLinear"]
@@ -149,10 +140,7 @@ def test_random_integrals_vs_oracle(ctx, kind, n):
         r = N.Rolling(fr, 0, interval, offset=offset, inclusive=inclusive)
         got = r.aggregate(specs)
         want = R.RefRolling(R.Frame(cols), 0, interval, offset=offset, inclusive=inclusive).aggregate(specs)
-        av = (np.abs(v[0].astype(np.float64)), v[1])
-        scale = R.RefRolling(R.Frame([cols[0], av]), 0, interval, offset=offset, inclusive=inclusive).aggregate(
-            [("WindowStart", 0), ("IntegralStep", 1), ("IntegralTrapezoid", 1)])
-        sc = np.maximum(np.where(scale[1][1], np.abs(scale[1][0]), 0), np.where(scale[2][1], np.abs(scale[2][0]), 0))
+        scales = H.term_scales(cols, 1, interval, offset=offset, inclusive=inclusive)
         what = f"{kind} n={n} I={interval} off={offset} inc={inclusive} trial={trial}"
         for j, sp in enumerate(specs):
             (gv, gm), (wv, wm) = got[j], want[j]
@@ -160,9 +148,8 @@ def test_random_integrals_vs_oracle(ctx, kind, n):
             if sp[0] in ("WindowStart", "Count"):
                 assert np.array_equal(gv, wv), (what, sp)
                 continue
-            tol = TOL * np.maximum(np.abs(wv), sc if sp[0].startswith("Integral") else sc / interval)
-            bad = np.flatnonzero(~(np.abs(gv - wv) <= tol) & (bits(gv) != bits(wv)))
-            assert bad.size == 0, f"{what} {sp}: {bad[:10]} got {gv[bad[:10]]} want {wv[bad[:10]]}"
+            fac = float(np.prod(np.abs(sp[2]))) if len(sp) > 2 else 1.0
+            H.assert_in_tolerance_class(gv, wv, scales[sp[0]], f"{what} {sp}", factor=fac)
             assert not np.any(bits(gv)[~gm]), f"{what} {sp}: non-zero value in a null slot"
 
 
@@ -211,12 +198,13 @@ def test_multi_column_and_duplicates(ctx):
     r = N.Rolling(fr, 0, 37, offset=5)
     got = r.aggregate(specs)
     want = R.RefRolling(R.Frame(cols), 0, 37, offset=5).aggregate(specs)
-    tolerant = {"Sum", "ArithmeticMean", "Min"}   # Min here carries factors applied to an exact value: still exact
+    scales = H.term_scales(cols, 1, 37, offset=5)
     for j, name in enumerate(names):
         (gv, gm), (wv, wm) = got[j], want[j]
         assert np.array_equal(gm, wm), name
-        if name in ("Sum", "ArithmeticMean"):
-            assert np.allclose(gv, wv, rtol=1e-12, atol=1e-9), name
+        if name in ("Sum", "ArithmeticMean"):   # (of the float column; Min carries factors applied to an exact value: exact)
+            fac = float(np.prod(np.abs(specs[j][2]))) if len(specs[j]) > 2 else 1.0
+            H.assert_in_tolerance_class(gv, wv, scales[name], f"{j} {name}", factor=fac)
         else:
             assert np.array_equal(bits(gv), bits(wv)), (j, name)
 
@@ -271,12 +259,29 @@ def test_sharded_matches_oracle(ctx, g):
         per = [PP.aggregate_shard(cols, s, 0, interval, s0, inclusive, specs) for s in shards]
         got = PP.concat_outputs(per)
         want = R.RefRolling(R.Frame(cols), 0, interval, offset=3, inclusive=inclusive).aggregate(specs)
+        scales = H.term_scales(cols, 1, interval, offset=3, inclusive=inclusive)
         for sp, (gv, gm), (wv, wm) in zip(specs, got, want):
             assert np.array_equal(gm, wm), (kind, sp)
             if sp[0] in EXACT:
                 assert np.array_equal(bits(gv), bits(wv)), (kind, sp)
             else:
-                assert np.allclose(gv, wv, rtol=1e-11, atol=1e-9), (kind, sp)
+                H.assert_in_tolerance_class(gv, wv, scales[sp[0]], f"{kind} {sp}")
+    # rows before the first window start (negative timestamps with an offset): the plan hands everything to shard 0,
+    # which runs as an ordinary rolling (partition.plan)
+    t = np.array([-15, -14, -12, -3, 4, 8, 25, 31, 32, 47], dtype=np.int64)
+    cols = [(t, None), (np.arange(len(t)) * 1.5 - 4.0, None)]
+    shards, s0 = PP.plan_for_columns(t, 10, 7, g)
+    assert shards[0].plain
+    per = [PP.aggregate_shard(cols, s, 0, 10, s0, False, specs) for s in shards if s.num_windows]
+    got = PP.concat_outputs(per)
+    want = R.RefRolling(R.Frame(cols), 0, 10, offset=7).aggregate(specs)
+    scales = H.term_scales(cols, 1, 10, offset=7)
+    for sp, (gv, gm), (wv, wm) in zip(specs, got, want):
+        assert np.array_equal(gm, wm), ("early rows", sp)
+        if sp[0] in EXACT:
+            assert np.array_equal(bits(gv), bits(wv)), ("early rows", sp)
+        else:
+            H.assert_in_tolerance_class(gv, wv, scales[sp[0]], f"early rows {sp}")
     runtime.set_default_ctx(None)
 
 
@@ -412,11 +417,10 @@ def test_pipelined_host_aggregate(ctx, n, kind):
              ("IntegralTrapezoid", 1), ("WeightedAverageStep", 3)]
     got = N.aggregate_host(ctx, cols, 0, interval, specs, offset=5)
     want = R.RefRolling(R.Frame(cols), 0, interval, offset=5).aggregate(specs)
+    scales = {c: H.term_scales(cols, c, interval, offset=5) for c in (1, 3)}
     for sp, (gv, gm), (wv, wm) in zip(specs, got, want):
         assert gv.dtype == wv.dtype and np.array_equal(gm, wm), (n, kind, sp)
-        a, b = gv[gm], wv[wm]
-        if sp[0] in ("Sum", "ArithmeticMean", "IntegralTrapezoid", "WeightedAverageStep"):
-            scale = 2000.0 * (interval if sp[0].startswith("Integral") else 1.0)
-            assert np.all(np.abs(a - b) <= 1e-12 * np.maximum(np.abs(b), scale) * 8), (n, kind, sp)
+        if sp[0] in H.TOL_OPS and not (sp[0] == "Sum" and sp[1] == 3):   # Sum of the int64 column: bit-exact
+            H.assert_in_tolerance_class(gv, wv, scales[sp[1]][sp[0]], f"{n} {kind} {sp}")
         else:
-            assert np.array_equal(a.view(np.int64), b.view(np.int64)), (n, kind, sp)
+            assert np.array_equal(gv[gm].view(np.int64), wv[wm].view(np.int64)), (n, kind, sp)

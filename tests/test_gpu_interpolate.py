@@ -108,13 +108,14 @@ def test_interpolate_then_aggregate(ctx):
     icols = [(vv, None if mm.all() else mm) for vv, mm in icols]
     assert_frames_equal(fi.download(), [(vv, np.ones(len(vv), bool) if mm is None else mm) for vv, mm in icols], "interp")
     want = R.RefRolling(R.Frame(icols), 0, 250, offset=70).aggregate(specs)
+    scales = {c: H.term_scales(icols, c, 250, offset=70) for c in (1, 2)}
     for j, sp in enumerate(specs):
         (gv, gm), (wv, wm) = got[j], want[j]
         assert np.array_equal(gm, wm), sp
         if gv.dtype == np.int64:
             assert np.array_equal(gv, wv), sp
         else:
-            assert np.allclose(gv, wv, rtol=1e-12, atol=1e-9 if sp[0].startswith("Integral") else 1e-12), sp
+            H.assert_in_tolerance_class(gv, wv, scales[sp[1]][sp[0]], str(sp))
 
 
 def test_interpolate_errors_and_empty(ctx):
@@ -339,3 +340,72 @@ def test_interpolate_all_null_column_is_not_quadratic(ctx):
     ts, (sp, spm), (sn, snm), (li, lim) = got[0][0], got[1], got[2], got[3]
     k = np.flatnonzero(ts % interval == 0)[-1]
     assert spm[k] and sp[k] == 0.25 and snm[k] and sn[k] == 9.5 and lim[k] and 0.25 < li[k] < 9.5
+
+
+@pytest.mark.parametrize("vtype", [L.INT64, L.FLOAT64])
+def test_stepnext_is_pinned_on_the_reference_fillnext_goldens(ctx, vtype):
+    """the CUDA StepNext against the reference's own FillNext golden table (G.STEPNEXT_VS_FILLNEXT), materialising and
+    fused entry points"""
+    from bow_b200 import native as N
+    A = G.STEPNEXT_VS_FILLNEXT
+    expected = [c for c in G.FILL_CASES if c[0] == A["expected_case"]][0][3]
+    conv = (lambda x: x) if vtype == L.INT64 else (lambda x: None if x is None else float(x))
+    cols = [[conv(r[c]) for r in G.FILL_ROWS] for c in range(5)]
+    npcols = H.np_cols_from_lists([list(A["times"])] + cols, [L.INT64] + [vtype] * 5)
+    fr = N.Frame.from_numpy(ctx, npcols)
+    r = N.Rolling(fr, 0, A["interval"], offset=A["offset"])
+    out = H.lists_from_np(r.interpolate(["WindowStart"] + ["StepNext"] * 5).download())
+    syn = [i for i, t in enumerate(out[0]) if (t - A["offset"]) % A["interval"] == 0]
+    assert len(syn) == len(A["times"])
+    for k, i in enumerate(syn):
+        H.assert_cols_equal([[out[c + 1][i]] for c in range(5)], [[conv(x)] for x in expected[k]], A["cite"])
+    # fused: First of every window of the interpolated frame is its synthetic row
+    got = r.interpolate_aggregate(["WindowStart"] + ["StepNext"] * 5, [("WindowStart", 0)] + [("First", c) for c in range(1, 6)])
+    for c in range(5):
+        gv, gm = got[c + 1]
+        vals = [None if not ok else (int(x) if vtype == L.INT64 else float(x)) for x, ok in zip(gv.tolist(), gm.tolist())]
+        assert vals == [conv(row[c]) for row in expected], (c, A["cite"])
+    r.close()
+    fr.close()
+
+
+def test_has_start_row_goes_through_float64_above_2_53(ctx):
+    """ns-epoch timestamps (> 2^53, one float64 ulp = 256 ns): the reference decides whether a window has a start row
+    through float64 (interpolation.go:121-128), so a first row within +-128 ns of S_k counts as the start row.  The
+    materialising Interpolate must reproduce that, and the fused call must notice it cannot (ST_INEXACT_START) and give
+    the same results through the materialising chain."""
+    from bow_b200 import native as N
+    rng = np.random.default_rng(77)
+    n, sec = 6000, 1_000_000_000
+    interval = 60 * sec
+    t0 = 1_700_000_000_000_000_000 // interval * interval       # a window start
+    t = t0 + np.arange(n, dtype=np.int64) * sec
+    jitter = rng.integers(-300, 300, size=n)                      # some land within 128 ns of a start, some do not
+    jitter[rng.random(n) < 0.3] = 0
+    t = np.sort(t + jitter)
+    assert int(t[0]) > 2 ** 53
+    a = H.random_values(rng, n, np.float64, 0.2)
+    b = H.random_values(rng, n, np.int64, 0.1)
+    cols = [(t, None), a, b]
+    ops = ["WindowStart", "Linear", "StepPrevious"]
+    fr = N.Frame.from_numpy(ctx, cols)
+    r = N.Rolling(fr, 0, interval)
+    out = r.interpolate(ops)
+    got = out.download()
+    out.close()
+    ref = R.RefRolling(R.Frame(cols), 0, interval)
+    want = ref.interpolate(ops)
+    n_exact = int(np.sum(t % interval == 0))
+    starts = ((t + interval // 2) // interval) * interval
+    n_near = int(np.sum(np.abs(t - starts) <= 128)) - n_exact
+    assert n_near > 5, "the test data must hold rows that match a window start only through float64"
+    assert_frames_equal(got, want, "ns-epoch interpolate")
+    specs = [("WindowStart", 0), ("Count", 1), ("First", 2), ("Last", 1), ("Max", 2)]
+    fused = r.interpolate_aggregate(ops, specs)
+    icols = [(vv, None if mm.all() else mm) for vv, mm in want]
+    chain = R.RefRolling(R.Frame(icols), 0, interval).aggregate(specs)
+    for sp, (gv, gm), (wv, wm) in zip(specs, fused, chain):
+        assert np.array_equal(gm, wm), sp
+        assert np.array_equal(bits(gv)[gm], bits(wv)[wm]), sp
+    r.close()
+    fr.close()

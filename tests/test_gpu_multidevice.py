@@ -5,6 +5,7 @@ import pytest
 
 from bow_b200 import parallel as PP
 from oracle import refc as R
+from tests import helpers as H
 
 pytestmark = pytest.mark.gpu
 
@@ -29,10 +30,11 @@ def test_two_contexts_one_process():
         outs.append(r.aggregate(specs))
     got = PP.concat_outputs(outs)
     want = R.RefRolling(R.Frame(cols), 0, interval, inclusive=True).aggregate(specs)
+    scales = H.term_scales(cols, 1, interval, inclusive=True)
     for sp, (gv, gm), (wv, wm) in zip(specs, got, want):
         assert np.array_equal(gm, wm), sp
         if sp[0] in ("Sum", "IntegralTrapezoid"):
-            assert np.allclose(gv[gm], wv[wm], rtol=1e-12, atol=1e-9), sp
+            H.assert_in_tolerance_class(gv, wv, scales[sp[0]], str(sp))
         else:
             assert np.array_equal(gv[gm].view(np.int64), wv[wm].view(np.int64)), sp
     for c in ctxs:

@@ -195,3 +195,27 @@ def test_whole_aggregate_api(name, rows, aggs, expected, cite):  # rolling/aggre
     got = aggregation.Aggregate(b, G.TIME, *la)
     want = B.NewBowFromColBasedInterfaces(expected["names"], [TYPES[t] for t in expected["types"]], expected["cols"])
     assert got.Equal(want), f"{cite}\nexpected: {want}\nactual: {got}"
+
+
+def test_interpolating_the_interval_column_with_none_fails_like_the_eager_path():
+    """Interpolate(None(time), ...) leaves null timestamps: the Rolling built on the interpolated Bow fails in
+    newIntervalRolling (rolling.go:91-94, deferred error).  The lazy (fused) Interpolate must not hide that behind the
+    parent's window lattice."""
+    t = np.arange(0, 40, 3, dtype=np.int64) + 1          # no row on a window start: every window gets a start row
+    b = B.NewBow(B.NewSeriesFromNumpy("time", t, None), B.NewSeriesFromNumpy("v", np.arange(len(t)) * 0.5, None))
+    r = rolling.IntervalRolling(b, "time", 10).Interpolate(interpolation.None_("time"), interpolation.Linear("v"))
+    with pytest.raises(B.BowError):
+        r.NumWindows()
+    with pytest.raises(B.BowError):
+        r.Aggregate(aggregation.WindowStart("time"), aggregation.Count("v")).Bow()
+
+
+def test_prev_row_must_match_the_bow_columns():
+    t = np.arange(0, 40, 3, dtype=np.int64) + 1
+    b = B.NewBow(B.NewSeriesFromNumpy("time", t, None), B.NewSeriesFromNumpy("v", np.arange(len(t)) * 0.5, None))
+    short = B.NewBow(B.NewSeriesFromNumpy("time", np.array([0], dtype=np.int64), None))
+    swapped = B.NewBow(B.NewSeriesFromNumpy("v", np.array([0.5]), None), B.NewSeriesFromNumpy("time", np.array([0], dtype=np.int64), None))
+    for bad in (short, swapped):
+        r = rolling.IntervalRolling(b, "time", 10, rolling.Options(PrevRow=bad))
+        with pytest.raises(B.BowError, match="prevRow must have the same columns"):
+            r.Interpolate(interpolation.WindowStart("time"), interpolation.StepPrevious("v")).Bow()

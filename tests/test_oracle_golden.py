@@ -152,3 +152,31 @@ def test_factor(name, x, expected):
     assert L.Factor(0.1)(x) == expected
     with pytest.raises(TypeError, match="factor: invalid type str"):
         L.Factor(0.1)("11")
+
+
+@pytest.mark.parametrize("vtype", [L.INT64, L.FLOAT64])
+def test_stepnext_is_pinned_on_the_reference_fillnext_goldens(vtype):
+    """interpolation.StepNext does not exist upstream; its next-valid semantics are pinned on the reference's FillNext
+    golden table instead (see G.STEPNEXT_VS_FILLNEXT): both oracles."""
+    import numpy as np
+    from oracle import refc as R
+    from tests import helpers as H
+    A = G.STEPNEXT_VS_FILLNEXT
+    case = [c for c in G.FILL_CASES if c[0] == A["expected_case"]][0]
+    expected = case[3]            # (the Float64 table of this case is the same, bowfill_test.go:269-288)
+    conv = (lambda x: x) if vtype == L.INT64 else (lambda x: None if x is None else float(x))
+    cols = [[conv(r[c]) for r in G.FILL_ROWS] for c in range(5)]
+    names = ["t", "a", "b", "c", "d", "e"]
+    fr = L.Frame(names, [L.INT64] + [vtype] * 5, [list(A["times"])] + cols)
+    r = L.IntervalRolling.create(fr, "t", A["interval"], L.Options(offset=A["offset"]))
+    out = r.interpolate(L.InterpWindowStart("t"), *[L.InterpStepNext(n) for n in names[1:]]).bow.materialize()
+    syn = [i for i, t in enumerate(out[0]) if (t - A["offset"]) % A["interval"] == 0]    # the synthetic rows
+    assert len(syn) == len(A["times"]) and len(out[0]) == 2 * len(A["times"])
+    for k, i in enumerate(syn):
+        assert [out[c + 1][i] for c in range(5)] == [conv(x) for x in expected[k]], (k, A["cite"])
+    # the C oracle
+    npcols = H.np_cols_from_lists([list(A["times"])] + cols, [L.INT64] + [vtype] * 5)
+    got = R.RefRolling(R.Frame(npcols), 0, A["interval"], offset=A["offset"]).interpolate(["WindowStart"] + ["StepNext"] * 5)
+    got = H.lists_from_np([(v, m) for v, m in got])
+    for k, i in enumerate(syn):
+        assert [got[c + 1][i] for c in range(5)] == [conv(x) for x in expected[k]], (k, "C oracle")

@@ -20,6 +20,8 @@ SPECS = [("WindowStart", 0), ("Count", 1), ("Sum", 1), ("ArithmeticMean", 1), ("
 def oracle_executor(cols, time_col, interval, s0, num_windows, inclusive, specs):
     """Shard executor backed by the oracle: runs it on the shard's rows and re-indexes its windows onto the
     pinned lattice (s0, num_windows); windows without rows get the empty-window defaults."""
+    if num_windows < 0:      # a `plain` shard (rows before the first window start): the whole frame, unsharded
+        return R.RefRolling(R.Frame(cols), time_col, interval, offset=s0 % interval, inclusive=inclusive).aggregate(specs)
     outs = []
     n = len(cols[0][0])
     ref_out, k_off, wl = None, 0, 0
@@ -197,3 +199,24 @@ def test_sharded_interpolate_matches_unsharded(kind, g, OPS):
         for (o, own), nxt in zip(per, per[1:]):
             if len(o[0][0]) > own and nxt[1] > 0:
                 assert o[0][0][own] == nxt[0][0][0][0]
+
+
+@pytest.mark.parametrize("g", [2, 3, 8])
+def test_rows_before_the_first_window_start_are_not_cut(g):
+    """negative timestamps with an offset: Go's truncating division puts the first window start AFTER the first rows
+    (t_first = -15, interval 10, offset 7 -> s0 = -13; rolling.go:96-99).  Window 0 keeps those rows iff it holds a row of
+    its own (rolling.go:194-211): only the unsharded iterator knows, so `plan` hands the whole frame to shard 0."""
+    for t_list, interval, offset in (([-15, -14, -12, -3, 4, 8, 25, 31], 10, 7), ([-15, -1, 0, 9, 13], 10, 7),
+                                     ([-29, -28, 40, 41, 99], 10, 3)):
+        t = np.array(t_list, dtype=np.int64)
+        v = (np.arange(len(t), dtype=np.float64) + 0.5, None)
+        cols = [(t, None), v]
+        off = P.normalise_offset(interval, offset)
+        assert int(t[0]) < P.first_window_start(int(t[0]), interval, off)
+        shards, s0 = PP.plan_for_columns(t, interval, offset, g)
+        assert shards[0].plain and shards[0].row_hi == len(t) and all(s.num_windows == 0 for s in shards[1:])
+        per = [PP.aggregate_shard(cols, s, 0, interval, s0, False, SPECS, executor=oracle_executor) for s in shards if s.num_windows]
+        got = PP.concat_outputs(per)
+        want = R.RefRolling(R.Frame(cols), 0, interval, offset=offset).aggregate(SPECS)
+        for sp, (gv, gm), (wv, wm) in zip(SPECS, got, want):
+            assert np.array_equal(gm, wm) and np.array_equal(gv[gm].view(np.int64), wv[wm].view(np.int64)), sp
