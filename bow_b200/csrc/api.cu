@@ -2013,15 +2013,20 @@ extern "C" int32_t bowgpu_rolling_interpolate_aggregate(bowgpu_rolling *r, const
 }
 
 // ================================================================================================
-// one-shot, pipelined host -> host aggregation
+// one-shot, pipelined host -> host calls (one process, one or several GPUs)
 // ================================================================================================
-// rolling.IntervalRolling(b, col, interval, opts).Aggregate(aggrs...) for a Bow that lives in HOST memory, results into
-// host buffers, in ONE call.  The window range is cut into chunks (multiples of 64 windows, so validity bitmaps land
-// byte aligned; each chunk carries the one-row halo of an inclusive window) exactly like the multi-GPU partitioning
-// (SURVEY 8e), and a few worker contexts - own stream, arena and pool each - run upload -> kernels -> download of
-// different chunks concurrently: the device-to-host copies and the kernels of one chunk hide behind the host-to-device
-// copy of the next, so the call takes the PCIe time of the inputs and little else.  Only the columns the aggregations
-// read are uploaded.
+// rolling.IntervalRolling(b, col, interval, opts)[.Interpolate(...)].Aggregate(aggrs...) for a Bow that lives in HOST
+// memory, results into host buffers, in ONE call (rolling.go:60, interpolation.go:30-69, aggregation.go:123-145).  The
+// window range is cut into chunks (multiples of 64 windows, so validity bitmaps land byte aligned; every chunk carries
+// its halo rows) exactly like the multi-GPU partitioning, and worker contexts - own stream, arena and pool
+// each, a few per GPU, on every GPU the caller lists - run upload -> kernels -> download of different chunks
+// concurrently: the device-to-host copies and the kernels of one chunk hide behind the host-to-device copy of the next,
+// so the call takes the PCIe time of the inputs and little else.  Only the columns the operators read are uploaded.
+// Worker threads belong to the library (never the caller's thread: a cgo call arrives on a Go runtime thread) and bind
+// themselves to the CPUs next to their GPU, so that pinned staging buffers are allocated NUMA-local.
+#include <sched.h>
+
+#include <mutex>
 namespace {
 
 int64_t host_time_at(const bowgpu_col &c, int64_t i) { return ((const int64_t *)c.values)[c.offset + i]; }
@@ -2037,118 +2042,258 @@ int64_t host_lower_bound(const bowgpu_col &c, int64_t n, int64_t x) {
     }
     return lo;
 }
+bool host_valid(const bowgpu_col &c, int64_t i) {
+    if (!c.validity || c.null_count == 0) return true;
+    const int64_t b = c.offset + i;
+    return (c.validity[b >> 3] >> (b & 7)) & 1;
+}
+// last row before `row` holding a valid value (0 if none) / one past the first row at or after `row` holding one (n if none)
+int64_t host_prev_valid(const bowgpu_col &c, int64_t row) {
+    for (int64_t i = row - 1; i >= 0; --i)
+        if (host_valid(c, i)) return i;
+    return 0;
+}
+int64_t host_next_valid_end(const bowgpu_col &c, int64_t n, int64_t row) {
+    for (int64_t i = row; i < n; ++i)
+        if (host_valid(c, i)) return i + 1;
+    return n;
+}
 
-}  // namespace
+// CPUs next to a GPU (sysfs local_cpulist of its PCI function); the calling thread is bound to them
+void bind_thread_near_device(int device) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    for (char *p = bus; *p; ++p) *p = (char)tolower(*p);
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/local_cpulist", bus);
+    FILE *f = fopen(path, "r");
+    if (!f) return;
+    char line[1024] = {0};
+    const bool ok = fgets(line, sizeof line, f) != nullptr;
+    fclose(f);
+    if (!ok) return;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int n = 0;
+    for (char *p = line; *p && *p != '\n';) {  // "0-15,32-47"
+        char *e;
+        long a = strtol(p, &e, 10);
+        if (e == p) break;
+        long b = a;
+        if (*e == '-') b = strtol(e + 1, &e, 10);
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c) CPU_SET((int)c, &set), ++n;
+        p = *e == ',' ? e + 1 : e;
+    }
+    if (n > 0) sched_setaffinity(0, sizeof set, &set);  // (tid 0 = the calling thread)
+}
 
-extern "C" int32_t bowgpu_aggregate_host(bowgpu_ctx *ctx, const bowgpu_col *cols, int32_t ncols, int32_t time_col,
-                                         int64_t interval, int64_t offset, int32_t inclusive,
-                                         const bowgpu_agg_spec *specs, int32_t nspecs, bowgpu_out_col *outs,
-                                         int64_t out_capacity, int64_t *num_windows) {
-    if (!ctx || !cols || !specs || !outs || ncols <= 0 || nspecs <= 0 || !num_windows) return BOWGPU_EINVAL;
+struct HostChunk {
+    int64_t k_lo, k_hi;      // windows owned
+    int64_t frame_lo;        // first row shipped (rows before row_lo: left halo of an interpolation)
+    int64_t row_lo;          // first row of window k_lo
+    int64_t halo_hi;         // one past the last row shipped
+};
+
+struct HostCall {
+    const bowgpu_col *cols;
+    int32_t ncols, time_col;
+    int64_t interval, offset;
+    int32_t inclusive;
+    const int32_t *ops;  // interpolations (null: plain Aggregate)
+    int32_t nops;
+    const bowgpu_col *prev_row;
+    const bowgpu_agg_spec *specs;
+    int32_t nspecs;
+    bowgpu_out_col *outs;
+    int64_t out_capacity;
+    int64_t *num_windows;
+    const bowgpu_host_opts *opts;
+};
+
+// worker contexts of `ctx` on `device` (created on first use, kept for the next call)
+int32_t workers_for(bowgpu_ctx *ctx, int device, int count, const std::vector<bowgpu_ctx *> &taken,
+                    std::vector<bowgpu_ctx *> &out) {
+    out.clear();
+    for (bowgpu_ctx *w : ctx->workers)  // (a device listed twice gets two sets of workers)
+        if (w->device == device && (int)out.size() < count && std::find(taken.begin(), taken.end(), w) == taken.end()) out.push_back(w);
+    while ((int)out.size() < count) {
+        bowgpu_ctx *w = nullptr;
+        int32_t rc = bowgpu_ctx_create(device, nullptr, &w);
+        if (rc) return fail(ctx, rc, "worker context on device %d", device);
+        ctx->workers.push_back(w);
+        out.push_back(w);
+    }
+    return BOWGPU_OK;
+}
+
+int32_t host_pipeline(bowgpu_ctx *ctx, const HostCall &H) {
+    if (!ctx || !H.cols || !H.specs || !H.outs || H.ncols <= 0 || H.nspecs <= 0 || !H.num_windows) return BOWGPU_EINVAL;
     Guard gd(ctx);
-    *num_windows = 0;
-    if (time_col < 0 || time_col >= ncols) return fail(ctx, BOWGPU_EINVAL, "time column index %d out of range", time_col);
-    const bowgpu_col &tc = cols[time_col];
+    *H.num_windows = 0;
+    const bowgpu_host_opts none = {};
+    const bowgpu_host_opts &O = H.opts ? *H.opts : none;
+    const bool interp = H.ops != nullptr;
+    if (H.time_col < 0 || H.time_col >= H.ncols) return fail(ctx, BOWGPU_EINVAL, "time column index %d out of range", H.time_col);
+    if (interp && H.nops != H.ncols)
+        return fail(ctx, BOWGPU_EINVAL, "interpolations must name every column in schema order (%d given, %d columns)", H.nops, H.ncols);
+    const bowgpu_col &tc = H.cols[H.time_col];
     const int64_t n = tc.length;
-    auto plain = [&]() -> int32_t {  // upload everything, one pass (small inputs and the cases chunks do not cover)
+    auto plain = [&]() -> int32_t {  // upload everything, one pass on the ctx's own device (small inputs, corner cases)
         bowgpu_frame *f = nullptr;
         bowgpu_rolling *r = nullptr;
-        int32_t rc = bowgpu_frame_create(ctx, cols, ncols, BOWGPU_MEM_HOST, &f);
-        if (rc == BOWGPU_OK) rc = bowgpu_rolling_create(f, time_col, interval, offset, inclusive, nullptr, &r);
+        int32_t rc = bowgpu_frame_create(ctx, H.cols, H.ncols, BOWGPU_MEM_HOST, &f);
+        if (rc == BOWGPU_OK)
+            rc = O.shard ? bowgpu_rolling_create_shard(f, H.time_col, H.interval, O.s0, O.num_windows, H.inclusive, H.prev_row, &r)
+                         : bowgpu_rolling_create(f, H.time_col, H.interval, H.offset, H.inclusive, H.prev_row, &r);
         if (rc == BOWGPU_OK) {
-            *num_windows = r->W;
-            if (r->W > out_capacity) rc = fail(ctx, BOWGPU_ECAPACITY, "%lld windows, capacity %lld", (long long)r->W, (long long)out_capacity);
+            *H.num_windows = r->W;
+            if (r->W > H.out_capacity) rc = fail(ctx, BOWGPU_ECAPACITY, "%lld windows, capacity %lld", (long long)r->W, (long long)H.out_capacity);
         }
-        if (rc == BOWGPU_OK) rc = bowgpu_rolling_aggregate(r, specs, nspecs, outs, BOWGPU_MEM_HOST);
+        if (rc == BOWGPU_OK)
+            rc = interp ? bowgpu_rolling_interpolate_aggregate(r, H.ops, H.nops, H.specs, H.nspecs, H.outs, BOWGPU_MEM_HOST)
+                        : bowgpu_rolling_aggregate(r, H.specs, H.nspecs, H.outs, BOWGPU_MEM_HOST);
         bowgpu_rolling_destroy(r);
         bowgpu_frame_destroy(f);
         return rc;
     };
-    if (tc.dtype != BOWGPU_INT64 || interval <= 0 || n < (int64_t)4 << 20 || (tc.validity && tc.null_count != 0)) return plain();
-    for (int j = 0; j < nspecs; ++j)
-        if (specs[j].col < 0 || specs[j].col >= ncols) return fail(ctx, BOWGPU_EINVAL, "aggregation %d: no column %d", j, specs[j].col);
-    // lattice, rolling.go:96-99,114-128,143-154
-    int64_t off = offset;
-    if (off >= interval || off <= -interval) off %= interval;
-    if (off < 0) off += interval;
+    const int64_t min_rows = O.chunk_rows > 0 ? 2 * O.chunk_rows : (int64_t)4 << 20;
+    if (tc.dtype != BOWGPU_INT64 || H.interval <= 0 || n < min_rows || (tc.validity && tc.null_count != 0)) return plain();
+    if (interp && (H.inclusive || H.ops[H.time_col] != BOWGPU_INTERP_WINDOW_START)) return plain();
+    for (int j = 0; j < H.nspecs; ++j)
+        if (H.specs[j].col < 0 || H.specs[j].col >= H.ncols) return fail(ctx, BOWGPU_EINVAL, "aggregation %d: no column %d", j, H.specs[j].col);
+    // lattice, rolling.go:96-99,114-128,143-154 (a shard brings its own)
     const int64_t t_first = host_time_at(tc, 0), t_last = host_time_at(tc, n - 1);
-    int64_t s0 = (int64_t)((uint64_t)((t_first / interval) * interval) + (uint64_t)off);
-    if (s0 > t_first) s0 = (int64_t)((uint64_t)s0 - (uint64_t)interval);
-    if (t_first < s0 || t_last < t_first) return plain();  // rows before the first window start / obviously unsorted
-    const int64_t W = (int64_t)(((uint64_t)t_last - (uint64_t)s0) / (uint64_t)interval) + 1;
-    *num_windows = W;
-    if (W > out_capacity) return fail(ctx, BOWGPU_ECAPACITY, "%lld windows, capacity %lld", (long long)W, (long long)out_capacity);
+    int64_t s0, W;
+    if (O.shard) {
+        s0 = O.s0;
+        W = O.num_windows;
+        if (W < 0) return BOWGPU_EINVAL;
+    } else {
+        int64_t off = H.offset;
+        if (off >= H.interval || off <= -H.interval) off %= H.interval;
+        if (off < 0) off += H.interval;
+        s0 = (int64_t)((uint64_t)((t_first / H.interval) * H.interval) + (uint64_t)off);
+        if (s0 > t_first) s0 = (int64_t)((uint64_t)s0 - (uint64_t)H.interval);
+        if (t_last < t_first) return plain();  // obviously unsorted: the plain path reports it
+        W = (int64_t)(((uint64_t)t_last - (uint64_t)s0) / (uint64_t)H.interval) + 1;
+    }
+    if (t_first < s0) return plain();  // rows before the first window start (or a left halo the caller shipped)
+    *H.num_windows = W;
+    if (W > H.out_capacity) return fail(ctx, BOWGPU_ECAPACITY, "%lld windows, capacity %lld", (long long)W, (long long)H.out_capacity);
 
-    // columns actually read, remapped to a compact frame
-    std::vector<int> used, remap(ncols, -1);
+    // columns actually read, remapped to a compact frame (an interpolation reads every column: positional append)
+    std::vector<int> used, remap(H.ncols, -1);
     auto use = [&](int c) {
         if (remap[c] < 0) {
             remap[c] = (int)used.size();
             used.push_back(c);
         }
     };
-    use(time_col);
-    for (int j = 0; j < nspecs; ++j) use(specs[j].col);
-    std::vector<bowgpu_agg_spec> sp(specs, specs + nspecs);
+    if (interp)
+        for (int c = 0; c < H.ncols; ++c) use(c);
+    use(H.time_col);
+    for (int j = 0; j < H.nspecs; ++j) use(H.specs[j].col);
+    std::vector<bowgpu_agg_spec> sp(H.specs, H.specs + H.nspecs);
     for (auto &x : sp) x.col = remap[x.col];
-    for (int j = 0; j < nspecs; ++j) outs[j].dtype = bowgpu_agg_return_type(specs[j].op, cols[specs[j].col].dtype);
+    for (int j = 0; j < H.nspecs; ++j) H.outs[j].dtype = bowgpu_agg_return_type(H.specs[j].op, H.cols[H.specs[j].col].dtype);
 
     // chunks of ~12M rows (a few ms of PCIe each), cut on multiples of 64 windows
-    const int64_t target_rows = (int64_t)12 << 20;
+    const int64_t target_rows = O.chunk_rows > 0 ? O.chunk_rows : (int64_t)12 << 20;
     int64_t nchunks = (n + target_rows - 1) / target_rows;
     if (nchunks > W / 64) nchunks = W / 64;
     if (nchunks < 2) return plain();
-    struct Chunk {
-        int64_t k_lo, k_hi, row_lo, row_hi;
-    };
-    std::vector<Chunk> chunks;
+    auto start_of = [&](int64_t k) { return (int64_t)((uint64_t)s0 + (uint64_t)k * (uint64_t)H.interval); };
+    std::vector<int> icols;  // columns whose interpolation looks at neighbouring valid rows
+    if (interp)
+        for (int c = 0; c < H.ncols; ++c)
+            if (H.ops[c] == BOWGPU_INTERP_LINEAR || H.ops[c] == BOWGPU_INTERP_STEP_PREVIOUS || H.ops[c] == BOWGPU_INTERP_STEP_NEXT) icols.push_back(c);
+    std::vector<HostChunk> chunks;
     int64_t k_prev = 0, row_prev = 0;
     for (int64_t c = 1; c <= nchunks; ++c) {
-        int64_t k = c == nchunks ? W : ((c * W) / nchunks) / 64 * 64;
+        const int64_t k = c == nchunks ? W : ((c * W) / nchunks) / 64 * 64;
         if (k <= k_prev) continue;
-        const int64_t row = c == nchunks ? n : host_lower_bound(tc, n, (int64_t)((uint64_t)s0 + (uint64_t)k * (uint64_t)interval));
-        int64_t hi = row;
-        if (c != nchunks && row < n) hi = row + 1;  // halo: the row an inclusive last window may borrow
-        chunks.push_back({k_prev, k, row_prev, hi});
+        const int64_t row = c == nchunks ? n : host_lower_bound(tc, n, start_of(k));
+        HostChunk ch{k_prev, k, row_prev, row_prev, row};
+        if (!interp) {
+            if (c != nchunks && row < n) ch.halo_hi = row + 1;  // halo: the row an inclusive last window may borrow
+        } else {
+            // SURVEY 8e / partition.plan_interpolate: left halo back to the last valid row of every interpolated column (what
+            // Linear / StepPrevious look up for the chunk's first windows), ONE EXTRA WINDOW on the right (its start row is the
+            // inclusive row of the chunk's last window) and a right halo up to the next valid row of every column
+            const int64_t extra = k < W ? 1 : 0;
+            const int64_t k_last = k - 1 + extra;
+            const int64_t end_rows = k_last + 1 < W ? host_lower_bound(tc, n, start_of(k_last + 1)) : n;
+            const int64_t r_last = host_lower_bound(tc, n, start_of(k_last));
+            int64_t hi = std::min<int64_t>(n, end_rows + 1);
+            for (int ic : icols) hi = std::max(hi, host_next_valid_end(H.cols[ic], n, r_last));
+            ch.halo_hi = std::min<int64_t>(n, hi);
+            if (row_prev > 0) {
+                int64_t lo = row_prev - 1;
+                for (int ic : icols) lo = std::min(lo, host_prev_valid(H.cols[ic], row_prev));
+                ch.frame_lo = std::max<int64_t>(0, lo);
+            }
+        }
+        chunks.push_back(ch);
         k_prev = k;
         row_prev = row;
     }
-    const int nworkers = (int)std::min<size_t>(3, chunks.size());
-    while ((int)ctx->workers.size() < nworkers) {
-        bowgpu_ctx *w = nullptr;
-        int32_t rc = bowgpu_ctx_create(ctx->device, nullptr, &w);
-        if (rc) return fail(ctx, rc, "worker context");
-        ctx->workers.push_back(w);
+    // workers: a few per device, on every device the caller lists
+    std::vector<int> devs;
+    if (O.devices && O.ndevices > 0)
+        devs.assign(O.devices, O.devices + O.ndevices);
+    else
+        devs.push_back(ctx->device);
+    const int per_dev = O.workers_per_device > 0 ? O.workers_per_device : 3;
+    std::vector<bowgpu_ctx *> workers;
+    for (int d : devs) {
+        std::vector<bowgpu_ctx *> w;
+        const int want = (int)std::min<size_t>((size_t)per_dev, (chunks.size() + devs.size() - 1) / devs.size());
+        int32_t rc = workers_for(ctx, d, std::max(want, 1), workers, w);
+        if (rc) return rc;
+        workers.insert(workers.end(), w.begin(), w.end());
     }
+    const int nworkers = (int)workers.size();
     std::atomic<size_t> next{0};
     std::vector<int32_t> status(nworkers, BOWGPU_OK);
     std::vector<std::string> errs(nworkers);
     auto work = [&](int wi) {
-        bowgpu_ctx *wc = ctx->workers[wi];
+        bowgpu_ctx *wc = workers[wi];
         cudaSetDevice(wc->device);
+        bind_thread_near_device(wc->device);
         for (;;) {
             const size_t ci = next.fetch_add(1);
             if (ci >= chunks.size() || status[wi] != BOWGPU_OK) return;
-            const Chunk &ch = chunks[ci];
+            const HostChunk &ch = chunks[ci];
             std::vector<bowgpu_col> cc(used.size());
             for (size_t u = 0; u < used.size(); ++u) {
-                cc[u] = cols[used[u]];
-                cc[u].offset += ch.row_lo;
-                cc[u].length = ch.row_hi - ch.row_lo;
+                cc[u] = H.cols[used[u]];
+                cc[u].offset += ch.frame_lo;
+                cc[u].length = ch.halo_hi - ch.frame_lo;
                 if (cc[u].validity && cc[u].null_count != 0) cc[u].null_count = -1;  // counted on the device
             }
-            std::vector<bowgpu_out_col> oc(nspecs);
-            for (int j = 0; j < nspecs; ++j) {
-                oc[j].values = (char *)outs[j].values + ch.k_lo * 8;
-                oc[j].validity = outs[j].validity + ch.k_lo / 8;
+            std::vector<bowgpu_out_col> oc(H.nspecs);
+            for (int j = 0; j < H.nspecs; ++j) {
+                oc[j].values = (char *)H.outs[j].values + ch.k_lo * 8;
+                oc[j].validity = H.outs[j].validity + ch.k_lo / 8;
             }
             bowgpu_frame *f = nullptr;
             bowgpu_rolling *r = nullptr;
             int32_t rc = bowgpu_frame_create(wc, cc.data(), (int32_t)cc.size(), BOWGPU_MEM_HOST, &f);
             if (rc == BOWGPU_OK)
-                rc = bowgpu_rolling_create_shard(f, remap[time_col], interval, (int64_t)((uint64_t)s0 + (uint64_t)ch.k_lo * (uint64_t)interval),
-                                                 ch.k_hi - ch.k_lo, inclusive, nullptr, &r);
-            if (rc == BOWGPU_OK) rc = aggregate_dispatch(r, sp.data(), nspecs, oc.data(), BOWGPU_MEM_HOST, nullptr);
+                rc = bowgpu_rolling_create_shard(f, remap[H.time_col], H.interval, start_of(ch.k_lo), ch.k_hi - ch.k_lo, H.inclusive,
+                                                 ci == 0 && ch.frame_lo == 0 ? H.prev_row : nullptr, &r);
+            if (rc == BOWGPU_OK) {
+                if (interp) {
+                    std::vector<int32_t> ops(used.size());
+                    for (size_t u = 0; u < used.size(); ++u) ops[u] = H.ops[used[u]];
+                    rc = bowgpu_rolling_interpolate_aggregate(r, ops.data(), (int32_t)ops.size(), sp.data(), H.nspecs, oc.data(), BOWGPU_MEM_HOST);
+                } else {
+                    rc = aggregate_dispatch(r, sp.data(), H.nspecs, oc.data(), BOWGPU_MEM_HOST, nullptr);
+                }
+            }
             if (rc != BOWGPU_OK) {
                 status[wi] = rc;
                 errs[wi] = wc->err;
@@ -2158,10 +2303,37 @@ extern "C" int32_t bowgpu_aggregate_host(bowgpu_ctx *ctx, const bowgpu_col *cols
         }
     };
     std::vector<std::thread> threads;
-    for (int wi = 1; wi < nworkers; ++wi) threads.emplace_back(work, wi);
-    work(0);
+    for (int wi = 0; wi < nworkers; ++wi) threads.emplace_back(work, wi);
     for (auto &t : threads) t.join();
     for (int wi = 0; wi < nworkers; ++wi)
         if (status[wi] != BOWGPU_OK) return fail(ctx, status[wi], "%s", errs[wi].c_str());
     return BOWGPU_OK;
+}
+
+}  // namespace
+
+extern "C" int32_t bowgpu_aggregate_host_ex(bowgpu_ctx *ctx, const bowgpu_col *cols, int32_t ncols, int32_t time_col,
+                                            int64_t interval, int64_t offset, int32_t inclusive,
+                                            const bowgpu_agg_spec *specs, int32_t nspecs, bowgpu_out_col *outs,
+                                            int64_t out_capacity, int64_t *num_windows, const bowgpu_host_opts *opts) {
+    HostCall H{cols, ncols, time_col, interval, offset, inclusive, nullptr, 0, nullptr, specs, nspecs, outs, out_capacity, num_windows, opts};
+    return host_pipeline(ctx, H);
+}
+
+extern "C" int32_t bowgpu_aggregate_host(bowgpu_ctx *ctx, const bowgpu_col *cols, int32_t ncols, int32_t time_col,
+                                         int64_t interval, int64_t offset, int32_t inclusive,
+                                         const bowgpu_agg_spec *specs, int32_t nspecs, bowgpu_out_col *outs,
+                                         int64_t out_capacity, int64_t *num_windows) {
+    return bowgpu_aggregate_host_ex(ctx, cols, ncols, time_col, interval, offset, inclusive, specs, nspecs, outs, out_capacity,
+                                    num_windows, nullptr);
+}
+
+extern "C" int32_t bowgpu_interpolate_aggregate_host(bowgpu_ctx *ctx, const bowgpu_col *cols, int32_t ncols, int32_t time_col,
+                                                     int64_t interval, int64_t offset, const bowgpu_col *prev_row,
+                                                     const int32_t *ops, int32_t nops, const bowgpu_agg_spec *specs,
+                                                     int32_t nspecs, bowgpu_out_col *outs, int64_t out_capacity,
+                                                     int64_t *num_windows, const bowgpu_host_opts *opts) {
+    if (!ops) return BOWGPU_EINVAL;
+    HostCall H{cols, ncols, time_col, interval, offset, 0, ops, nops, prev_row, specs, nspecs, outs, out_capacity, num_windows, opts};
+    return host_pipeline(ctx, H);
 }

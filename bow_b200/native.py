@@ -38,7 +38,7 @@ SYMBOLS = [
     "bowgpu_rolling_bounds", "bowgpu_rolling_aggregate", "bowgpu_agg_return_type", "bowgpu_agg_needs_inclusive",
     "bowgpu_rolling_interpolate", "bowgpu_frame_aggregate_whole", "bowgpu_frame_fill", "bowgpu_frame_fill_linear",
     "bowgpu_rolling_interpolate_aggregate", "bowgpu_frame_drop_nils", "bowgpu_frame_is_col_sorted",
-    "bowgpu_aggregate_host", "bowgpu_frame_sort_by_col",
+    "bowgpu_aggregate_host", "bowgpu_frame_sort_by_col", "bowgpu_aggregate_host_ex", "bowgpu_interpolate_aggregate_host",
 ]
 
 
@@ -66,6 +66,12 @@ class OutCol(C.Structure):
 class Timing(C.Structure):
     _fields_ = [("total_ms", C.c_float), ("main_ms", C.c_float), ("launches", C.c_int32),
                 ("main_launches", C.c_int32)]
+
+
+class HostOpts(C.Structure):
+    _fields_ = [("devices", C.POINTER(C.c_int32)), ("ndevices", C.c_int32), ("workers_per_device", C.c_int32),
+                ("chunk_rows", C.c_int64), ("shard", C.c_int32), ("_pad", C.c_int32), ("s0", C.c_int64),
+                ("num_windows", C.c_int64)]
 
 
 class GenSpec(C.Structure):
@@ -112,6 +118,11 @@ def lib():
         L.bowgpu_aggregate_host.argtypes = [C.c_void_p, C.POINTER(Col), C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int32,
                                             C.POINTER(AggSpec), C.c_int32, C.POINTER(OutCol), C.c_int64,
                                             C.POINTER(C.c_int64)]
+        L.bowgpu_aggregate_host_ex.argtypes = L.bowgpu_aggregate_host.argtypes + [C.POINTER(HostOpts)]
+        L.bowgpu_interpolate_aggregate_host.argtypes = [C.c_void_p, C.POINTER(Col), C.c_int32, C.c_int32, C.c_int64, C.c_int64,
+                                                        C.POINTER(Col), C.POINTER(C.c_int32), C.c_int32, C.POINTER(AggSpec),
+                                                        C.c_int32, C.POINTER(OutCol), C.c_int64, C.POINTER(C.c_int64),
+                                                        C.POINTER(HostOpts)]
         L.bowgpu_frame_drop_nils.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p)]
         L.bowgpu_frame_is_col_sorted.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
         L.bowgpu_frame_sort_by_col.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
@@ -220,17 +231,21 @@ class Ctx:
             pass
 
 
-def aggregate_host(ctx: "Ctx", cols: Sequence[NpCol], time_col: int, interval: int, specs: Sequence[tuple],
-                   offset: int = 0, inclusive: bool = False, num_windows: Optional[int] = None):
-    """One-shot pipelined IntervalRolling -> Aggregate from host columns to host results (bowgpu_aggregate_host)
-    -> list of (values ndarray, valid mask ndarray)"""
-    arr, keep = cols_from_numpy(cols)
-    t = cols[time_col][0]
-    if num_windows is None:   # countWindows on the host (rolling.go:96-99,143-154), like the Go side
-        from . import partition as P
-        num_windows = P.num_windows(int(t[0]), int(t[-1]), interval, P.normalise_offset(interval, offset)) if len(t) else 0
-    W = num_windows
-    sarr = make_specs(specs)
+def make_host_opts(devices: Optional[Sequence[int]] = None, workers_per_device: int = 0, chunk_rows: int = 0,
+                   shard: Optional[Tuple[int, int]] = None):
+    """-> (HostOpts, keep-alive) for the one-shot host calls; shard = (s0, num_windows) of a range-partitioned shard"""
+    o = HostOpts()
+    keep = None
+    if devices:
+        keep = (C.c_int32 * len(devices))(*devices)
+        o.devices, o.ndevices = keep, len(devices)
+    o.workers_per_device, o.chunk_rows = workers_per_device, chunk_rows
+    if shard is not None:
+        o.shard, o.s0, o.num_windows = 1, int(shard[0]), int(shard[1])
+    return o, keep
+
+
+def _host_outs(specs, W):
     outs = (OutCol * len(specs))()
     bufs = []
     for j in range(len(specs)):
@@ -238,15 +253,59 @@ def aggregate_host(ctx: "Ctx", cols: Sequence[NpCol], time_col: int, interval: i
         b = np.full((W + 7) // 8 + 1, 0xAA, dtype=np.uint8)
         bufs.append((v, b))
         outs[j].values, outs[j].validity = v.ctypes.data, b.ctypes.data
-    got = C.c_int64()
-    ctx.check(lib().bowgpu_aggregate_host(ctx.h, arr, len(cols), time_col, interval, offset, int(inclusive), sarr,
-                                          len(specs), outs, W, C.byref(got)))
-    assert got.value == W, (got.value, W)
+    return outs, bufs
+
+
+def _host_results(outs, bufs, W):
     res = []
     for j, (v, b) in enumerate(bufs):
         vals = v[:W] if outs[j].dtype == INT64 else v[:W].view(np.float64)
         res.append((vals, unpack_bits(b, W)))
     return res
+
+
+def _count_windows(t, interval, offset):   # countWindows on the host (rolling.go:96-99,143-154), like the Go side
+    from . import partition as P
+    return P.num_windows(int(t[0]), int(t[-1]), interval, P.normalise_offset(interval, offset)) if len(t) else 0
+
+
+def aggregate_host(ctx: "Ctx", cols: Sequence[NpCol], time_col: int, interval: int, specs: Sequence[tuple],
+                   offset: int = 0, inclusive: bool = False, num_windows: Optional[int] = None,
+                   devices: Optional[Sequence[int]] = None, workers_per_device: int = 0, chunk_rows: int = 0,
+                   shard: Optional[Tuple[int, int]] = None):
+    """One-shot pipelined IntervalRolling -> Aggregate from host columns to host results (bowgpu_aggregate_host_ex),
+    spread over `devices` (default: the ctx's GPU) -> list of (values ndarray, valid mask ndarray)"""
+    arr, keep = cols_from_numpy(cols)
+    if shard is not None:
+        num_windows = shard[1]
+    W = _count_windows(cols[time_col][0], interval, offset) if num_windows is None else num_windows
+    sarr = make_specs(specs)
+    outs, bufs = _host_outs(specs, W)
+    opts, okeep = make_host_opts(devices, workers_per_device, chunk_rows, shard)
+    got = C.c_int64()
+    ctx.check(lib().bowgpu_aggregate_host_ex(ctx.h, arr, len(cols), time_col, interval, offset, int(inclusive), sarr,
+                                             len(specs), outs, W, C.byref(got), C.byref(opts)))
+    assert got.value == W, (got.value, W)
+    return _host_results(outs, bufs, W)
+
+
+def interpolate_aggregate_host(ctx: "Ctx", cols: Sequence[NpCol], time_col: int, interval: int, ops: Sequence,
+                               specs: Sequence[tuple], offset: int = 0, prev_row: Optional[Sequence[NpCol]] = None,
+                               devices: Optional[Sequence[int]] = None, workers_per_device: int = 0, chunk_rows: int = 0):
+    """One-shot pipelined IntervalRolling -> Interpolate -> Aggregate from host columns to host results
+    (bowgpu_interpolate_aggregate_host) -> list of (values ndarray, valid mask ndarray)"""
+    arr, keep = cols_from_numpy(cols)
+    W = _count_windows(cols[time_col][0], interval, offset)
+    sarr = make_specs(specs)
+    outs, bufs = _host_outs(specs, W)
+    opts, okeep = make_host_opts(devices, workers_per_device, chunk_rows)
+    codes = (C.c_int32 * len(ops))(*[INTERP[o] if isinstance(o, str) else int(o) for o in ops])
+    parr, pkeep = (None, None) if prev_row is None else cols_from_numpy(prev_row)
+    got = C.c_int64()
+    ctx.check(lib().bowgpu_interpolate_aggregate_host(ctx.h, arr, len(cols), time_col, interval, offset, parr, codes, len(ops),
+                                                      sarr, len(specs), outs, W, C.byref(got), C.byref(opts)))
+    assert got.value == W, (got.value, W)
+    return _host_results(outs, bufs, W)
 
 
 class Frame:

@@ -286,6 +286,36 @@ int32_t bowgpu_aggregate_host(bowgpu_ctx *ctx, const bowgpu_col *cols, int32_t n
                               int64_t offset, int32_t inclusive, const bowgpu_agg_spec *specs, int32_t nspecs,
                               bowgpu_out_col *outs, int64_t out_capacity, int64_t *num_windows);
 
+/* Options of the one-shot host calls; zero-initialise for the defaults.  ONE process drives every GPU it lists: this is
+ * what a Go program calling rolling.IntervalRolling(...) (rolling.go:60 - one call, one process) binds for multi-GPU runs;
+ * the window range is range-partitioned over the devices chunk by chunk, results land in the caller's buffers, no
+ * collective anywhere. */
+typedef struct bowgpu_host_opts {
+    const int32_t *devices;     /* GPUs to spread the chunks over; NULL / ndevices == 0: the ctx's own device */
+    int32_t ndevices;
+    int32_t workers_per_device; /* concurrent upload -> kernels -> download pipelines per GPU; 0 = default (3) */
+    int64_t chunk_rows;         /* rows per chunk; 0 = default (~12 M).  Inputs below two chunks take the plain path */
+    int32_t shard;              /* 1: the rows are ONE range-partitioned shard of a larger Bow (one process per GPU): */
+    int32_t _pad;
+    int64_t s0;                 /*    start of the first window it owns on the global lattice S_k = s0 + k*interval ...  */
+    int64_t num_windows;        /*    ... and how many windows it owns (see bowgpu_rolling_create_shard) */
+} bowgpu_host_opts;
+int32_t bowgpu_aggregate_host_ex(bowgpu_ctx *ctx, const bowgpu_col *cols, int32_t ncols, int32_t time_col, int64_t interval,
+                                 int64_t offset, int32_t inclusive, const bowgpu_agg_spec *specs, int32_t nspecs,
+                                 bowgpu_out_col *outs, int64_t out_capacity, int64_t *num_windows,
+                                 const bowgpu_host_opts *opts);
+
+/* rolling.IntervalRolling(b, col, interval, Options{Offset, PrevRow}).Interpolate(ops...).Aggregate(aggrs...) for a Bow in
+ * HOST memory, in one call (rolling.go:60, interpolation.go:30-69, aggregation.go:123-145): the pipelined counterpart of
+ * bowgpu_rolling_interpolate_aggregate.  Every chunk of the window range ships its halo - back to the last valid row of
+ * each interpolated column, one extra window and forward to the next valid row (what interpolation.Linear / StepPrevious
+ * look at, linear.go:14-27; for the first chunk Options.PrevRow plays the left part) - so the chunks are independent.
+ * prev_row: NULL or `ncols` one-row host columns.  ops / nops as in bowgpu_rolling_interpolate. */
+int32_t bowgpu_interpolate_aggregate_host(bowgpu_ctx *ctx, const bowgpu_col *cols, int32_t ncols, int32_t time_col,
+                                          int64_t interval, int64_t offset, const bowgpu_col *prev_row, const int32_t *ops,
+                                          int32_t nops, const bowgpu_agg_spec *specs, int32_t nspecs, bowgpu_out_col *outs,
+                                          int64_t out_capacity, int64_t *num_windows, const bowgpu_host_opts *opts);
+
 #ifdef __cplusplus
 }
 #endif

@@ -424,3 +424,46 @@ def test_pipelined_host_aggregate(ctx, n, kind):
             H.assert_in_tolerance_class(gv, wv, scales[sp[1]][sp[0]], f"{n} {kind} {sp}")
         else:
             assert np.array_equal(gv[gm].view(np.int64), wv[wm].view(np.int64)), (n, kind, sp)
+
+
+@pytest.mark.parametrize("kind", ["regular", "bursty", "sparse"])
+def test_host_aggregate_over_a_device_list_and_as_a_shard(ctx, kind):
+    """bowgpu_aggregate_host_ex: ONE process, the chunks of the window range dealt to worker contexts on every listed
+    device (here every visible GPU, and the same GPU listed twice), and the shard form one process per GPU
+    uses.  Same results as the oracle."""
+    import torch
+    from bow_b200 import native as N
+    from bow_b200 import parallel as PP
+    rng = np.random.default_rng(H.seed_of("hostagg-multi", kind))
+    n = 600_000
+    t = H.random_times(rng, n, kind)
+    t = t - int(t[0]) + 999
+    v = H.random_values(rng, n, np.float64, 0.2)
+    w = H.random_values(rng, n, np.int64, 0.0)
+    cols = [(t, None), v, w]
+    interval = 29
+    specs = [("WindowStart", 0), ("Count", 1), ("Max", 1), ("First", 2), ("Sum", 2), ("ArithmeticMean", 1),
+             ("IntegralTrapezoid", 1), ("WeightedAverageStep", 2)]
+    want = R.RefRolling(R.Frame(cols), 0, interval, offset=4).aggregate(specs)
+    scales = {c: H.term_scales(cols, c, interval, offset=4) for c in (1, 2)}
+
+    def check(got, want, what):
+        for sp, (gv, gm), (wv, wm) in zip(specs, got, want):
+            assert gv.dtype == wv.dtype and np.array_equal(gm, wm), (what, sp)
+            if sp[0] in H.TOL_OPS and not (sp[0] == "Sum" and sp[1] == 2):
+                H.assert_in_tolerance_class(gv, wv, scales[sp[1]][sp[0]], f"{what} {sp}")
+            else:
+                assert np.array_equal(gv[gm].view(np.int64), wv[wm].view(np.int64)), (what, sp)
+
+    ngpu = torch.cuda.device_count()
+    for devices in ([0, 0], list(range(ngpu)), None):
+        got = N.aggregate_host(ctx, cols, 0, interval, specs, offset=4, devices=devices, workers_per_device=2, chunk_rows=40_000)
+        check(got, want, f"devices={devices}")
+    # the shard form: the frame cut in three by partition.plan, every piece through the pipelined call
+    shards, s0 = PP.plan_for_columns(t, interval, 4, 3)
+    per = []
+    for sh in shards:
+        local = PP.slice_cols(cols, sh.row_lo, sh.halo_hi)
+        per.append(N.aggregate_host(ctx, local, 0, interval, specs, chunk_rows=30_000,
+                                    shard=(s0 + sh.k_lo * interval, sh.num_windows)))
+    check(PP.concat_outputs(per), want, "shards")

@@ -409,3 +409,37 @@ def test_has_start_row_goes_through_float64_above_2_53(ctx):
         assert np.array_equal(bits(gv)[gm], bits(wv)[wm]), sp
     r.close()
     fr.close()
+
+
+@pytest.mark.parametrize("kind,null_p", [("regular", 0.1), ("bursty", 0.6), ("sparse", 0.97)])
+def test_pipelined_host_interpolate_aggregate(ctx, kind, null_p):
+    """bowgpu_interpolate_aggregate_host: host columns in, host results out, every chunk of the window range with its
+    left halo / extra window / right halo, over a device list.  Must equal Interpolate followed by Aggregate
+    of the oracle — including the windows at chunk cuts and columns that are null for long stretches."""
+    import torch
+    from bow_b200 import native as N
+    rng = np.random.default_rng(H.seed_of("hostinterp", kind))
+    n = 500_000
+    t = H.random_times(rng, n, kind)
+    t = t - int(t[0]) + 12
+    a = H.random_values(rng, n, np.float64, null_p)
+    b = H.random_values(rng, n, np.int64, null_p / 2)
+    c = H.random_values(rng, n, np.float64, 0.0)
+    cols = [(t, None), a, b, c]
+    interval = 41
+    ops = ["WindowStart", "Linear", "StepPrevious", "StepNext"]
+    specs = [("WindowStart", 0), ("Count", 1), ("First", 2), ("Last", 3), ("WeightedAverageLinear", 1), ("IntegralTrapezoid", 3),
+             ("Min", 1), ("IntegralStep", 2)]
+    ref = R.RefRolling(R.Frame(cols), 0, interval, offset=7)
+    icols = [(vv, None if mm.all() else mm) for vv, mm in ref.interpolate(ops)]
+    want = R.RefRolling(R.Frame(icols), 0, interval, offset=7).aggregate(specs)
+    scales = {j: H.term_scales(icols, j, interval, offset=7, inclusive=True) for j in (1, 2, 3)}
+    ngpu = torch.cuda.device_count()
+    for devices in (None, [0, 0], list(range(ngpu))):
+        got = N.interpolate_aggregate_host(ctx, cols, 0, interval, ops, specs, offset=7, devices=devices, chunk_rows=35_000)
+        for sp, (gv, gm), (wv, wm) in zip(specs, got, want):
+            assert gv.dtype == wv.dtype and np.array_equal(gm, wm), (kind, devices, sp, np.flatnonzero(gm != wm)[:5])
+            if sp[0] in H.TOL_OPS:
+                H.assert_in_tolerance_class(gv, wv, scales[sp[1]][sp[0]], f"{kind} {devices} {sp}")
+            else:
+                assert np.array_equal(bits(gv)[gm], bits(wv)[wm]), (kind, devices, sp)
