@@ -2246,7 +2246,9 @@ int32_t host_pipeline(bowgpu_ctx *ctx, const HostCall &H) {
         devs.assign(O.devices, O.devices + O.ndevices);
     else
         devs.push_back(ctx->device);
-    const int per_dev = O.workers_per_device > 0 ? O.workers_per_device : 3;
+    // pageable inputs (the Go heap) pass through pinned staging chunks filled by the worker's own memcpy: more workers
+    // = more copy threads (measured on the B200 box: 29 GB/s with 3)
+    const int per_dev = O.workers_per_device > 0 ? O.workers_per_device : (is_pinned(tc.values) ? 3 : 6);
     std::vector<bowgpu_ctx *> workers;
     for (int d : devs) {
         std::vector<bowgpu_ctx *> w;
