@@ -1289,7 +1289,8 @@ static int32_t aggregate_core(bowgpu_rolling *r, const bowgpu_agg_spec *specs, i
     }
     const size_t wv = align_up((size_t)W * 8, 256), wb = align_up((size_t)((W + 7) / 8) + 16, 256);
     const size_t carry_bytes = std::max(seg_carry_bytes(g.n), integral_carry_bytes(g.n));
-    size_t need = 8192 + (size_t)n_basic_cols * 2 * (wv + 256) + (size_t)n_int_cols * 4 * (wv + 256) + carry_bytes + 512;
+    const size_t skip_bytes = std::max(seg_skip_bytes(g.n), integral_skip_bytes(g.n)) + 256;
+    size_t need = 8192 + skip_bytes + (size_t)n_basic_cols * 2 * (wv + 256) + (size_t)n_int_cols * 4 * (wv + 256) + carry_bytes + 512;
     if (mem == BOWGPU_MEM_HOST) need += (size_t)nspecs * (wv + wb);
     int32_t rc = arena_reserve(ctx, need);
     if (rc) return rc;
@@ -1307,6 +1308,7 @@ static int32_t aggregate_core(bowgpu_rolling *r, const bowgpu_agg_spec *specs, i
         if (!dvals[j] || !dbits[j]) return fail(ctx, BOWGPU_EINVAL, "aggregation %d: null output buffer", j);
     }
     uint8_t *carry = (uint8_t *)arena_take(ctx, carry_bytes);
+    uint8_t *skip = (uint8_t *)arena_take(ctx, skip_bytes);
 
     timing_begin(ctx);
     // per spec: the per-window count that decides validity, and the base quantity a derived op divides
@@ -1353,6 +1355,7 @@ static int32_t aggregate_core(bowgpu_rolling *r, const bowgpu_agg_spec *specs, i
             L.g = g;
             L.carry_head = (BasicCarry *)carry;
             L.carry_tail = (BasicCarry *)carry + seg_num_tiles(g.n);
+            L.skip = (BasicCarry *)skip;
             L.status = ctx->d_status;
             if (syn_by_col) L.syn = syn_by_col[c];
             // the valid-row count drives every validity bitmap: Count output if it can be used as is, else scratch
@@ -1397,6 +1400,7 @@ static int32_t aggregate_core(bowgpu_rolling *r, const bowgpu_agg_spec *specs, i
             L.g = g;
             L.carry_head = carry;
             L.carry_tail = carry + integral_carry_bytes(g.n) / 2;
+            L.skip = skip;
             L.status = ctx->d_status;
             if (syn_by_col) L.syn = syn_by_col[c];
             const bool want_step = count[BOWGPU_AGG_INTEGRAL_STEP] || count[BOWGPU_AGG_WAVG_STEP];

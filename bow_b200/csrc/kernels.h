@@ -78,12 +78,14 @@ struct SegLaunch {
     BasicOut out;
     BasicCarry *carry_head;   // [ntiles]
     BasicCarry *carry_tail;   // [ntiles]
+    BasicCarry *skip;         // [seg_skip_bytes(n) / sizeof] combined records of long runs of tiles, or null
     int32_t *status;
     FusedSyn syn;
 };
 
 int64_t seg_num_tiles(int64_t n);
 size_t seg_carry_bytes(int64_t n);  // bytes for carry_head + carry_tail
+size_t seg_skip_bytes(int64_t n);   // bytes of the skip records (windows spanning very many tiles)
 // launches main + fixup kernels on `stream`; returns cudaError_t as int
 int launch_segreduce_basic(const SegLaunch &L, int sm_count, cudaStream_t stream, cudaEvent_t ev_main0,
                            cudaEvent_t ev_main1);
@@ -104,10 +106,12 @@ struct IntLaunch {
     IntegralOut out;
     void *carry_head;  // [ntiles] of integral_carry_bytes(n) / 2
     void *carry_tail;
+    void *skip;        // integral_skip_bytes(n) or null
     int32_t *status;
     FusedSyn syn;
 };
 size_t integral_carry_bytes(int64_t n);
+size_t integral_skip_bytes(int64_t n);
 int launch_segreduce_integral(const IntLaunch &L, int sm_count, cudaStream_t stream, cudaEvent_t ev_main0,
                               cudaEvent_t ev_main1);
 

@@ -187,6 +187,7 @@ int launch_ops(const SegLaunch &L, int sm, cudaStream_t s, cudaEvent_t e0, cudaE
         A.out = L.out;
         A.carry_head = L.carry_head;
         A.carry_tail = L.carry_tail;
+        A.skip = L.skip;
         A.status = L.status;
         A.syn = L.syn;
     };
@@ -206,6 +207,7 @@ int launch_ops(const SegLaunch &L, int sm, cudaStream_t s, cudaEvent_t e0, cudaE
 
 int64_t seg_num_tiles(int64_t n) { return (n + SEG_T - 1) / SEG_T; }
 size_t seg_carry_bytes(int64_t n) { return (size_t)seg_num_tiles(n) * 2 * sizeof(BasicCarry); }
+size_t seg_skip_bytes(int64_t n) { return (size_t)seg_skip_records(seg_num_tiles(n)) * sizeof(BasicCarry); }
 
 int launch_segreduce_basic(const SegLaunch &L, int sm_count, cudaStream_t stream, cudaEvent_t e0, cudaEvent_t e1) {
     if (L.ops & OPS_FIRSTLAST) return launch_ops<OPS_SUMCNT | OPS_MINMAX | OPS_FIRSTLAST>(L, sm_count, stream, e0, e1);

@@ -253,6 +253,7 @@ int launch_mode(const IntLaunch &L, int sm, cudaStream_t s, cudaEvent_t e0, cuda
         A.out = L.out;
         A.carry_head = (ICarry *)L.carry_head;
         A.carry_tail = (ICarry *)L.carry_tail;
+        A.skip = (ICarry *)L.skip;
         A.status = L.status;
         A.syn = L.syn;
     };
@@ -271,6 +272,7 @@ int launch_mode(const IntLaunch &L, int sm, cudaStream_t s, cudaEvent_t e0, cuda
 }  // namespace
 
 size_t integral_carry_bytes(int64_t n) { return (size_t)((n + SEG_T - 1) / SEG_T) * 2 * sizeof(ICarry); }
+size_t integral_skip_bytes(int64_t n) { return (size_t)seg_skip_records((n + SEG_T - 1) / SEG_T) * sizeof(ICarry); }
 
 int launch_segreduce_integral(const IntLaunch &L, int sm_count, cudaStream_t stream, cudaEvent_t e0, cudaEvent_t e1) {
     const bool step = L.out.step != nullptr, trap = L.out.trap != nullptr;

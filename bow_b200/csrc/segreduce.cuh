@@ -108,6 +108,7 @@ struct SegArgs {
     typename Pol::Out out;
     typename Pol::Carry *carry_head;  // [ntiles]
     typename Pol::Carry *carry_tail;  // [ntiles]
+    typename Pol::Carry *skip;        // [seg_skip_records(ntiles)] or null: combined records of runs of 32 / 1024 / 32768 tiles
     int32_t *status;
     FusedSyn syn;                     // fused Interpolate -> Aggregate (FUSED instantiations only)
 };
@@ -617,6 +618,63 @@ __global__ void __launch_bounds__(SEG_NT, MIN_CTAS)
     if (bad) atomicOr(A.status, ST_UNSORTED);
 }
 
+// ---- skip records: windows that span very many tiles -------------------------------------------------------------------
+// The fix-up walk below visits one tile record per step, which is fine for windows of a few tiles and hopeless for
+// aggregation.Aggregate over a whole Bow (ONE window: 122 070 tiles at 1e9 rows).  When windows are that long the tile
+// records are first combined bottom-up: level l holds, for every aligned group of 32^l tiles that lies INSIDE one window
+// (no tile of it closes a window), the left-to-right combination of its records; the walk then jumps over whole groups.
+constexpr int SKIP_FAN = 32, SKIP_LEVELS = 3;
+inline int64_t seg_skip_level_count(int64_t ntiles, int level) {  // level 1..SKIP_LEVELS
+    int64_t n = ntiles;
+    for (int l = 0; l < level; ++l) n = (n + SKIP_FAN - 1) / SKIP_FAN;
+    return n;
+}
+inline int64_t seg_skip_records(int64_t ntiles) {
+    int64_t t = 0;
+    for (int l = 1; l <= SKIP_LEVELS; ++l) t += seg_skip_level_count(ntiles, l);
+    return t;
+}
+__host__ __device__ inline int64_t seg_skip_offset(int64_t ntiles, int level) {  // first record of `level` inside the skip array
+    int64_t off = 0, n = ntiles;
+    for (int l = 1; l < level; ++l) {
+        n = (n + SKIP_FAN - 1) / SKIP_FAN;
+        off += n;
+    }
+    return off;
+}
+// record of group i of `level` = children [32 i, 32 i + 32) of the level below (level 0 = the tiles' head records); a group
+// that is incomplete, holds a closing tile or mixes windows gets key -2
+template <class Pol>
+__global__ void seg_skip_build_kernel(const __grid_constant__ SegArgs<Pol> A, const int64_t ntiles, const int level) {
+    using Carry = typename Pol::Carry;
+    int64_t nc = ntiles;  // children at the level below
+    for (int l = 1; l < level; ++l) nc = (nc + SKIP_FAN - 1) / SKIP_FAN;
+    const int64_t ngroups = (nc + SKIP_FAN - 1) / SKIP_FAN;
+    const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= ngroups) return;
+    const Carry *child = level == 1 ? A.carry_head : A.skip + seg_skip_offset(ntiles, level - 1);
+    Carry *out = A.skip + seg_skip_offset(ntiles, level);
+    const int64_t c0 = gi * SKIP_FAN;
+    Carry acc;
+    bool ok = c0 + SKIP_FAN <= nc;
+    if (ok) {
+        acc = child[c0];
+        ok = Pol::carry_key(acc) >= 0 && !Pol::carry_closed(acc);
+        const int64_t key = Pol::carry_key(acc);
+        for (int j = 1; ok && j < SKIP_FAN; ++j) {
+            const Carry h = child[c0 + j];
+            ok = Pol::carry_key(h) == key && !Pol::carry_closed(h);
+            if (ok) Pol::carry_combine(acc, h);
+        }
+        if (ok) Pol::carry_set_key(acc, key);
+    }
+    if (!ok) {
+        acc = child[c0 < nc ? c0 : 0];
+        Pol::carry_set_key(acc, -2);
+    }
+    out[gi] = acc;
+}
+
 // Joins the per-tile records, strictly left to right.  Thread j owns the windows whose first row lies in tile j
 // and that are not complete inside it: the one at the left edge of the tile (head record, unless it continues a
 // window of an earlier tile) and the one open at its right edge (tail record).
@@ -629,6 +687,20 @@ __global__ void seg_fixup_kernel(const __grid_constant__ SegArgs<Pol> A, const i
     auto walk = [&](Carry a, int64_t i) {
         const int64_t key = Pol::carry_key(a);
         for (; i < ntiles; ++i) {
+            if (A.skip && (i % SKIP_FAN) == 0) {  // jump over whole groups of tiles that lie inside this window
+                bool jumped = false;
+                int64_t span = SKIP_FAN * SKIP_FAN * SKIP_FAN;
+                for (int l = SKIP_LEVELS; l >= 1 && !jumped; --l, span /= SKIP_FAN)
+                    if (i % span == 0 && i + span <= ntiles) {
+                        const Carry g_ = A.skip[seg_skip_offset(ntiles, l) + i / span];
+                        if (Pol::carry_key(g_) == key) {
+                            Pol::carry_combine(a, g_);
+                            i += span - 1;  // (the loop adds one)
+                            jumped = true;
+                        }
+                    }
+                if (jumped) continue;
+            }
             const Carry h = A.carry_head[i];
             if (Pol::carry_key(h) != key) {  // the window ended exactly at the tile boundary
                 if (FUSED) {  // (also writes the empty windows up to the next tile's first window)
@@ -760,7 +832,18 @@ int seg_launch_impl(const SegArgs<Pol> &A, int sm_count, cudaStream_t stream, cu
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     const int fb = 128;
-    seg_fixup_kernel<Pol, FUSED><<<(unsigned)((ntiles + fb - 1) / fb), fb, 0, stream>>>(A, ntiles);
+    SegArgs<Pol> F = A;
+    // windows of (on average) dozens of tiles: combine the tile records bottom-up first (see seg_skip_build_kernel)
+    const bool long_windows = A.skip && ntiles > 4 * SKIP_FAN && A.g.n / (A.g.W > 0 ? A.g.W : 1) > (int64_t)16 * SEG_T;
+    if (long_windows) {
+        for (int l = 1; l <= SKIP_LEVELS; ++l) {
+            const int64_t groups = seg_skip_level_count(ntiles, l);
+            seg_skip_build_kernel<Pol><<<(unsigned)((groups + fb - 1) / fb), fb, 0, stream>>>(A, ntiles, l);
+        }
+    } else {
+        F.skip = nullptr;
+    }
+    seg_fixup_kernel<Pol, FUSED><<<(unsigned)((ntiles + fb - 1) / fb), fb, 0, stream>>>(F, ntiles);
     return (int)cudaGetLastError();
 }
 

@@ -422,6 +422,10 @@ class Frame:
             res.append((vals, unpack_bits(b, n_out)))
         return res
 
+    def aggregate_whole_device(self, time_col: int, specs_arr, nspecs: int, outs) -> None:
+        """same, results left in device buffers (asynchronous)"""
+        self.ctx.check(lib().bowgpu_frame_aggregate_whole(self.h, time_col, specs_arr, nspecs, outs, MEM_DEVICE))
+
     def close(self):
         if self.h:
             lib().bowgpu_frame_destroy(self.h)

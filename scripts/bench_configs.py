@@ -53,7 +53,7 @@ def report(name, n, secs, alg_bytes, extra=None):
 
 def main():
     ctx = N.Ctx(0)
-    which = sys.argv[1:] or ["1", "1b", "2", "3", "4", "fill", "sort"]
+    which = sys.argv[1:] or ["1", "1b", "2", "3", "4", "whole", "fill", "sort"]
     if "1" in which or "1b" in which:
         for tag, n in (("1", int(1e8 * SCALE)), ("1b", int(1e9 * SCALE))):
             if tag not in which:
@@ -141,6 +141,24 @@ def main():
         report("configs[4] one GPU share: 16 columns x all aggregations (177 outputs)", n, dt,
                136 * n + 8 * n // 8 + len(specs) * (8 * W + W // 8))
         r.close(); fr.close(); del keep
+    if "whole" in which:  # aggregation.Aggregate over the whole Bow = ONE window of 1e9 rows, and a rolling
+        # whose single window holds every row (the huge-window end of the load-balance range: 122 070 tile records to join)
+        n = int(1e9 * SCALE)
+        fr = N.Frame.generate(ctx, n, ncols=1, seed=42)
+        specs = [("WindowStart", 0), ("ArithmeticMean", 1), ("Sum", 1), ("Min", 1), ("Max", 1), ("Count", 1)]
+        arr = N.make_specs(specs)
+        outs, keep = dev_outs(1, len(specs))
+        dt = timed(ctx, lambda: fr.aggregate_whole_device(0, arr, len(specs), outs), reps=10)
+        report("whole-frame aggregation.Aggregate (one window) mean/sum/min/max/count", n, dt, 16 * n)
+        r = N.Rolling(fr, 0, 2 * n * SEC)
+        dt = timed(ctx, lambda: r.aggregate_device(arr, len(specs), outs), reps=10)
+        report("IntervalRolling with ONE window holding every row, mean/sum/min/max/count", n, dt, 16 * n)
+        specs2 = [("WindowStart", 0), ("IntegralStep", 1), ("IntegralTrapezoid", 1), ("WeightedAverageLinear", 1)]
+        arr2 = N.make_specs(specs2)
+        outs2, keep2 = dev_outs(1, len(specs2))
+        dt = timed(ctx, lambda: fr.aggregate_whole_device(0, arr2, len(specs2), outs2), reps=10)
+        report("whole-frame aggregation.Aggregate (one window) integrals", n, dt, 16 * n)
+        r.close(); fr.close(); del keep, keep2
     if "fill" in which:   # next row of SURVEY 8(f): whole-column fills (bowfill.go)
         n = int(1e9 * SCALE)
         fr = N.Frame.generate(ctx, n, ncols=2, seed=5, null_mask=0x3, null_mod=10)

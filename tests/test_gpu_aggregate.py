@@ -467,3 +467,41 @@ def test_host_aggregate_over_a_device_list_and_as_a_shard(ctx, kind):
         per.append(N.aggregate_host(ctx, local, 0, interval, specs, chunk_rows=30_000,
                                     shard=(s0 + sh.k_lo * interval, sh.num_windows)))
     check(PP.concat_outputs(per), want, "shards")
+
+
+@pytest.mark.parametrize("vtype", [np.float64, np.int64])
+def test_whole_aggregate_over_thousands_of_tiles(ctx, vtype):
+    """aggregation.Aggregate over a Bow of 3e7 rows (3 662 tiles in ONE window): the tile records are joined through the
+    skip records (seg_skip_build_kernel) instead of one by one; every aggregation against the oracle."""
+    from bow_b200 import native as N
+    rng = np.random.default_rng(H.seed_of("whole-big", str(vtype)))
+    n = 30_000_123
+    t = np.cumsum(rng.integers(0, 3, size=n)).astype(np.int64) + 5
+    v = H.random_values(rng, n, vtype, 0.05)
+    cols = [(t, None), v]
+    specs = [(a, 0 if a == "WindowStart" else 1) for a in WHOLE_ALL]
+    fr = N.Frame.from_numpy(ctx, cols)
+    got = fr.aggregate_whole(0, specs)
+    want = R.aggregate_whole(R.Frame(cols), 0, specs)
+    av = np.abs(v[0].astype(np.float64))
+    span = float(t[-1] - t[0])
+    scale = {"Sum": float(av[v[1]].sum()) if v[1] is not None else float(av.sum())}
+    scale["ArithmeticMean"] = scale["Sum"] / n
+    scale["IntegralStep"] = scale["IntegralTrapezoid"] = float(av.max()) * span
+    scale["WeightedAverageStep"] = scale["WeightedAverageLinear"] = float(av.max())
+    for sp, (gv, gm), (wv, wm) in zip(specs, got, want):
+        assert gv.dtype == wv.dtype and np.array_equal(gm, wm), sp
+        if sp[0] in H.TOL_OPS and not (sp[0] == "Sum" and vtype == np.int64):
+            H.assert_in_tolerance_class(gv, wv, scale[sp[0]], str(sp))
+        else:
+            assert np.array_equal(bits(gv), bits(wv)), sp
+    # the same rows as ONE rolling window
+    r = N.Rolling(fr, 0, int(t[-1] - t[0]) + 10, offset=int(t[0]) % (int(t[-1] - t[0]) + 10))
+    assert r.num_windows == 1
+    g2 = r.aggregate([("WindowStart", 0), ("Count", 1), ("Min", 1), ("Max", 1), ("First", 1), ("Last", 1)])
+    w2 = R.RefRolling(R.Frame(cols), 0, int(t[-1] - t[0]) + 10, offset=int(t[0]) % (int(t[-1] - t[0]) + 10)).aggregate(
+        [("WindowStart", 0), ("Count", 1), ("Min", 1), ("Max", 1), ("First", 1), ("Last", 1)])
+    for (gv, gm), (wv, wm) in zip(g2, w2):
+        assert np.array_equal(gm, wm) and np.array_equal(bits(gv), bits(wv))
+    r.close()
+    fr.close()
