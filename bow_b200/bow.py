@@ -281,3 +281,41 @@ def NewBowFromRowBasedInterfaces(colNames: Sequence[str], colTypes: Sequence[Typ
     """bow.go:150-170"""
     cols = [[r[j] for r in rows] for j in range(len(colNames))]
     return NewBowFromColBasedInterfaces(colNames, colTypes, cols)
+
+
+def NewBowFromParquet(path: str, verbose: bool = False, colNames: Optional[Sequence[str]] = None) -> Bow:
+    """bowparquet.go:44-155: loads a parquet file into a new Bow.  The footer and the page headers are walked on the
+    host; the column data is decompressed and decoded on the GPU (csrc/parquet.cu) and downloaded.  The reference maps
+    BOOLEAN / INT64 / DOUBLE / BYTE_ARRAY leaves (bowparquet.go:20-25); the GPU backend has Int64 and Float64 only, so a
+    file holding other columns needs `colNames` (the numeric columns to load) — there is no CPU decode to fall back to.
+    Key-value metadata of the footer (bowparquet.go:118-134) is not carried over."""
+    from . import native as N
+    from .runtime import default_ctx
+    try:
+        with N.ParquetFile(path) as pf:
+            if colNames is None:
+                idx = list(range(len(pf.names)))
+            else:
+                idx = []
+                for name in colNames:
+                    if name not in pf.names:
+                        raise BowError(f"bow.NewBowFromParquet: no column '{name}' in {path}")
+                    idx.append(pf.names.index(name))
+            for j in idx:
+                if not pf.dtypes[j]:
+                    raise BowError(f"bow.NewBowFromParquet: column '{pf.names[j]}' (parquet type {pf.physical[j]}): only "
+                                   "INT64 / DOUBLE columns run on the GPU backend; name the columns to load in colNames")
+            frame = pf.read(default_ctx(), idx)
+            try:
+                cols = frame.download()
+            finally:
+                frame.close()
+            names = [pf.names[j] for j in idx]
+            nrows = pf.num_rows
+    except N.BowGpuError as e:
+        raise BowError("bow.NewBowFromParquet: " + str(e).split(": ", 1)[-1])
+    series = [NewSeriesFromNumpy(name, v, m) for name, (v, m) in zip(names, cols)]
+    b = NewBow(*series)
+    if verbose:
+        print(f"bow.NewBowFromParquet: {path} successfully read: {nrows} rows\n{b.Record.schema}")
+    return b

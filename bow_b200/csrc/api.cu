@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "kernels.h"
+#include "parquet.h"
 
 using namespace bowgpu;
 
@@ -43,6 +44,11 @@ struct bowgpu_ctx {
     size_t pinned_bytes = 0;
     // worker contexts of bowgpu_aggregate_host (own stream, arena, pool each), created on first use
     std::vector<bowgpu_ctx *> workers;
+    // side streams of Rolling.Aggregate: the streaming launches of several value columns run side by side, each on its
+    // share of the SMs, so that the time tiles they all read are fetched from DRAM once and served from L2 after that
+    std::vector<cudaStream_t> side;
+    std::vector<cudaEvent_t> side_done;
+    cudaEvent_t side_fork = nullptr;
     // timing
     int timing = 0;  // 0 off, 1 per call, 2 accumulate over calls
     cudaEvent_t ev_total[2] = {nullptr, nullptr};
@@ -316,6 +322,7 @@ extern "C" const char *bowgpu_status_string(int32_t s) {
     case BOWGPU_ECUDA: return "CUDA error";
     case BOWGPU_ENOMEM: return "out of memory";
     case BOWGPU_EUNSUPPORTED: return "not supported by the GPU backend";
+    case BOWGPU_EIO: return "file cannot be read or is malformed";
     }
     return "unknown status";
 }
@@ -381,6 +388,9 @@ extern "C" void bowgpu_ctx_destroy(bowgpu_ctx *ctx) {
         if (ctx->ev_total[i]) cudaEventDestroy(ctx->ev_total[i]);
     }
     for (auto e : ctx->ev_main) cudaEventDestroy(e);
+    for (auto st : ctx->side) cudaStreamDestroy(st);
+    for (auto e : ctx->side_done) cudaEventDestroy(e);
+    if (ctx->side_fork) cudaEventDestroy(ctx->side_fork);
     if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -633,6 +643,165 @@ extern "C" int32_t bowgpu_frame_download_range(const bowgpu_frame *f, int64_t ro
 
 extern "C" int32_t bowgpu_frame_download(const bowgpu_frame *f, bowgpu_out_col *outs, int32_t ncols) {
     return bowgpu_frame_download_range(f, 0, f ? f->n : 0, outs, ncols);
+}
+
+// ================================================================================================
+// Parquet ingest (bowparquet.go:44-155): metadata on the host, data on the device (parquet.cu)
+// ================================================================================================
+struct bowgpu_parquet {
+    PqFile *file = nullptr;
+};
+
+extern "C" int32_t bowgpu_parquet_open(const char *path, bowgpu_parquet **out, char *err, int32_t err_cap) {
+    if (!path || !out) return BOWGPU_EINVAL;
+    *out = nullptr;
+    std::string msg;
+    PqFile *f = nullptr;
+    const int rc = pq_open(path, &f, msg);
+    if (rc) {
+        if (err && err_cap > 0) snprintf(err, (size_t)err_cap, "%s", msg.c_str());
+        return rc;
+    }
+    bowgpu_parquet *p = new (std::nothrow) bowgpu_parquet();
+    if (!p) {
+        pq_close(f);
+        return BOWGPU_ENOMEM;
+    }
+    p->file = f;
+    *out = p;
+    return BOWGPU_OK;
+}
+extern "C" void bowgpu_parquet_close(bowgpu_parquet *pq) {
+    if (!pq) return;
+    pq_close(pq->file);
+    delete pq;
+}
+extern "C" int64_t bowgpu_parquet_num_rows(const bowgpu_parquet *pq) { return pq ? pq_num_rows(pq->file) : -1; }
+extern "C" int32_t bowgpu_parquet_num_cols(const bowgpu_parquet *pq) { return pq ? (int32_t)pq_columns(pq->file).size() : -1; }
+extern "C" const char *bowgpu_parquet_col_name(const bowgpu_parquet *pq, int32_t col) {
+    if (!pq || col < 0 || col >= (int32_t)pq_columns(pq->file).size()) return nullptr;
+    return pq_columns(pq->file)[col].name.c_str();
+}
+extern "C" int32_t bowgpu_parquet_col_dtype(const bowgpu_parquet *pq, int32_t col) {
+    if (!pq || col < 0 || col >= (int32_t)pq_columns(pq->file).size()) return -1;
+    return pq_columns(pq->file)[col].dtype;
+}
+extern "C" int32_t bowgpu_parquet_col_physical_type(const bowgpu_parquet *pq, int32_t col) {
+    if (!pq || col < 0 || col >= (int32_t)pq_columns(pq->file).size()) return -1;
+    return pq_columns(pq->file)[col].physical;
+}
+extern "C" int64_t bowgpu_frame_col_null_count(const bowgpu_frame *f, int32_t col) {
+    if (!f || col < 0 || col >= (int32_t)f->cols.size()) return -1;
+    return f->cols[col].validity ? f->cols[col].null_count : 0;
+}
+
+extern "C" int32_t bowgpu_parquet_plan(const bowgpu_parquet *pq, const int32_t *cols, int32_t ncols, int64_t *out4, char *err,
+                                       int32_t err_cap) {
+    if (!pq || !out4 || ncols < 0 || (ncols > 0 && !cols)) return BOWGPU_EINVAL;
+    PqPlan plan;
+    std::string msg;
+    const int32_t rc = pq_plan(pq->file, cols, ncols, plan, msg);
+    if (rc && err && err_cap > 0) snprintf(err, (size_t)err_cap, "%s", msg.c_str());
+    out4[0] = (int64_t)plan.pages.size();
+    out4[1] = plan.image_bytes;
+    out4[2] = plan.scratch_bytes;
+    out4[3] = plan.aux_entries;
+    return rc;
+}
+
+extern "C" int32_t bowgpu_parquet_read(bowgpu_ctx *ctx, const bowgpu_parquet *pq, const int32_t *cols, int32_t ncols,
+                                       bowgpu_frame **out) {
+    if (!ctx || !pq || !out || ncols < 0 || (ncols > 0 && !cols)) return BOWGPU_EINVAL;
+    *out = nullptr;
+    Guard gd(ctx);
+    PqPlan plan;
+    std::string msg;
+    int32_t rc = pq_plan(pq->file, cols, ncols, plan, msg);
+    if (rc) return fail(ctx, rc, "%s", msg.c_str());
+    const int64_t n = pq_num_rows(pq->file);
+    const auto &pcols = pq_columns(pq->file);
+    bowgpu_frame *f = new (std::nothrow) bowgpu_frame();
+    if (!f) return BOWGPU_ENOMEM;
+    f->ctx = ctx;
+    f->n = n;
+    f->cols.resize(ncols);
+    uint8_t *image = nullptr, *scratch = nullptr;
+    int32_t *aux = nullptr;
+    auto cleanup = [&](int32_t code) {
+        pool_free(ctx, image);
+        pool_free(ctx, scratch);
+        pool_free(ctx, aux);
+        if (code) {
+            cudaStreamSynchronize(ctx->stream);
+            for (auto &c : f->cols) free_col(ctx, c);
+            delete f;
+        }
+        return code;
+    };
+    for (int j = 0; j < ncols; ++j) {
+        rc = alloc_col(ctx, f->cols[j], n, pcols[cols[j]].dtype, pcols[cols[j]].optional && n > 0);
+        if (rc) return cleanup(rc);
+    }
+    const int npages = (int)plan.pages.size();
+    if (n == 0 || npages == 0) {
+        *out = f;
+        return BOWGPU_OK;
+    }
+    // small tables (page descriptors, column outputs, valid-row counters) live in the arena
+    const size_t pb = align_up((size_t)npages * sizeof(PqPage), 256), cb = align_up((size_t)ncols * sizeof(PqColOut), 256);
+    const size_t nb = align_up((size_t)ncols * 8, 256);
+    rc = arena_reserve(ctx, pb + cb + nb + 1024);
+    if (rc) return cleanup(rc);
+    arena_reset(ctx);
+    PqPage *d_pages = (PqPage *)arena_take(ctx, pb);
+    PqColOut *d_cols = (PqColOut *)arena_take(ctx, cb);
+    unsigned long long *d_counts = (unsigned long long *)arena_take(ctx, nb);
+    auto ck = [&](cudaError_t e, const char *what) -> int32_t {
+        if (e == cudaSuccess) return BOWGPU_OK;
+        return fail(ctx, e == cudaErrorMemoryAllocation ? BOWGPU_ENOMEM : BOWGPU_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+    };
+    if ((rc = ck(pool_alloc(ctx, (void **)&image, (size_t)plan.image_bytes), "parquet image"))) return cleanup(rc);
+    if ((rc = ck(pool_alloc(ctx, (void **)&scratch, (size_t)plan.scratch_bytes), "parquet scratch"))) return cleanup(rc);
+    if ((rc = ck(pool_alloc(ctx, (void **)&aux, (size_t)(plan.aux_entries + 16) * 4), "parquet index scratch"))) return cleanup(rc);
+    // the file bytes of the chosen column chunks, as they are
+    const uint8_t *bytes = pq_bytes(pq->file);
+    for (const PqRange &rg : plan.ranges) {
+        rc = copy_h2d(ctx, image + rg.image_off, bytes + rg.file_off, (size_t)rg.len);
+        if (rc) return cleanup(rc);
+    }
+    std::vector<PqColOut> hc(ncols);
+    for (int j = 0; j < ncols; ++j) {
+        hc[j].values = f->cols[j].values;
+        hc[j].validity = (uint32_t *)f->cols[j].validity;
+        hc[j].valid_count = d_counts + j;
+    }
+    if ((rc = ck(cudaMemsetAsync(d_counts, 0, nb, ctx->stream), "memset"))) return cleanup(rc);
+    rc = copy_h2d(ctx, d_pages, plan.pages.data(), (size_t)npages * sizeof(PqPage));
+    if (!rc) rc = copy_h2d(ctx, d_cols, hc.data(), (size_t)ncols * sizeof(PqColOut));
+    if (rc) return cleanup(rc);
+    if ((rc = ck((cudaError_t)launch_pq_decode(d_pages, npages, image, scratch, aux, d_cols, ctx->d_status, ctx->stream), "parquet decode")))
+        return cleanup(rc);
+    std::vector<unsigned long long> counts(ncols);
+    int32_t st = 0;
+    rc = copy_d2h(ctx, counts.data(), d_counts, (size_t)ncols * 8);
+    if (!rc) rc = ck(cudaMemcpyAsync(&st, ctx->d_status, 4, cudaMemcpyDeviceToHost, ctx->stream), "status");
+    if (!rc) rc = ck(cudaStreamSynchronize(ctx->stream), "parquet decode");
+    if (rc) return cleanup(rc);
+    if (st & ST_PARQUET) {
+        cudaMemsetAsync(ctx->d_status, 0, 4, ctx->stream);
+        return cleanup(fail(ctx, BOWGPU_EIO, "malformed parquet page data (Snappy stream, levels or values out of bounds)"));
+    }
+    for (int j = 0; j < ncols; ++j) {
+        DevCol &c = f->cols[j];
+        c.null_count = n - (int64_t)counts[j];
+        if (c.validity && c.null_count == 0) {  // no nulls: the kernels take the all-valid path
+            pool_free(ctx, c.validity);
+            c.validity = nullptr;
+            c.own_validity = false;
+        }
+    }
+    *out = f;
+    return cleanup(BOWGPU_OK);
 }
 
 extern "C" int32_t bowgpu_frame_generate(bowgpu_ctx *ctx, const bowgpu_gen_spec *spec, bowgpu_frame **out) {
@@ -1249,6 +1418,29 @@ static int32_t whole_return_type(int32_t op, int32_t input_dtype) {  // whole.go
 
 // syn_by_col: null, or one FusedSyn per frame column (fused Interpolate -> Aggregate: the aggregation runs over the
 // interpolated frame without materialising it)
+// width of a wave of side-by-side streaming launches (BOWGPU_SEG_SIDE, 1 = one launch after the other on the ctx stream)
+static int side_width() {
+    static const int k = [] {
+        const char *e = getenv("BOWGPU_SEG_SIDE");
+        int v = e ? atoi(e) : 1;  // measured on B200: side by side is no faster
+        return v < 1 ? 1 : (v > 16 ? 16 : v);
+    }();
+    return k;
+}
+static int32_t ensure_side(bowgpu_ctx *ctx, int k) {
+    if (k <= 1) return BOWGPU_OK;
+    if (!ctx->side_fork) CK(cudaEventCreateWithFlags(&ctx->side_fork, cudaEventDisableTiming));
+    while ((int)ctx->side.size() < k) {
+        cudaStream_t st;
+        cudaEvent_t ev;
+        CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        ctx->side.push_back(st);
+        CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx->side_done.push_back(ev);
+    }
+    return BOWGPU_OK;
+}
+
 static int32_t aggregate_core(bowgpu_rolling *r, const bowgpu_agg_spec *specs, int32_t nspecs, bowgpu_out_col *outs,
                               int32_t mem, const FusedSyn *syn_by_col) {
     if (!r || !specs || !outs || nspecs <= 0) return BOWGPU_EINVAL;
@@ -1287,12 +1479,22 @@ static int32_t aggregate_core(bowgpu_rolling *r, const bowgpu_agg_spec *specs, i
         n_basic_cols += b;
         n_int_cols += i;
     }
+    // ---- side-by-side launches: the streaming launches of one kernel family run in waves of up to K columns, every lane
+    // of a wave on its own stream and on 1/K of the SMs' CTA slots.  Tiles are dealt round-robin inside a launch, so the
+    // lanes of a wave move through the rows abreast and the time tiles all of them read come from DRAM once and from L2
+    // after that (a lane that runs ahead takes the misses and falls back) — DESIGN.md 3.7.
+    const int n_fam[2] = {n_basic_cols, n_int_cols};
+    int K = std::min(side_width(), std::max(n_basic_cols, n_int_cols));
+    if (K < 1) K = 1;
+    int32_t rc = ensure_side(ctx, K);
+    if (rc) return rc;
     const size_t wv = align_up((size_t)W * 8, 256), wb = align_up((size_t)((W + 7) / 8) + 16, 256);
-    const size_t carry_bytes = std::max(seg_carry_bytes(g.n), integral_carry_bytes(g.n));
-    const size_t skip_bytes = std::max(seg_skip_bytes(g.n), integral_skip_bytes(g.n)) + 256;
-    size_t need = 8192 + skip_bytes + (size_t)n_basic_cols * 2 * (wv + 256) + (size_t)n_int_cols * 4 * (wv + 256) + carry_bytes + 512;
+    const size_t carry_bytes = align_up(std::max(seg_carry_bytes(g.n), integral_carry_bytes(g.n)), 256);
+    const size_t skip_bytes = align_up(std::max(seg_skip_bytes(g.n), integral_skip_bytes(g.n)) + 256, 256);
+    size_t need = 8192 + (size_t)K * (skip_bytes + carry_bytes + 512) + (size_t)n_basic_cols * 2 * (wv + 256) +
+                  (size_t)n_int_cols * 4 * (wv + 256);
     if (mem == BOWGPU_MEM_HOST) need += (size_t)nspecs * (wv + wb);
-    int32_t rc = arena_reserve(ctx, need);
+    rc = arena_reserve(ctx, need);
     if (rc) return rc;
     arena_reset(ctx);
     std::vector<void *> dvals(nspecs);
@@ -1307,131 +1509,157 @@ static int32_t aggregate_core(bowgpu_rolling *r, const bowgpu_agg_spec *specs, i
         }
         if (!dvals[j] || !dbits[j]) return fail(ctx, BOWGPU_EINVAL, "aggregation %d: null output buffer", j);
     }
-    uint8_t *carry = (uint8_t *)arena_take(ctx, carry_bytes);
-    uint8_t *skip = (uint8_t *)arena_take(ctx, skip_bytes);
+    std::vector<uint8_t *> carry_of(K), skip_of(K);  // tile records: one set per lane
+    for (int l = 0; l < K; ++l) {
+        carry_of[l] = (uint8_t *)arena_take(ctx, carry_bytes);
+        skip_of[l] = (uint8_t *)arena_take(ctx, skip_bytes);
+    }
 
     timing_begin(ctx);
     // per spec: the per-window count that decides validity, and the base quantity a derived op divides
     std::vector<const int64_t *> spec_cnt(nspecs, nullptr);
     std::vector<const double *> spec_src(nspecs, nullptr);
-    for (int c : cols_used) {
-        const DevCol &dc = f->cols[c];
-        // first spec of each op on this column receives the kernel output; duplicates are copied afterwards
-        int primary[BOWGPU_AGG__COUNT], count[BOWGPU_AGG__COUNT];
-        for (int o = 0; o < BOWGPU_AGG__COUNT; ++o) primary[o] = -1, count[o] = 0;
-        for (int j = 0; j < nspecs; ++j)
-            if (specs[j].col == c) {
-                if (primary[specs[j].op] < 0) primary[specs[j].op] = j;
-                ++count[specs[j].op];
-            }
-        auto prim = [&](int op) -> void * { return primary[op] >= 0 ? dvals[primary[op]] : nullptr; };
-        // A base quantity (sum / integral) feeds its own op and a derived op that divides it in the epilogue
-        // (mean, weighted averages).  It lands in the base op's output unless a Factor rescales that one in
-        // place while a derived op still needs the raw values.
-        auto pick_dst = [&](int base_op, int derived_op) -> double * {
-            const int pb = primary[base_op], pd = primary[derived_op];
-            if (pb >= 0 && (specs[pb].nfactors == 0 || count[derived_op] == 0)) return (double *)dvals[pb];
-            if (count[derived_op] == 1 && count[base_op] == 0) return (double *)dvals[pd];  // divided in place
-            if (count[derived_op] > 0) return (double *)arena_take(ctx, wv);
-            return nullptr;
-        };
-        auto copy_dups = [&](int op, const void *src) -> int32_t {  // duplicates of an (op, column) pair
-            for (int j = 0; j < nspecs; ++j) {
-                if (specs[j].col != c || specs[j].op != op || !src || src == dvals[j]) continue;
-                CK(cudaMemcpyAsync(dvals[j], src, (size_t)W * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-            }
-            return BOWGPU_OK;
-        };
-        bool any_basic = false, any_int = false;
-        for (int o = 0; o < BOWGPU_AGG__COUNT; ++o)
-            if (count[o]) any_basic |= agg_is_basic(o), any_int |= agg_is_integral(o);
-        if (any_basic) {
-            SegLaunch L;
-            memset(&L, 0, sizeof L);
-            L.time = (const int64_t *)f->cols[r->time_col].values;
-            L.values = dc.values;
-            L.validity = dc.validity;
-            L.is_int = dc.dtype == BOWGPU_INT64;
-            L.g = g;
-            L.carry_head = (BasicCarry *)carry;
-            L.carry_tail = (BasicCarry *)carry + seg_num_tiles(g.n);
-            L.skip = (BasicCarry *)skip;
-            L.status = ctx->d_status;
-            if (syn_by_col) L.syn = syn_by_col[c];
-            // the valid-row count drives every validity bitmap: Count output if it can be used as is, else scratch
-            int64_t *cnt = nullptr;
-            if (primary[BOWGPU_AGG_COUNT] >= 0 && specs[primary[BOWGPU_AGG_COUNT]].nfactors == 0)
-                cnt = (int64_t *)dvals[primary[BOWGPU_AGG_COUNT]];
-            else
-                cnt = (int64_t *)arena_take(ctx, wv);
-            CK(cudaMemsetAsync(cnt, 0, (size_t)W * 8, ctx->stream));
-            L.out.cnt = cnt;
-            double *sum_dst = pick_dst(BOWGPU_AGG_SUM, BOWGPU_AGG_MEAN);
-            L.out.sum = sum_dst;
-            L.out.mn = (double *)prim(BOWGPU_AGG_MIN);
-            L.out.mx = (double *)prim(BOWGPU_AGG_MAX);
-            L.out.first = (uint64_t *)prim(BOWGPU_AGG_FIRST);
-            L.out.last = (uint64_t *)prim(BOWGPU_AGG_LAST);
-            L.ops = OPS_SUMCNT;
-            if (L.out.mn || L.out.mx) L.ops |= OPS_MINMAX;
-            if (L.out.first || L.out.last) L.ops |= OPS_FIRSTLAST;
-            cudaEvent_t e0, e1;
-            timing_main_pair(ctx, &e0, &e1);
-            CK(launch_segreduce_basic(L, ctx->sm_count, ctx->stream, e0, e1));
-            count_launch(ctx, 1, true);
-            count_launch(ctx, 1);
-            if ((rc = copy_dups(BOWGPU_AGG_COUNT, cnt))) return rc;
-            if ((rc = copy_dups(BOWGPU_AGG_SUM, sum_dst))) return rc;
-            for (int op : {BOWGPU_AGG_MIN, BOWGPU_AGG_MAX, BOWGPU_AGG_FIRST, BOWGPU_AGG_LAST})
-                if ((rc = copy_dups(op, prim(op)))) return rc;
+    for (int fam = 0; fam < 2; ++fam) {
+        int left = n_fam[fam], lane = 0, width = 0;  // launches of the family still to go; lane and width of the open wave
+        for (int c : cols_used) {
+            const DevCol &dc = f->cols[c];
+            // first spec of each op on this column receives the kernel output; duplicates are copied afterwards
+            int primary[BOWGPU_AGG__COUNT], count[BOWGPU_AGG__COUNT];
+            for (int o = 0; o < BOWGPU_AGG__COUNT; ++o) primary[o] = -1, count[o] = 0;
             for (int j = 0; j < nspecs; ++j)
-                if (specs[j].col == c && agg_is_basic(specs[j].op)) {
-                    spec_cnt[j] = cnt;
-                    if (specs[j].op == BOWGPU_AGG_MEAN) spec_src[j] = sum_dst;  // every mean divides the shared sums
+                if (specs[j].col == c) {
+                    if (primary[specs[j].op] < 0) primary[specs[j].op] = j;
+                    ++count[specs[j].op];
                 }
-        }
-        if (any_int) {
-            IntLaunch L;
-            memset(&L, 0, sizeof L);
-            L.time = (const int64_t *)f->cols[r->time_col].values;
-            L.values = dc.values;
-            L.validity = dc.validity;
-            L.is_int = dc.dtype == BOWGPU_INT64;
-            L.g = g;
-            L.carry_head = carry;
-            L.carry_tail = carry + integral_carry_bytes(g.n) / 2;
-            L.skip = skip;
-            L.status = ctx->d_status;
-            if (syn_by_col) L.syn = syn_by_col[c];
-            const bool want_step = count[BOWGPU_AGG_INTEGRAL_STEP] || count[BOWGPU_AGG_WAVG_STEP];
-            const bool want_trap = count[BOWGPU_AGG_INTEGRAL_TRAPEZOID] || count[BOWGPU_AGG_WAVG_LINEAR];
-            if (want_step) {
-                L.out.n_step = (int64_t *)arena_take(ctx, wv);
-                CK(cudaMemsetAsync(L.out.n_step, 0, (size_t)W * 8, ctx->stream));
-                L.out.step = pick_dst(BOWGPU_AGG_INTEGRAL_STEP, BOWGPU_AGG_WAVG_STEP);
+            bool any_basic = false, any_int = false;
+            for (int o = 0; o < BOWGPU_AGG__COUNT; ++o)
+                if (count[o]) any_basic |= agg_is_basic(o), any_int |= agg_is_integral(o);
+            if (!(fam == 0 ? any_basic : any_int)) continue;
+            // ---- the lane this launch runs on
+            if (lane == width) {  // open a wave (the main stream has already been told to wait for the previous one)
+                width = std::min(K, left);
+                lane = 0;
+                if (width > 1) CK(cudaEventRecord(ctx->side_fork, ctx->stream));
             }
-            if (want_trap) {
-                L.out.n_trap = (int64_t *)arena_take(ctx, wv);
-                CK(cudaMemsetAsync(L.out.n_trap, 0, (size_t)W * 8, ctx->stream));
-                L.out.trap = pick_dst(BOWGPU_AGG_INTEGRAL_TRAPEZOID, BOWGPU_AGG_WAVG_LINEAR);
+            cudaStream_t st = ctx->stream;
+            if (width > 1) {
+                st = ctx->side[lane];
+                CK(cudaStreamWaitEvent(st, ctx->side_fork, 0));
             }
-            cudaEvent_t e0, e1;
-            timing_main_pair(ctx, &e0, &e1);
-            CK(launch_segreduce_integral(L, ctx->sm_count, ctx->stream, e0, e1));
-            count_launch(ctx, 1, true);
-            count_launch(ctx, 1);
-            if ((rc = copy_dups(BOWGPU_AGG_INTEGRAL_STEP, L.out.step))) return rc;
-            if ((rc = copy_dups(BOWGPU_AGG_INTEGRAL_TRAPEZOID, L.out.trap))) return rc;
-            for (int j = 0; j < nspecs; ++j) {
-                if (specs[j].col != c) continue;
-                switch (specs[j].op) {
-                case BOWGPU_AGG_INTEGRAL_STEP: spec_cnt[j] = L.out.n_step; break;
-                case BOWGPU_AGG_INTEGRAL_TRAPEZOID: spec_cnt[j] = L.out.n_trap; break;
-                case BOWGPU_AGG_WAVG_STEP: spec_cnt[j] = L.out.n_step, spec_src[j] = L.out.step; break;
-                case BOWGPU_AGG_WAVG_LINEAR: spec_cnt[j] = L.out.n_trap, spec_src[j] = L.out.trap; break;
-                default: break;
+            const int sm_share = std::max(1, ctx->sm_count / width);
+            uint8_t *carry = carry_of[lane], *skip = skip_of[lane];
+
+            auto prim = [&](int op) -> void * { return primary[op] >= 0 ? dvals[primary[op]] : nullptr; };
+            // A base quantity (sum / integral) feeds its own op and a derived op that divides it in the epilogue
+            // (mean, weighted averages).  It lands in the base op's output unless a Factor rescales that one in
+            // place while a derived op still needs the raw values.
+            auto pick_dst = [&](int base_op, int derived_op) -> double * {
+                const int pb = primary[base_op], pd = primary[derived_op];
+                if (pb >= 0 && (specs[pb].nfactors == 0 || count[derived_op] == 0)) return (double *)dvals[pb];
+                if (count[derived_op] == 1 && count[base_op] == 0) return (double *)dvals[pd];  // divided in place
+                if (count[derived_op] > 0) return (double *)arena_take(ctx, wv);
+                return nullptr;
+            };
+            auto copy_dups = [&](int op, const void *src) -> int32_t {  // duplicates of an (op, column) pair
+                for (int j = 0; j < nspecs; ++j) {
+                    if (specs[j].col != c || specs[j].op != op || !src || src == dvals[j]) continue;
+                    CK(cudaMemcpyAsync(dvals[j], src, (size_t)W * 8, cudaMemcpyDeviceToDevice, st));
+                }
+                return BOWGPU_OK;
+            };
+            if (fam == 0) {
+                SegLaunch L;
+                memset(&L, 0, sizeof L);
+                L.time = (const int64_t *)f->cols[r->time_col].values;
+                L.values = dc.values;
+                L.validity = dc.validity;
+                L.is_int = dc.dtype == BOWGPU_INT64;
+                L.g = g;
+                L.carry_head = (BasicCarry *)carry;
+                L.carry_tail = (BasicCarry *)carry + seg_num_tiles(g.n);
+                L.skip = (BasicCarry *)skip;
+                L.status = ctx->d_status;
+                if (syn_by_col) L.syn = syn_by_col[c];
+                // the valid-row count drives every validity bitmap: Count output if it can be used as is, else scratch
+                int64_t *cnt = nullptr;
+                if (primary[BOWGPU_AGG_COUNT] >= 0 && specs[primary[BOWGPU_AGG_COUNT]].nfactors == 0)
+                    cnt = (int64_t *)dvals[primary[BOWGPU_AGG_COUNT]];
+                else
+                    cnt = (int64_t *)arena_take(ctx, wv);
+                CK(cudaMemsetAsync(cnt, 0, (size_t)W * 8, st));
+                L.out.cnt = cnt;
+                double *sum_dst = pick_dst(BOWGPU_AGG_SUM, BOWGPU_AGG_MEAN);
+                L.out.sum = sum_dst;
+                L.out.mn = (double *)prim(BOWGPU_AGG_MIN);
+                L.out.mx = (double *)prim(BOWGPU_AGG_MAX);
+                L.out.first = (uint64_t *)prim(BOWGPU_AGG_FIRST);
+                L.out.last = (uint64_t *)prim(BOWGPU_AGG_LAST);
+                L.ops = OPS_SUMCNT;
+                if (L.out.mn || L.out.mx) L.ops |= OPS_MINMAX;
+                if (L.out.first || L.out.last) L.ops |= OPS_FIRSTLAST;
+                cudaEvent_t e0, e1;
+                timing_main_pair(ctx, &e0, &e1);
+                CK(launch_segreduce_basic(L, sm_share, st, e0, e1));
+                count_launch(ctx, 1, true);
+                count_launch(ctx, 1);
+                if ((rc = copy_dups(BOWGPU_AGG_COUNT, cnt))) return rc;
+                if ((rc = copy_dups(BOWGPU_AGG_SUM, sum_dst))) return rc;
+                for (int op : {BOWGPU_AGG_MIN, BOWGPU_AGG_MAX, BOWGPU_AGG_FIRST, BOWGPU_AGG_LAST})
+                    if ((rc = copy_dups(op, prim(op)))) return rc;
+                for (int j = 0; j < nspecs; ++j)
+                    if (specs[j].col == c && agg_is_basic(specs[j].op)) {
+                        spec_cnt[j] = cnt;
+                        if (specs[j].op == BOWGPU_AGG_MEAN) spec_src[j] = sum_dst;  // every mean divides the shared sums
+                    }
+            } else {
+                IntLaunch L;
+                memset(&L, 0, sizeof L);
+                L.time = (const int64_t *)f->cols[r->time_col].values;
+                L.values = dc.values;
+                L.validity = dc.validity;
+                L.is_int = dc.dtype == BOWGPU_INT64;
+                L.g = g;
+                L.carry_head = carry;
+                L.carry_tail = carry + integral_carry_bytes(g.n) / 2;
+                L.skip = skip;
+                L.status = ctx->d_status;
+                if (syn_by_col) L.syn = syn_by_col[c];
+                const bool want_step = count[BOWGPU_AGG_INTEGRAL_STEP] || count[BOWGPU_AGG_WAVG_STEP];
+                const bool want_trap = count[BOWGPU_AGG_INTEGRAL_TRAPEZOID] || count[BOWGPU_AGG_WAVG_LINEAR];
+                if (want_step) {
+                    L.out.n_step = (int64_t *)arena_take(ctx, wv);
+                    CK(cudaMemsetAsync(L.out.n_step, 0, (size_t)W * 8, st));
+                    L.out.step = pick_dst(BOWGPU_AGG_INTEGRAL_STEP, BOWGPU_AGG_WAVG_STEP);
+                }
+                if (want_trap) {
+                    L.out.n_trap = (int64_t *)arena_take(ctx, wv);
+                    CK(cudaMemsetAsync(L.out.n_trap, 0, (size_t)W * 8, st));
+                    L.out.trap = pick_dst(BOWGPU_AGG_INTEGRAL_TRAPEZOID, BOWGPU_AGG_WAVG_LINEAR);
+                }
+                cudaEvent_t e0, e1;
+                timing_main_pair(ctx, &e0, &e1);
+                CK(launch_segreduce_integral(L, sm_share, st, e0, e1));
+                count_launch(ctx, 1, true);
+                count_launch(ctx, 1);
+                if ((rc = copy_dups(BOWGPU_AGG_INTEGRAL_STEP, L.out.step))) return rc;
+                if ((rc = copy_dups(BOWGPU_AGG_INTEGRAL_TRAPEZOID, L.out.trap))) return rc;
+                for (int j = 0; j < nspecs; ++j) {
+                    if (specs[j].col != c) continue;
+                    switch (specs[j].op) {
+                    case BOWGPU_AGG_INTEGRAL_STEP: spec_cnt[j] = L.out.n_step; break;
+                    case BOWGPU_AGG_INTEGRAL_TRAPEZOID: spec_cnt[j] = L.out.n_trap; break;
+                    case BOWGPU_AGG_WAVG_STEP: spec_cnt[j] = L.out.n_step, spec_src[j] = L.out.step; break;
+                    case BOWGPU_AGG_WAVG_LINEAR: spec_cnt[j] = L.out.n_trap, spec_src[j] = L.out.trap; break;
+                    default: break;
+                    }
                 }
             }
+            if (width > 1) {  // the main stream goes on when every lane of the wave is through
+                CK(cudaEventRecord(ctx->side_done[lane], st));
+                CK(cudaStreamWaitEvent(ctx->stream, ctx->side_done[lane], 0));
+            }
+            ++lane;
+            --left;
         }
     }
     // ---- epilogue: specs without Factor are grouped by the count array that decides their validity (fast path);

@@ -34,7 +34,7 @@ __host__ __device__ __forceinline__ int64_t window_last_value(const WindowGeom &
 }
 
 // status word bits written by the kernels
-enum { ST_UNSORTED = 1, ST_INEXACT_START = 2 };
+enum { ST_UNSORTED = 1, ST_INEXACT_START = 2, ST_PARQUET = 4 /* malformed page data */ };
 
 // ---- carry record of one tile edge (segreduce) ------------------------------------------------
 struct alignas(16) BasicCarry {

@@ -24,7 +24,7 @@ AGG = dict(WindowStart=0, Count=1, Sum=2, ArithmeticMean=3, Min=4, Max=5, First=
 INTERP = dict(WindowStart=0, Linear=1, StepPrevious=2, None_=3, StepNext=4)
 FILL = dict(Previous=0, Next=1, Mean=2, Linear=3)
 STATUS = {0: "OK", 1: "EINVAL", 2: "ETYPE", 3: "EFIRSTNULL", 4: "EPREVROW", 5: "ENOINTERVALCOL", 6: "ECAPACITY",
-          7: "EUNSORTED", 8: "ENULLTIME", 9: "ECUDA", 10: "ENOMEM", 11: "EUNSUPPORTED"}
+          7: "EUNSORTED", 8: "ENULLTIME", 9: "ECUDA", 10: "ENOMEM", 11: "EUNSUPPORTED", 12: "EIO"}
 
 # every symbol include/bowgpu.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
@@ -39,6 +39,9 @@ SYMBOLS = [
     "bowgpu_rolling_interpolate", "bowgpu_frame_aggregate_whole", "bowgpu_frame_fill", "bowgpu_frame_fill_linear",
     "bowgpu_rolling_interpolate_aggregate", "bowgpu_frame_drop_nils", "bowgpu_frame_is_col_sorted",
     "bowgpu_aggregate_host", "bowgpu_frame_sort_by_col", "bowgpu_aggregate_host_ex", "bowgpu_interpolate_aggregate_host",
+    "bowgpu_parquet_open", "bowgpu_parquet_close", "bowgpu_parquet_num_rows", "bowgpu_parquet_num_cols",
+    "bowgpu_parquet_col_name", "bowgpu_parquet_col_dtype", "bowgpu_parquet_col_physical_type", "bowgpu_parquet_read", "bowgpu_parquet_plan",
+    "bowgpu_frame_col_null_count",
 ]
 
 
@@ -142,6 +145,20 @@ def lib():
         L.bowgpu_ctx_last_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
         L.bowgpu_frame_col_dtype.argtypes = [C.c_void_p, C.c_int32]
         L.bowgpu_frame_col_has_validity.argtypes = [C.c_void_p, C.c_int32]
+        L.bowgpu_frame_col_null_count.argtypes = [C.c_void_p, C.c_int32]
+        L.bowgpu_frame_col_null_count.restype = C.c_int64
+        L.bowgpu_parquet_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.c_char_p, C.c_int32]
+        L.bowgpu_parquet_close.argtypes = [C.c_void_p]
+        L.bowgpu_parquet_close.restype = None
+        L.bowgpu_parquet_num_rows.argtypes = [C.c_void_p]
+        L.bowgpu_parquet_num_rows.restype = C.c_int64
+        L.bowgpu_parquet_num_cols.argtypes = [C.c_void_p]
+        L.bowgpu_parquet_col_name.argtypes = [C.c_void_p, C.c_int32]
+        L.bowgpu_parquet_col_name.restype = C.c_char_p
+        L.bowgpu_parquet_col_dtype.argtypes = [C.c_void_p, C.c_int32]
+        L.bowgpu_parquet_col_physical_type.argtypes = [C.c_void_p, C.c_int32]
+        L.bowgpu_parquet_plan.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int64), C.c_char_p, C.c_int32]
+        L.bowgpu_parquet_read.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p)]
         assert L.bowgpu_abi_version() == 1
         _lib = L
     return _lib
@@ -348,6 +365,9 @@ class Frame:
     def dtype(self, j: int) -> int:
         return lib().bowgpu_frame_col_dtype(self.h, j)
 
+    def null_count(self, j: int) -> int:
+        return lib().bowgpu_frame_col_null_count(self.h, j)
+
     def device_ptrs(self, j: int) -> Tuple[int, int]:
         v, b = C.c_void_p(), C.c_void_p()
         self.ctx.check(lib().bowgpu_frame_col_device_ptrs(self.h, j, C.byref(v), C.byref(b)))
@@ -430,6 +450,62 @@ class Frame:
         if self.h:
             lib().bowgpu_frame_destroy(self.h)
             self.h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ParquetFile:
+    """An open Parquet file: footer parsed on the host (bowparquet.go:44-66); read() decodes chosen columns on the GPU."""
+
+    def __init__(self, path: str):
+        h = C.c_void_p()
+        err = C.create_string_buffer(512)
+        rc = lib().bowgpu_parquet_open(os.fsencode(path), C.byref(h), err, 512)
+        if rc:
+            raise BowGpuError(rc, err.value.decode(errors="replace"))
+        self.h = h
+        L = lib()
+        self.num_rows = L.bowgpu_parquet_num_rows(h)
+        nc = L.bowgpu_parquet_num_cols(h)
+        self.names = [L.bowgpu_parquet_col_name(h, j).decode() for j in range(nc)]
+        self.dtypes = [L.bowgpu_parquet_col_dtype(h, j) for j in range(nc)]          # INT64 / FLOAT64 / 0 (no GPU type)
+        self.physical = [L.bowgpu_parquet_col_physical_type(h, j) for j in range(nc)]  # parquet.Type
+
+    def plan(self, cols: Optional[Sequence[int]] = None) -> dict:
+        """The host-side page walk only: pages, uploaded bytes, scratch bytes, dictionary-index entries."""
+        if cols is None:
+            cols = [j for j, d in enumerate(self.dtypes) if d]
+        arr = (C.c_int32 * max(1, len(cols)))(*cols)
+        out = (C.c_int64 * 4)()
+        err = C.create_string_buffer(512)
+        rc = lib().bowgpu_parquet_plan(self.h, arr, len(cols), out, err, 512)
+        if rc:
+            raise BowGpuError(rc, err.value.decode(errors="replace"))
+        return {"pages": out[0], "image_bytes": out[1], "scratch_bytes": out[2], "aux_entries": out[3]}
+
+    def read(self, ctx: "Ctx", cols: Optional[Sequence[int]] = None) -> "Frame":
+        """cols = leaf column indices (default: every column with a GPU type)."""
+        if cols is None:
+            cols = [j for j, d in enumerate(self.dtypes) if d]
+        arr = (C.c_int32 * max(1, len(cols)))(*cols)
+        h = C.c_void_p()
+        ctx.check(lib().bowgpu_parquet_read(ctx.h, self.h, arr, len(cols), C.byref(h)))
+        return Frame(ctx, h)
+
+    def close(self):
+        if self.h:
+            lib().bowgpu_parquet_close(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
 
     def __del__(self):  # pragma: no cover
         try:

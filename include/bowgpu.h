@@ -42,7 +42,8 @@ enum {
     BOWGPU_ENULLTIME = 8,      /* time column holds nulls (GPU path precondition) */
     BOWGPU_ECUDA = 9,          /* CUDA runtime / launch failure; see bowgpu_last_error */
     BOWGPU_ENOMEM = 10,        /* device or pinned host allocation failed */
-    BOWGPU_EUNSUPPORTED = 11   /* operator not executable on the device (custom Go closure, Bool/String column) */
+    BOWGPU_EUNSUPPORTED = 11,  /* operator not executable on the device (custom Go closure, Bool/String column) */
+    BOWGPU_EIO = 12            /* file cannot be read or is not well-formed Parquet (bowparquet.go:45-56 error paths) */
 };
 
 /* ---- column types: bow.Float64 / bow.Int64 (bowtypes.go:21-22) ---------------------- */
@@ -165,6 +166,31 @@ int32_t bowgpu_frame_download(const bowgpu_frame *frame, bowgpu_out_col *outs, i
 /* Same for rows [row0, row0 + nrows): the counterpart of Bow.NewSlice (bow.go:279-283) + download. */
 int32_t bowgpu_frame_download_range(const bowgpu_frame *frame, int64_t row0, int64_t nrows, bowgpu_out_col *outs,
                                     int32_t ncols);
+/* ---- Parquet ingest: bow.NewBowFromParquet (bowparquet.go:44-155) ------------------------
+ * The host walks the footer and the page headers only; the bytes of the chosen column chunks go to the
+ * device as they are and are decompressed (Snappy) and decoded there (definition levels -> validity
+ * bitmap, PLAIN / dictionary values -> bow.NewBuffer layout).  Flat schemas, INT64 / DOUBLE leaves
+ * (mapParquetToBowTypes, bowparquet.go:20-25; Boolean and String columns have no GPU type: dtype 0),
+ * UNCOMPRESSED / SNAPPY, data pages v1 and v2.  `err` (may be null) receives the message of a failed open. */
+typedef struct bowgpu_parquet bowgpu_parquet;
+int32_t bowgpu_parquet_open(const char *path, bowgpu_parquet **out, char *err, int32_t err_cap);
+void bowgpu_parquet_close(bowgpu_parquet *pq);
+int64_t bowgpu_parquet_num_rows(const bowgpu_parquet *pq);
+int32_t bowgpu_parquet_num_cols(const bowgpu_parquet *pq);                 /* leaf columns, schema order */
+const char *bowgpu_parquet_col_name(const bowgpu_parquet *pq, int32_t col);
+int32_t bowgpu_parquet_col_dtype(const bowgpu_parquet *pq, int32_t col);   /* BOWGPU_INT64 / BOWGPU_FLOAT64 / 0 */
+int32_t bowgpu_parquet_col_physical_type(const bowgpu_parquet *pq, int32_t col); /* parquet.Type */
+/* Reads the leaf columns cols[0..ncols) (every one must have a GPU type: else BOWGPU_ETYPE) into a new
+ * device-resident frame; column j of the frame = cols[j].  Malformed page data -> BOWGPU_EIO. */
+int32_t bowgpu_parquet_read(bowgpu_ctx *ctx, const bowgpu_parquet *pq, const int32_t *cols, int32_t ncols,
+                            bowgpu_frame **out);
+/* The page walk alone (host only, no device work): out4 = {pages, bytes uploaded, bytes of uncompressed
+ * scratch, dictionary-index entries} for the chosen columns.  Diagnostic; also what sizes the device buffers. */
+int32_t bowgpu_parquet_plan(const bowgpu_parquet *pq, const int32_t *cols, int32_t ncols, int64_t *out4, char *err,
+                            int32_t err_cap);
+/* null count of a device column (-1: bad index) */
+int64_t bowgpu_frame_col_null_count(const bowgpu_frame *frame, int32_t col);
+
 /* Device-side synthetic generators for the BASELINE.json configs.  Deterministic in
  * (seed, column, row): any sub-range can be regenerated.  kind: see BOWGPU_GEN_*. */
 #define BOWGPU_GEN_REGULAR 0 /* t[i] = t0 + (row0+i)*step ; float64 v in [0,1) ; optional nulls */
