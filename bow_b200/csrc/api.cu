@@ -3,8 +3,10 @@
 #include "../../include/bowgpu.h"
 
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <cerrno>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -46,6 +48,9 @@ struct bowgpu_ctx {
     std::vector<bowgpu_ctx *> workers;
     // side streams of Rolling.Aggregate: the streaming launches of several value columns run side by side, each on its
     // share of the SMs, so that the time tiles they all read are fetched from DRAM once and served from L2 after that
+    // staging of file reads (bowgpu_parquet_read): reader threads pread() straight into pinned chunks
+    std::vector<uint8_t *> file_stage;
+    std::vector<cudaEvent_t> file_stage_ev;
     std::vector<cudaStream_t> side;
     std::vector<cudaEvent_t> side_done;
     cudaEvent_t side_fork = nullptr;
@@ -388,6 +393,8 @@ extern "C" void bowgpu_ctx_destroy(bowgpu_ctx *ctx) {
         if (ctx->ev_total[i]) cudaEventDestroy(ctx->ev_total[i]);
     }
     for (auto e : ctx->ev_main) cudaEventDestroy(e);
+    for (auto b : ctx->file_stage) cudaFreeHost(b);
+    for (auto e : ctx->file_stage_ev) cudaEventDestroy(e);
     for (auto st : ctx->side) cudaStreamDestroy(st);
     for (auto e : ctx->side_done) cudaEventDestroy(e);
     if (ctx->side_fork) cudaEventDestroy(ctx->side_fork);
@@ -648,6 +655,62 @@ extern "C" int32_t bowgpu_frame_download(const bowgpu_frame *f, bowgpu_out_col *
 // ================================================================================================
 // Parquet ingest (bowparquet.go:44-155): metadata on the host, data on the device (parquet.cu)
 // ================================================================================================
+// File bytes -> device: FILE_READERS threads pread() slices of the ranges into their own pair of pinned chunks and queue the
+// DMA on the ctx stream (one memcpy page cache -> pinned per byte; a single thread copying out of an mmap tops out near
+// 8 GB/s and pays a page fault per 4 KB).  The reference reads with 4 goroutines as well (pr.NP = 4, bowparquet.go:52).
+constexpr int FILE_READERS = 4;
+constexpr size_t FILE_SLICE = (size_t)16 << 20;
+static int32_t upload_file_ranges(bowgpu_ctx *ctx, int fd, const std::vector<PqRange> &ranges, uint8_t *image) {
+    struct Slice {
+        int64_t file_off, len, image_off;
+    };
+    std::vector<Slice> slices;
+    for (const PqRange &rg : ranges)
+        for (int64_t o = 0; o < rg.len; o += (int64_t)FILE_SLICE)
+            slices.push_back({rg.file_off + o, std::min<int64_t>((int64_t)FILE_SLICE, rg.len - o), rg.image_off + o});
+    if (slices.empty()) return BOWGPU_OK;
+    while (ctx->file_stage.size() < (size_t)2 * FILE_READERS) {
+        uint8_t *b = nullptr;
+        cudaEvent_t e;
+        CK(cudaHostAlloc((void **)&b, FILE_SLICE, cudaHostAllocDefault));
+        ctx->file_stage.push_back(b);
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->file_stage_ev.push_back(e);
+    }
+    const int nthreads = (int)std::min<size_t>(FILE_READERS, slices.size());
+    std::atomic<size_t> next{0};
+    std::atomic<int> err{0};
+    auto work = [&](int t) {
+        cudaSetDevice(ctx->device);
+        int b = 0;
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= slices.size() || err.load()) break;
+            const Slice &sl = slices[i];
+            uint8_t *buf = ctx->file_stage[2 * t + b];
+            cudaEvent_t ev = ctx->file_stage_ev[2 * t + b];
+            if (cudaEventSynchronize(ev) != cudaSuccess) { err = 1; break; }
+            int64_t done = 0;
+            while (done < sl.len) {
+                const ssize_t r = pread(fd, buf + done, (size_t)(sl.len - done), (off_t)(sl.file_off + done));
+                if (r <= 0) { err = 2; break; }
+                done += r;
+            }
+            if (err.load()) break;
+            if (cudaMemcpyAsync(image + sl.image_off, buf, (size_t)sl.len, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+                cudaEventRecord(ev, ctx->stream) != cudaSuccess) { err = 1; break; }
+            b ^= 1;
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    if (err.load() == 2) return fail(ctx, BOWGPU_EIO, "pread: %s", strerror(errno));
+    if (err.load()) return fail(ctx, BOWGPU_ECUDA, "file upload: %s", cudaGetErrorString(cudaGetLastError()));
+    return BOWGPU_OK;
+}
+
 struct bowgpu_parquet {
     PqFile *file = nullptr;
 };
@@ -764,11 +827,11 @@ extern "C" int32_t bowgpu_parquet_read(bowgpu_ctx *ctx, const bowgpu_parquet *pq
     if ((rc = ck(pool_alloc(ctx, (void **)&scratch, (size_t)plan.scratch_bytes), "parquet scratch"))) return cleanup(rc);
     if ((rc = ck(pool_alloc(ctx, (void **)&aux, (size_t)(plan.aux_entries + 16) * 4), "parquet index scratch"))) return cleanup(rc);
     // the file bytes of the chosen column chunks, as they are
-    const uint8_t *bytes = pq_bytes(pq->file);
-    for (const PqRange &rg : plan.ranges) {
-        rc = copy_h2d(ctx, image + rg.image_off, bytes + rg.file_off, (size_t)rg.len);
-        if (rc) return cleanup(rc);
-    }
+    // (the padding behind every range / page is read by the word-granular loads of the decoder, never used: zero it)
+    if ((rc = ck(cudaMemsetAsync(image, 0, (size_t)plan.image_bytes, ctx->stream), "memset"))) return cleanup(rc);
+    if ((rc = ck(cudaMemsetAsync(scratch, 0, (size_t)plan.scratch_bytes, ctx->stream), "memset"))) return cleanup(rc);
+    rc = upload_file_ranges(ctx, pq_fd(pq->file), plan.ranges, image);
+    if (rc) return cleanup(rc);
     std::vector<PqColOut> hc(ncols);
     for (int j = 0; j < ncols; ++j) {
         hc[j].values = f->cols[j].values;

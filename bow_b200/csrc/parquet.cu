@@ -331,6 +331,7 @@ void pq_close(PqFile *f) {
 int64_t pq_num_rows(const PqFile *f) { return f->num_rows; }
 const std::vector<PqColumn> &pq_columns(const PqFile *f) { return f->cols; }
 const uint8_t *pq_bytes(const PqFile *f) { return f->map; }
+int pq_fd(const PqFile *f) { return f->fd; }
 
 int pq_plan(const PqFile *f, const int32_t *cols, int32_t ncols, PqPlan &plan, std::string &err) {
     plan = PqPlan();

@@ -60,6 +60,7 @@ void pq_close(PqFile *f);
 int64_t pq_num_rows(const PqFile *f);
 const std::vector<PqColumn> &pq_columns(const PqFile *f);
 const uint8_t *pq_bytes(const PqFile *f);
+int pq_fd(const PqFile *f);
 // walks the page headers of the chosen leaf columns (indices into pq_columns, output column j = cols[j])
 int pq_plan(const PqFile *f, const int32_t *cols, int32_t ncols, PqPlan &plan, std::string &err);
 

@@ -53,7 +53,7 @@ def report(name, n, secs, alg_bytes, extra=None):
 
 def main():
     ctx = N.Ctx(0)
-    which = sys.argv[1:] or ["1", "1b", "2", "3", "4", "whole", "fill", "sort"]
+    which = sys.argv[1:] or ["1", "1b", "2", "3", "4", "whole", "fill", "sort", "parquet"]
     if "1" in which or "1b" in which:
         for tag, n in (("1", int(1e8 * SCALE)), ("1b", int(1e9 * SCALE))):
             if tag not in which:
@@ -204,6 +204,38 @@ def main():
             g0, g1 = v0[order], v1[order]
         torch.cuda.synchronize()
         report("(context) torch.sort(stable) + 2 gathers of the same timestamps", n, (time.perf_counter() - t0) / 3, 2 * 3 * 8 * n)
+    if "parquet" in which:  # bow.NewBowFromParquet — file (page cache) -> device-resident frame
+        import numpy as np
+        import pyarrow as pa
+        import pyarrow.parquet as pq
+        import tempfile
+        n = int(5e7 * SCALE)
+        rng = np.random.default_rng(3)
+        tcol = 1_700_000_000_000_000_000 + np.arange(n, dtype=np.int64) * SEC
+        table = pa.table({"t": pa.array(tcol),
+                          "a": pa.array(rng.random(n), mask=rng.random(n) < 0.1),
+                          "b": pa.array(rng.random(n), mask=rng.random(n) < 0.1)})
+        d = tempfile.mkdtemp()
+        for tag, opts in (("SNAPPY, PLAIN, 1 MiB pages (pyarrow defaults without dictionary)", dict(compression="SNAPPY", use_dictionary=False)),
+                          ("UNCOMPRESSED, PLAIN", dict(compression="NONE", use_dictionary=False)),
+                          ("SNAPPY, PLAIN, 8 KiB pages (the page size of the reference's writer)",
+                           dict(compression="SNAPPY", use_dictionary=False, data_page_size=8192))):
+            path = os.path.join(d, "f.parquet")
+            pq.write_table(table, path, **opts)
+            fbytes = os.path.getsize(path)
+            open(path, "rb").read()  # page cache
+            pf = N.ParquetFile(path)
+
+            def run():
+                pf.read(ctx).close()
+            dt = timed(ctx, run, reps=3, warm=1)
+            t0 = time.perf_counter()
+            pq.read_table(path, use_threads=True)
+            t_arrow = time.perf_counter() - t0
+            report(f"NewBowFromParquet {tag}: file -> device frame (3 columns, 10 % nulls)", n, dt, 3 * 8 * n,
+                   {"file_bytes": fbytes, "pages": pf.plan()["pages"], "pyarrow_read_table_ms_all_threads": t_arrow * 1e3})
+            pf.close()
+            os.remove(path)
 
 
 if __name__ == "__main__":
