@@ -191,3 +191,28 @@ def test_mirror_NewBowFromParquet(ctx, tmp_path):
             B.NewBowFromParquet(str(tmp_path / "nope.parquet"))
     finally:
         runtime.set_default_ctx(None)
+
+
+@pytest.mark.parametrize("interval", [10, 1000])
+def test_config0_from_the_parquet_file_stays_on_the_device(ctx, interval):
+    """BASELINE.json configs[0] as the reference runs it (benchmarks/bow1-100000-rows.parquet: NewBowFromParquet ->
+    IntervalRolling(Int64_ref, 10) -> ArithmeticMean / Count / Min / Max), file -> device frame -> Aggregate without a
+    host round trip, against the oracle on the independently decoded columns."""
+    from oracle import refc as R
+    path = os.path.join(GOLD, "bow1-100000-rows.parquet")
+    names = ["Int64_ref", "Int64_bow1", "Float64_bow1"]
+    with N.ParquetFile(path) as pf:
+        fr = pf.read(ctx, [pf.names.index(n) for n in names])
+    specs = [("WindowStart", 0)] + [(a, c) for c in (1, 2) for a in ("ArithmeticMean", "Count", "Min", "Max")]
+    r = N.Rolling(fr, 0, interval)
+    got = r.aggregate(specs)
+    r.close()
+    fr.close()
+    cols = [(v, None if m.all() else m) for v, m in arrow_cols(path, names)]
+    want = R.RefRolling(R.Frame(cols), 0, interval).aggregate(specs)
+    for sp, (gv, gm), (wv, wm) in zip(specs, got, want):
+        assert np.array_equal(gm, wm), sp
+        if sp[0] == "ArithmeticMean":
+            assert np.allclose(gv[gm], wv[wm], rtol=1e-12, atol=0), sp
+        else:
+            assert np.array_equal(gv[gm].view(np.int64), wv[wm].view(np.int64)), sp
