@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cerrno>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -779,8 +780,15 @@ extern "C" int32_t bowgpu_parquet_read(bowgpu_ctx *ctx, const bowgpu_parquet *pq
     Guard gd(ctx);
     PqPlan plan;
     std::string msg;
+    const bool dbg = getenv("BOWGPU_PQ_DEBUG") != nullptr;  // stage times on stderr (synchronises between stages)
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [&](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(now() - t0).count();
+    };
+    auto t_stage = now();
     int32_t rc = pq_plan(pq->file, cols, ncols, plan, msg);
     if (rc) return fail(ctx, rc, "%s", msg.c_str());
+    if (dbg) fprintf(stderr, "pq: plan %.2f ms (%zu pages)\n", ms_since(t_stage), plan.pages.size());
     const int64_t n = pq_num_rows(pq->file);
     const auto &pcols = pq_columns(pq->file);
     bowgpu_frame *f = new (std::nothrow) bowgpu_frame();
@@ -830,8 +838,18 @@ extern "C" int32_t bowgpu_parquet_read(bowgpu_ctx *ctx, const bowgpu_parquet *pq
     // (the padding behind every range / page is read by the word-granular loads of the decoder, never used: zero it)
     if ((rc = ck(cudaMemsetAsync(image, 0, (size_t)plan.image_bytes, ctx->stream), "memset"))) return cleanup(rc);
     if ((rc = ck(cudaMemsetAsync(scratch, 0, (size_t)plan.scratch_bytes, ctx->stream), "memset"))) return cleanup(rc);
+    if (dbg) {
+        cudaStreamSynchronize(ctx->stream);
+        fprintf(stderr, "pq: alloc + memset %.2f ms\n", ms_since(t_stage));
+        t_stage = now();
+    }
     rc = upload_file_ranges(ctx, pq_fd(pq->file), plan.ranges, image);
     if (rc) return cleanup(rc);
+    if (dbg) {
+        cudaStreamSynchronize(ctx->stream);
+        fprintf(stderr, "pq: upload %.2f ms (%.1f MB)\n", ms_since(t_stage), plan.image_bytes / 1e6);
+        t_stage = now();
+    }
     std::vector<PqColOut> hc(ncols);
     for (int j = 0; j < ncols; ++j) {
         hc[j].values = f->cols[j].values;
@@ -850,6 +868,7 @@ extern "C" int32_t bowgpu_parquet_read(bowgpu_ctx *ctx, const bowgpu_parquet *pq
     if (!rc) rc = ck(cudaMemcpyAsync(&st, ctx->d_status, 4, cudaMemcpyDeviceToHost, ctx->stream), "status");
     if (!rc) rc = ck(cudaStreamSynchronize(ctx->stream), "parquet decode");
     if (rc) return cleanup(rc);
+    if (dbg) fprintf(stderr, "pq: tables + decompress + decode %.2f ms\n", ms_since(t_stage));
     if (st & ST_PARQUET) {
         cudaMemsetAsync(ctx->d_status, 0, 4, ctx->stream);
         return cleanup(fail(ctx, BOWGPU_EIO, "malformed parquet page data (Snappy stream, levels or values out of bounds)"));
