@@ -12,6 +12,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <new>
 #include <atomic>
 #include <string>
@@ -843,13 +845,6 @@ extern "C" int32_t bowgpu_parquet_read(bowgpu_ctx *ctx, const bowgpu_parquet *pq
         fprintf(stderr, "pq: alloc + memset %.2f ms\n", ms_since(t_stage));
         t_stage = now();
     }
-    rc = upload_file_ranges(ctx, pq_fd(pq->file), plan.ranges, image);
-    if (rc) return cleanup(rc);
-    if (dbg) {
-        cudaStreamSynchronize(ctx->stream);
-        fprintf(stderr, "pq: upload %.2f ms (%.1f MB)\n", ms_since(t_stage), plan.image_bytes / 1e6);
-        t_stage = now();
-    }
     std::vector<PqColOut> hc(ncols);
     for (int j = 0; j < ncols; ++j) {
         hc[j].values = f->cols[j].values;
@@ -860,7 +855,18 @@ extern "C" int32_t bowgpu_parquet_read(bowgpu_ctx *ctx, const bowgpu_parquet *pq
     rc = copy_h2d(ctx, d_pages, plan.pages.data(), (size_t)npages * sizeof(PqPage));
     if (!rc) rc = copy_h2d(ctx, d_cols, hc.data(), (size_t)ncols * sizeof(PqColOut));
     if (rc) return cleanup(rc);
-    if ((rc = ck((cudaError_t)launch_pq_decode(d_pages, npages, image, scratch, aux, d_cols, ctx->d_status, ctx->stream), "parquet decode")))
+    rc = upload_file_ranges(ctx, pq_fd(pq->file), plan.ranges, image);
+    if (rc) return cleanup(rc);
+    if (dbg) {
+        cudaStreamSynchronize(ctx->stream);
+        fprintf(stderr, "pq: upload %.2f ms (%.1f MB)\n", ms_since(t_stage), plan.image_bytes / 1e6);
+        t_stage = now();
+    }
+    // Decompress + decode after the last byte has arrived.  Launching the kernels of a column chunk as soon as its bytes were
+    // queued (second stream, behind an event) was measured and is WORSE on B200: 44.5 instead of 38.5 ms uncompressed,
+    // 1138 instead of 61 ms with Snappy and 1 MiB pages (the long-running one-warp-per-page kernel and the H2D stream get
+    // in each other's way) — gpurun_out/s12_parquet.jsonl.
+    if ((rc = ck((cudaError_t)launch_pq_decode(d_pages, 0, npages, image, scratch, aux, d_cols, ctx->d_status, ctx->stream), "parquet decode")))
         return cleanup(rc);
     std::vector<unsigned long long> counts(ncols);
     int32_t st = 0;
@@ -868,7 +874,7 @@ extern "C" int32_t bowgpu_parquet_read(bowgpu_ctx *ctx, const bowgpu_parquet *pq
     if (!rc) rc = ck(cudaMemcpyAsync(&st, ctx->d_status, 4, cudaMemcpyDeviceToHost, ctx->stream), "status");
     if (!rc) rc = ck(cudaStreamSynchronize(ctx->stream), "parquet decode");
     if (rc) return cleanup(rc);
-    if (dbg) fprintf(stderr, "pq: tables + decompress + decode %.2f ms\n", ms_since(t_stage));
+    if (dbg) fprintf(stderr, "pq: decompress + decode %.2f ms\n", ms_since(t_stage));
     if (st & ST_PARQUET) {
         cudaMemsetAsync(ctx->d_status, 0, 4, ctx->stream);
         return cleanup(fail(ctx, BOWGPU_EIO, "malformed parquet page data (Snappy stream, levels or values out of bounds)"));
@@ -1573,7 +1579,7 @@ static int32_t aggregate_core(bowgpu_rolling *r, const bowgpu_agg_spec *specs, i
     const size_t wv = align_up((size_t)W * 8, 256), wb = align_up((size_t)((W + 7) / 8) + 16, 256);
     const size_t carry_bytes = align_up(std::max(seg_carry_bytes(g.n), integral_carry_bytes(g.n)), 256);
     const size_t skip_bytes = align_up(std::max(seg_skip_bytes(g.n), integral_skip_bytes(g.n)) + 256, 256);
-    size_t need = 8192 + (size_t)K * (skip_bytes + carry_bytes + 512) + (size_t)n_basic_cols * 2 * (wv + 256) +
+    size_t need = 8192 + 256 * (size_t)(n_basic_cols + n_int_cols + 2) + (size_t)K * (skip_bytes + carry_bytes + 512) + (size_t)n_basic_cols * 2 * (wv + 256) +
                   (size_t)n_int_cols * 4 * (wv + 256);
     if (mem == BOWGPU_MEM_HOST) need += (size_t)nspecs * (wv + wb);
     rc = arena_reserve(ctx, need);
@@ -1603,6 +1609,7 @@ static int32_t aggregate_core(bowgpu_rolling *r, const bowgpu_agg_spec *specs, i
     std::vector<const double *> spec_src(nspecs, nullptr);
     for (int fam = 0; fam < 2; ++fam) {
         int left = n_fam[fam], lane = 0, width = 0;  // launches of the family still to go; lane and width of the open wave
+        int32_t *gate = nullptr;
         for (int c : cols_used) {
             const DevCol &dc = f->cols[c];
             // first spec of each op on this column receives the kernel output; duplicates are copied afterwards
@@ -1621,7 +1628,12 @@ static int32_t aggregate_core(bowgpu_rolling *r, const bowgpu_agg_spec *specs, i
             if (lane == width) {  // open a wave (the main stream has already been told to wait for the previous one)
                 width = std::min(K, left);
                 lane = 0;
-                if (width > 1) CK(cudaEventRecord(ctx->side_fork, ctx->stream));
+                gate = nullptr;
+                if (width > 1) {
+                    gate = (int32_t *)arena_take(ctx, 256);  // the lanes of a wave start their walk together
+                    if (gate) CK(cudaMemsetAsync(gate, 0, 4, ctx->stream));
+                    CK(cudaEventRecord(ctx->side_fork, ctx->stream));
+                }
             }
             cudaStream_t st = ctx->stream;
             if (width > 1) {
@@ -1662,6 +1674,8 @@ static int32_t aggregate_core(bowgpu_rolling *r, const bowgpu_agg_spec *specs, i
                 L.skip = (BasicCarry *)skip;
                 L.status = ctx->d_status;
                 if (syn_by_col) L.syn = syn_by_col[c];
+                L.gate = gate;
+                L.gate_lanes = width;
                 // the valid-row count drives every validity bitmap: Count output if it can be used as is, else scratch
                 int64_t *cnt = nullptr;
                 if (primary[BOWGPU_AGG_COUNT] >= 0 && specs[primary[BOWGPU_AGG_COUNT]].nfactors == 0)
@@ -1706,6 +1720,8 @@ static int32_t aggregate_core(bowgpu_rolling *r, const bowgpu_agg_spec *specs, i
                 L.skip = skip;
                 L.status = ctx->d_status;
                 if (syn_by_col) L.syn = syn_by_col[c];
+                L.gate = gate;
+                L.gate_lanes = width;
                 const bool want_step = count[BOWGPU_AGG_INTEGRAL_STEP] || count[BOWGPU_AGG_WAVG_STEP];
                 const bool want_trap = count[BOWGPU_AGG_INTEGRAL_TRAPEZOID] || count[BOWGPU_AGG_WAVG_LINEAR];
                 if (want_step) {

@@ -81,6 +81,8 @@ struct SegLaunch {
     BasicCarry *skip;         // [seg_skip_bytes(n) / sizeof] combined records of long runs of tiles, or null
     int32_t *status;
     FusedSyn syn;
+    int32_t *gate;            // side-by-side lanes (api.cu): every lane's first CTA checks in here and all CTAs wait
+    int32_t gate_lanes;       // until gate_lanes lanes have (bounded wait), so that the lanes walk the rows abreast; null = none
 };
 
 int64_t seg_num_tiles(int64_t n);
@@ -109,6 +111,8 @@ struct IntLaunch {
     void *skip;        // integral_skip_bytes(n) or null
     int32_t *status;
     FusedSyn syn;
+    int32_t *gate;            // side-by-side lanes (api.cu): every lane's first CTA checks in here and all CTAs wait
+    int32_t gate_lanes;       // until gate_lanes lanes have (bounded wait), so that the lanes walk the rows abreast; null = none
 };
 size_t integral_carry_bytes(int64_t n);
 size_t integral_skip_bytes(int64_t n);

@@ -51,6 +51,7 @@ struct PqRange {  // bytes of the file the selected columns need, and where they
 struct PqPlan {
     std::vector<PqRange> ranges;
     std::vector<PqPage> pages;
+    std::vector<int32_t> range_first_page;  // pages of ranges[r] = [range_first_page[r], range_first_page[r + 1])
     int64_t image_bytes = 0, scratch_bytes = 0, aux_entries = 0;
 };
 
@@ -65,7 +66,8 @@ int pq_fd(const PqFile *f);
 int pq_plan(const PqFile *f, const int32_t *cols, int32_t ncols, PqPlan &plan, std::string &err);
 
 // decompress (one warp per compressed page) and decode (one CTA per data page); ST_PARQUET in *status on malformed data
-int launch_pq_decode(const PqPage *d_pages, int npages, const uint8_t *image, uint8_t *scratch, int32_t *aux,
+// (pages [first, first + count) of the table; dictionary references are indices into the whole table)
+int launch_pq_decode(const PqPage *d_pages, int first, int count, const uint8_t *image, uint8_t *scratch, int32_t *aux,
                      const PqColOut *d_cols, int32_t *status, cudaStream_t stream);
 
 }  // namespace bowgpu

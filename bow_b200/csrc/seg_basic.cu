@@ -49,6 +49,8 @@ __device__ __forceinline__ void write_window(const BasicOut &o, int64_t W, int64
 
 template <uint32_t OPS, bool IS_INT>
 struct BasicPol {
+    static constexpr bool LINEAR_PHASE = false;  // (the basic family runs at the DRAM rate with the generic row loop)
+    struct Lin {};
     using State = BState;
     using Carry = BasicCarry;
     using Out = BasicOut;
@@ -190,6 +192,8 @@ int launch_ops(const SegLaunch &L, int sm, cudaStream_t s, cudaEvent_t e0, cudaE
         A.skip = L.skip;
         A.status = L.status;
         A.syn = L.syn;
+        A.gate = L.gate;
+        A.gate_lanes = L.gate_lanes;
     };
     if (L.is_int) {
         SegArgs<BasicPol<OPS, true>> A;

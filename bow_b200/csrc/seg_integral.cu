@@ -82,6 +82,73 @@ struct IntegralPol {
         s.lV = v;
         s.has = 1;
     }
+    // ---- straight-line phase (segreduce.cuh seg_phase_linear) ---------------------------------------------------------------
+    static constexpr bool LINEAR_PHASE = true;
+    struct Lin {
+        double lT, lV;             // the previous valid point of the chain
+        double sSa, sTa, sSb, sTb; // sums of the open window (a) and of the window that begins at the boundary row (b)
+        bool has;                  // the chain has a previous point inside the same window
+    };
+    static __device__ __forceinline__ Lin lin_begin(const State &s) {
+        Lin L;
+        L.lT = s.lT;
+        L.lV = s.lV;
+        L.sSa = s.sS;
+        L.sTa = s.sT;
+        L.sSb = L.sTb = 0.0;
+        L.has = s.has != 0;
+        return L;
+    }
+    // row j of the phase (j is a constant after unrolling); rows from b on belong to the next window
+    static __device__ __forceinline__ void lin_row(Lin &L, const int j, const int b, const int64_t t, const uint64_t raw,
+                                                   const bool valid) {
+        const double T = (double)t, v = val(raw);
+        const bool in_b = j >= b;
+        const bool has = L.has && j != b;  // the boundary row has no predecessor in its window
+        const double dt = T - L.lT;
+        const bool join = valid && has;
+        if (STEP) {
+            const double ts = L.lV * dt;  // integral.go:57
+            if (join && !in_b) L.sSa += ts;
+            if (join && in_b) L.sSb += ts;
+        }
+        if (TRAP) {
+            const double tt = (L.lV + v) / 2 * dt;  // integral.go:28
+            if (join && !in_b) L.sTa += tt;
+            if (join && in_b) L.sTb += tt;
+        }
+        if (valid) {
+            L.lT = T;
+            L.lV = v;
+        }
+        L.has = has || valid;
+    }
+    static __device__ __forceinline__ void lin_end_open(State &s, const Lin &L) {  // no boundary in the phase
+        s.lT = L.lT;
+        s.lV = L.lV;
+        s.sS = L.sSa;
+        s.sT = L.sTa;
+        s.has = L.has;
+    }
+    // one boundary: sa = the open window after its rows (mask ma), sb = the next window's rows of this phase (mask mb)
+    static __device__ __forceinline__ void lin_end_split(State &sa, State &sb, const Lin &L, const uint32_t ma, const uint32_t mb,
+                                                         const int64_t *trow, const uint64_t *vrow, const int swz) {
+        sa.sS = L.sSa;
+        sa.sT = L.sTa;
+        if (ma) {  // its last point: the last valid row before the boundary
+            const int j = (31 - __clz(ma)) ^ swz;
+            sa.lT = (double)trow[j];
+            sa.lV = val(vrow[j]);
+            sa.has = 1;
+        }
+        sb.sS = L.sSb;
+        sb.sT = L.sTb;
+        if (mb) {
+            sb.lT = L.lT;
+            sb.lV = L.lV;
+            sb.has = 1;
+        }
+    }
     // the number of points and the first point of a run come from the validity bits of the rows that joined it
     static __device__ __forceinline__ void note(State &s, uint32_t mask, const int64_t *trow, const uint64_t *vrow, const int swz) {
         if (mask) {
@@ -256,6 +323,8 @@ int launch_mode(const IntLaunch &L, int sm, cudaStream_t s, cudaEvent_t e0, cuda
         A.skip = (ICarry *)L.skip;
         A.status = L.status;
         A.syn = L.syn;
+        A.gate = L.gate;
+        A.gate_lanes = L.gate_lanes;
     };
     if (L.is_int) {
         SegArgs<IntegralPol<STEP, TRAP, true>> A;

@@ -75,6 +75,9 @@ constexpr bool SEG_SWZ = SEG_CFG_SWZ != 0;
 #ifndef SEG_CFG_FUSED_PREFETCH
 #define SEG_CFG_FUSED_PREFETCH 1
 #endif
+#ifndef SEG_CFG_LINEAR
+#define SEG_CFG_LINEAR 1
+#endif
 constexpr int SEG_UNROLL = SEG_CFG_UNROLL;  // row pairs per trip of the streaming loop
 constexpr int SEG_NT = SEG_CFG_NT;
 constexpr int SEG_P = 16;                     // rows per phase (box start columns must be 16-byte aligned in global memory)
@@ -111,6 +114,8 @@ struct SegArgs {
     typename Pol::Carry *skip;        // [seg_skip_records(ntiles)] or null: combined records of runs of 32 / 1024 / 32768 tiles
     int32_t *status;
     FusedSyn syn;                     // fused Interpolate -> Aggregate (FUSED instantiations only)
+    int32_t *gate;                    // start gate of side-by-side lanes (null = none), see SegLaunch
+    int32_t gate_lanes;
 };
 
 template <class Pol>
@@ -232,7 +237,125 @@ struct SegThread {
     uint64_t first_raw;
     uint32_t first_flags;
     int nclose;
+    // fused kernel: the first window boundary of the thread in this tile, met by the straight-line phase and resolved later
+    // (seg_resolve_deferred): the window that closed, the row that closed it
+    uint64_t dk;
+    int64_t dx;
+    uint64_t draw;
+    uint32_t dvalid;
+    int deferred;
 };
+
+// Fused Interpolate -> Aggregate: what a window boundary needs — the inclusive row of the window that closed and the
+// synthetic start row of the one that began (global loads, ~300 dependent instructions executed by the one or two lanes of
+// a warp that met a boundary) — used to run inside the phase, where the other three warps of the CTA wait for it at the
+// phase barrier (ncu: 26 % of the kernel's stall samples on that barrier, 1.86 barrier stalls per issued instruction
+// against 1.0 in the unfused kernel).  The straight-line phase now only PARKS the first boundary of a thread (state of the
+// closed window in local memory, the boundary row in registers) and goes on with the next window from the identity; the
+// rest happens once per tile, before the stitch, in all threads at the same time.  States are monoids, so joining the
+// synthetic start row afterwards (combine(fresh, rows)) gives the window the same value up to float64 association.
+template <class Pol>
+__device__ __forceinline__ void seg_resolve_deferred(SegThread<Pol> &c, const SegArgs<Pol> &A, typename Pol::Inc *finc) {
+    if (!c.deferred) return;
+    typename Pol::State fresh;
+    *finc = fused_boundary<Pol>(A, c.dk, true, c.dk + 1, c.dx, c.draw, c.dvalid != 0, fresh);
+    c.st = Pol::combine(fresh, c.st);
+    c.deferred = 0;
+}
+
+// ---- straight-line phase (policies with Pol::LINEAR_PHASE) ---------------------------------------------------------------
+// The generic row loop below tests every row for a window boundary and for validity with branches; between two branches
+// ptxas has one row to schedule, so the float64 chain of a row (convert, subtract, multiply, add: ~50 cycles) is exposed
+// once per row and the integral kernels ran latency bound at a third of the issue rate.  When the 16 rows of a thread's
+// phase hold AT MOST ONE window boundary and no empty window follows it (decided from the phase's last row: rows are
+// sorted), the phase is executed as ONE basic block instead: every row forms its joint term with the previous valid row
+// unconditionally and adds it, under predicates, to the sums of the open window (rows before the boundary) or of the
+// window that begins at the boundary row; the boundary itself is dealt with once, after the rows.  The rows of different
+// positions are independent up to the predicated selects, so their float64 chains overlap.  Anything else — a second
+// boundary, windows without rows, tiles at the edges of the column — takes the generic loop.
+template <class Pol, bool HAS_NULLS, bool FUSED>
+__device__ __forceinline__ bool seg_phase_linear(SegThread<Pol> &c, const SegArgs<Pol> &A, const int64_t *trow,
+                                                 const uint64_t *vrow, const int swz, const uint32_t vbits, bool &bad,
+                                                 typename Pol::State *fhead, typename Pol::Inc *finc) {
+    using State = typename Pol::State;
+    using Inc = typename Pol::Inc;
+    constexpr int P = SEG_P;
+    const WindowGeom &g = A.g;
+    const uint64_t d = g.div.d;
+    const longlong2 *t2 = reinterpret_cast<const longlong2 *>(trow);
+    const ulonglong2 *v2 = reinterpret_cast<const ulonglong2 *>(vrow);
+    const int sh = swz >> 1;
+    const int64_t xend = trow[(P - 1) ^ swz];
+    int b = P;  // rows [0, b) belong to the open window, row b (if any) starts the next one
+    if (xend >= c.eabs) {
+        if ((uint64_t)xend - (uint64_t)c.eabs >= d) return false;  // a second boundary or windows without rows
+        b = 0;
+#pragma unroll
+        for (int q = 0; q < P / 2; ++q) {
+            const longlong2 tq = t2[q ^ sh];
+            b += (tq.x < c.eabs) + (tq.y < c.eabs);
+        }
+    }
+    if (FUSED && b < P) seg_resolve_deferred<Pol>(c, A, finc);  // (a second boundary in my rows of this tile: rare)
+    typename Pol::Lin L = Pol::lin_begin(c.st);
+    int64_t xprev = c.xlast;
+    bool unsorted = false;
+#pragma unroll
+    for (int q = 0; q < P / 2; ++q) {
+        const longlong2 tq = t2[q ^ sh];
+        const ulonglong2 vq = v2[q ^ sh];
+        unsorted |= tq.x < xprev;
+        unsorted |= tq.y < tq.x;
+        xprev = tq.y;
+        Pol::lin_row(L, 2 * q, b, tq.x, vq.x, !HAS_NULLS || ((vbits >> (2 * q)) & 1u));
+        Pol::lin_row(L, 2 * q + 1, b, tq.y, vq.y, !HAS_NULLS || ((vbits >> (2 * q + 1)) & 1u));
+    }
+    bad |= unsorted;
+    c.xlast = xend;
+    if (b == P) {  // no boundary: the open window takes all my rows
+        Pol::lin_end_open(c.st, L);
+        Pol::note(c.st, vbits, trow, vrow, swz);
+        return true;
+    }
+    // ---- one boundary, at row b ------------------------------------------------------------------------------------------
+    const uint32_t below = (1u << b) - 1u;
+    State sa = c.st, sb = Pol::identity();
+    Pol::lin_end_split(sa, sb, L, vbits & below, vbits & ~below, trow, vrow, swz);
+    Pol::note(sa, vbits & below, trow, vrow, swz);
+    Pol::note(sb, vbits & ~below, trow, vrow, swz);
+    const int64_t xb = trow[b ^ swz];
+    const uint64_t rb = vrow[b ^ swz];
+    const bool vb = (vbits >> b) & 1u;
+    const uint64_t kold = c.kcur;
+    ++c.kcur;
+    if (!FUSED) {
+        const Inc inc = Pol::make_inc(xb == c.eabs, vb, rb, xb);
+        if (c.nclose == 0) {
+            c.head = sa;
+            c.inc_head = inc;
+        } else {
+            Pol::write(A.out, g, (int64_t)kold, sa, inc);
+        }
+        c.st = sb;
+    } else {
+        // (the window that begins at row b starts from its synthetic row, if it has one: joined like two adjacent runs)
+        if (c.nclose == 0) {  // park it (seg_resolve_deferred)
+            *fhead = sa;
+            c.dk = kold;
+            c.dx = xb;
+            c.draw = rb;
+            c.dvalid = vb;
+            c.deferred = 1;
+            c.st = sb;
+        } else {
+            const State fresh = fused_close_cold<Pol>(A, kold, c.kcur, xb, rb, vb, sa, fhead, finc, c.nclose);
+            c.st = Pol::combine(fresh, sb);
+        }
+    }
+    c.eabs = (int64_t)((uint64_t)c.eabs + d);
+    ++c.nclose;
+    return true;
+}
 
 // One phase: P rows of every thread.  FULL: all rows of the tile exist and none lies before s0 (the common case,
 // free of per-row existence predicates).
@@ -296,6 +419,13 @@ __device__ __forceinline__ void seg_phase(SegThread<Pol> &c, const SegArgs<Pol> 
         }
 #endif
     }
+
+    if constexpr (Pol::LINEAR_PHASE && SEG_CFG_LINEAR) {
+        if (FULL && !(FUSED && SEG_CFG_FUSED_COLD != 2))
+            if (seg_phase_linear<Pol, HAS_NULLS, FUSED>(c, A, trow, vrow, swz, vbits, bad, fhead, finc)) return;
+    }
+
+    if (FUSED) seg_resolve_deferred<Pol>(c, A, finc);  // (the generic loop closes windows on the spot)
 
     int segstart = 0;  // first row of this phase that belongs to the open window
     // One row: order check against the previous row, window boundary test against the running absolute end,
@@ -541,6 +671,14 @@ __global__ void __launch_bounds__(SEG_NT, MIN_CTAS)
         fence_proxy_async();
     }
     __syncthreads();
+    if (A.gate) {  // side-by-side lanes start together (bounded wait: a lane that never shows up must not hang the others)
+        if (tid == 0) {
+            if (blockIdx.x == 0) atomicAdd(A.gate, 1);
+            const long long t0 = clock64();
+            while (*reinterpret_cast<volatile int32_t *>(A.gate) < A.gate_lanes && clock64() - t0 < 400000) __nanosleep(100);
+        }
+        __syncthreads();
+    }
     if (tid == 0)
         for (int q = 0; q < nstages; ++q) issue_item(q);
 
@@ -556,6 +694,11 @@ __global__ void __launch_bounds__(SEG_NT, MIN_CTAS)
         c.head = Pol::identity();
         c.inc_head = Pol::make_inc(false, false, 0, 0);
         c.nclose = 0;
+        c.deferred = 0;
+        c.dk = 0;
+        c.dx = 0;
+        c.draw = 0;
+        c.dvalid = 0;
         c.first_flags = 0;
         c.first_t = 0;
         c.first_raw = 0;
@@ -605,6 +748,7 @@ __global__ void __launch_bounds__(SEG_NT, MIN_CTAS)
             __syncthreads();  // every read of this slot is done
             if (tid == 0) issue_item(q + nstages);
         }
+        if (FUSED) seg_resolve_deferred<Pol>(c, A, &finc);
         if (FUSED && SEG_CFG_FUSED_COLD == 2) {
             c.head = fhead;
             c.inc_head = finc;

@@ -40,6 +40,7 @@ for r in rows:
 tot_i = sum(v[0] for v in agg.values())
 tot_s = sum(v[1] for v in agg.values())
 print(f"total warp-instructions {tot_i}  samples {tot_s}")
-for (f, ln), v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+bysmp = len(sys.argv) > 3 and sys.argv[3] == "samples"
+for (f, ln), v in sorted(agg.items(), key=lambda kv: -kv[1][1 if bysmp else 0])[:top]:
     st = ",".join(f"{k[6:]}:{n}" for k, n in sorted(v[2].items(), key=lambda kv: -kv[1])[:3])
     print(f"{100*v[0]/tot_i:5.1f}% inst {100*v[1]/max(1,tot_s):5.1f}% smp  {f}:{ln:<4} {v[3]}   [{st}]")
