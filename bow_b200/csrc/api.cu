@@ -2322,7 +2322,14 @@ extern "C" int32_t bowgpu_rolling_interpolate_aggregate(bowgpu_rolling *r, const
     B.g = gx;
     B.first = d_first;
     B.status = ctx->d_status;
-    int e = launch_bounds(B, ctx->sm_count, ctx->stream, nullptr, nullptr);
+    // window boundaries: one streaming pass over the time column, or — when windows hold hundreds of rows — a binary
+    // search per window (the fused reduction that follows checks the order of every row itself)
+    static const int search_mode = [] {
+        const char *e_ = getenv("BOWGPU_BOUNDS_SEARCH");  // 0 never, 1 always (tests), default: by rows per window
+        return e_ ? atoi(e_) : -1;
+    }();
+    const bool by_search = search_mode == 1 || (search_mode != 0 && gx.n / (gx.W + 1) >= 256);
+    int e = by_search ? launch_bounds_search(B, ctx->stream) : launch_bounds(B, ctx->sm_count, ctx->stream, nullptr, nullptr);
     void *pyr = attach_pyramids(ctx, L, gx.n);
     if (!e) e = launch_interp_windows(L, ctx->stream);
     pool_free(ctx, pyr);

@@ -141,6 +141,31 @@ __global__ void inclusive_bitmap_kernel(const int64_t *time, const int64_t *firs
     if ((lane & 7) == 0 && k < g.W) bitmap[k >> 3] = (uint8_t)(ball >> lane);
 }
 
+// first[k] by one binary search per window instead of one pass over the time column: the same values as bounds_kernel
+// (first row at or beyond S_k among the rows from s0 on; first[0] = 0 unless the rows before s0 are a shard's halo) at
+// (W + 1) * log2(n) scattered loads instead of 8 n streamed bytes — the better deal when windows hold hundreds of rows
+// (configs[2]: 1.1e6 windows over 1e9 rows, 1.28 ms -> see DESIGN 3.2).  No order check: callers use it only where a
+// streaming kernel that checks every row follows (the fused Interpolate -> Aggregate path).
+__global__ void bounds_search_kernel(const __grid_constant__ BoundsLaunch P) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const WindowGeom &g = P.g;
+    if (k > g.W) return;
+    if (k == 0) {
+        P.first[0] = g.shard ? g.early_rows : 0;
+        return;
+    }
+    const uint64_t target = (uint64_t)k * g.div.d;  // S_k - s0
+    int64_t lo = g.early_rows, hi = g.n;
+    while (lo < hi) {
+        const int64_t mid = lo + ((hi - lo) >> 1);
+        if ((uint64_t)P.time[mid] - (uint64_t)g.s0 < target)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    P.first[k] = lo;
+}
+
 __global__ void lower_bound_kernel(const int64_t *time, int64_t n, int64_t x, int64_t *out) {
     int64_t lo = 0, hi = n;
     while (lo < hi) {
@@ -202,6 +227,12 @@ int launch_bounds(const BoundsLaunch &L, int sm_count, cudaStream_t stream, cuda
     if (e0) cudaEventRecord(e0, stream);
     bounds_kernel<<<(unsigned)grid, BND_NT, smem, stream>>>(L, ntiles);
     if (e1) cudaEventRecord(e1, stream);
+    return (int)cudaGetLastError();
+}
+
+int launch_bounds_search(const BoundsLaunch &L, cudaStream_t stream) {
+    const int nt = 128;
+    bounds_search_kernel<<<(unsigned)((L.g.W + 1 + nt - 1) / nt), nt, 0, stream>>>(L);
     return (int)cudaGetLastError();
 }
 

@@ -12,6 +12,7 @@
 //      overlapping its tile into shared memory, every thread binary-searches its row's window there and
 //      copies all columns; validity words are built with ballot, so the bit-granular shift caused by
 //      inserted rows costs nothing.  Balanced by rows, independent of window sizes.
+#include <algorithm>
 #include "../../include/bowgpu.h"
 #include "kernels.h"
 
@@ -94,8 +95,14 @@ __global__ void pyramid_level_kernel(const uint32_t *in, const int64_t nin, uint
     if ((threadIdx.x & 31) == 0 && i < nin) out[i >> 5] = ball;
 }
 
-__global__ void interp_window_kernel(const InterpLaunch P) {
+// One thread per (window, column): blockIdx.y is the column.  The chain of dependent loads of a window (first row, its
+// time, validity words, summary levels, the two points of Linear) is the whole cost of this kernel; one thread walking it
+// for every column in turn took 551 us for 1.1e6 windows x 5 columns (ncu: 44 long-scoreboard stall cycles per issued
+// instruction), a thread per column recomputes the window's header and walks one chain.  The per-window outputs are
+// written by the thread of column 0.
+__global__ void interp_window_kernel(const __grid_constant__ InterpLaunch P) {  // (grid constant: P.cols[j] is read in place; by value the 2.8 KB struct was copied to every thread's stack)
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int jcol = blockIdx.y;
     const WindowGeom &g = P.g;
     if (k >= g.W) return;
     const int64_t *t = P.time;
@@ -111,16 +118,19 @@ __global__ void interp_window_kernel(const InterpLaunch P) {
     // interpolation.go:119-128: the comparison goes through float64
     const int64_t fcv = hi > lo ? f64_to_i64_go((double)t[lo]) : -1;
     const int missing = fcv != Sk;
-    if (P.off) {
-        P.off[k] = (int64_t)missing + (hi - lo);
-        P.wsrc[k] = (lo - missing) * 2 + missing;  // fixed up to "source row - output row" after the scan
+    if (jcol == 0) {
+        if (P.off) {
+            P.off[k] = (int64_t)missing + (hi - lo);
+            P.wsrc[k] = (lo - missing) * 2 + missing;  // fixed up to "source row - output row" after the scan
+        }
+        if (P.missing) P.missing[k] = (uint8_t)missing;
+        // beyond 2^53 a first row NEAR S_k passes the float64 test without sitting exactly on it: the fused
+        // Interpolate -> Aggregate path cannot express that frame and falls back to the materialising one
+        if (!missing && hi > lo && t[lo] != Sk && P.status) atomicOr(P.status, ST_INEXACT_START);
     }
-    if (P.missing) P.missing[k] = (uint8_t)missing;
-    // beyond 2^53 a first row NEAR S_k passes the float64 test without sitting exactly on it: the fused
-    // Interpolate -> Aggregate path cannot express that frame and falls back to the materialising one
-    if (!missing && hi > lo && t[lo] != Sk && P.status) atomicOr(P.status, ST_INEXACT_START);
-    if (!missing) return;
-    for (int j = 0; j < P.ncols; ++j) {
+    if (!missing || jcol >= P.ncols) return;
+    {
+        const int j = jcol;
         const InterpCol &c = P.cols[j];
         uint64_t bits = 0;
         bool valid = false;
@@ -412,7 +422,7 @@ int launch_interp_windows(const InterpLaunch &L0, cudaStream_t stream) {
         }
     }
     const int nt = 128;
-    interp_window_kernel<<<(unsigned)((L.g.W + nt - 1) / nt), nt, 0, stream>>>(L);
+    interp_window_kernel<<<dim3((unsigned)((L.g.W + nt - 1) / nt), (unsigned)std::max(1, (int)L.ncols)), nt, 0, stream>>>(L);
     return (int)cudaGetLastError();
 }
 

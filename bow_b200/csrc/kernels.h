@@ -193,6 +193,8 @@ struct BoundsLaunch {
     int32_t *status;
 };
 int launch_bounds(const BoundsLaunch &L, int sm_count, cudaStream_t stream, cudaEvent_t ev0, cudaEvent_t ev1);
+// the same first[] by a binary search per window (no order check): for windows of hundreds of rows
+int launch_bounds_search(const BoundsLaunch &L, cudaStream_t stream);
 // inclusive flags: inc[k] = first[k+1] < n && t[first[k+1]] == S_{k+1}; bitmap of ceil(W/8) bytes
 int launch_inclusive_bitmap(const int64_t *time, const int64_t *first, WindowGeom g, uint8_t *bitmap,
                             cudaStream_t stream);

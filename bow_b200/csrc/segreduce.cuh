@@ -78,6 +78,9 @@ constexpr bool SEG_SWZ = SEG_CFG_SWZ != 0;
 #ifndef SEG_CFG_LINEAR
 #define SEG_CFG_LINEAR 1
 #endif
+#ifndef SEG_CFG_WARPSYNC
+#define SEG_CFG_WARPSYNC 2  // 0 never, 1 every instantiation, 2 the fused integral kernels only (see the kernel)
+#endif
 constexpr int SEG_UNROLL = SEG_CFG_UNROLL;  // row pairs per trip of the streaming loop
 constexpr int SEG_NT = SEG_CFG_NT;
 constexpr int SEG_P = 16;                     // rows per phase (box start columns must be 16-byte aligned in global memory)
@@ -629,6 +632,7 @@ __global__ void __launch_bounds__(SEG_NT, MIN_CTAS)
                      const __grid_constant__ CUtensorMap tm_val, const int64_t ntiles, const int nstages) {
     extern __shared__ __align__(SEG_SLOT_ALIGN) uint8_t smem_raw[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);                    // [SEG_MAX_STAGES]
+    int *done = reinterpret_cast<int *>(smem_raw + 32);                         // [SEG_MAX_STAGES] warps through with a slot
     WarpEdge *wedge = reinterpret_cast<WarpEdge *>(smem_raw + 64);              // [SEG_NW]
     WarpTotal<Pol> *wtot = reinterpret_cast<WarpTotal<Pol> *>(smem_raw + 64 + SEG_NW * sizeof(WarpEdge));
     static_assert(64 + SEG_NW * (sizeof(WarpEdge) + sizeof(WarpTotal<Pol>)) <= SEG_HEADER_MIN, "header layout");
@@ -638,6 +642,7 @@ __global__ void __launch_bounds__(SEG_NT, MIN_CTAS)
 
     const int tid = threadIdx.x;
     const WindowGeom &g = A.g;
+    constexpr bool WARP_SYNC = SEG_CFG_WARPSYNC == 1 || (SEG_CFG_WARPSYNC == 2 && FUSED && Pol::LINEAR_PHASE);
     const int64_t bitmap_total = ((g.n + 7) / 8 + 15) & ~(int64_t)15;  // device bitmaps are padded to 16 bytes
 
     auto tile_full = [&](int64_t tile) {  // staged by TMA: whole tile + one more row exist, no row before s0
@@ -667,6 +672,7 @@ __global__ void __launch_bounds__(SEG_NT, MIN_CTAS)
 
     if (tid == 0) {
         for (int s = 0; s < nstages; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < SEG_MAX_STAGES; ++s) done[s] = 0;
         fence_mbar_init();
         fence_proxy_async();
     }
@@ -745,9 +751,27 @@ __global__ void __launch_bounds__(SEG_NT, MIN_CTAS)
                 e._pad = 0;
                 wedge[tid >> 5] = e;
             }
-            __syncthreads();  // every read of this slot is done
-            if (tid == 0) issue_item(q + nstages);
+            // WARP_SYNC: a slot is refilled by whichever warp lets go of it LAST (a counter per slot), not behind a CTA-wide
+            // barrier per phase: a warp that met a window boundary in this phase no longer holds up the other three (they
+            // run ahead by up to nstages - 1 phases).  Tiles staged by plain loads keep the barrier.  Measured on B200
+            // (gpurun_out/s19_*): the fused integral kernel gains 12 % (configs[2] fused 15.1 -> 13.3 ms), the DRAM-bound
+            // instantiations lose 3 % (their lock step keeps the DRAM pages of a tile together) - so it is on for the
+            // former only.
+            if (WARP_SYNC && fullt) {
+                __syncwarp();
+                if ((tid & 31) == 0) {
+                    __threadfence_block();
+                    if (atomicAdd(&done[s], 1) == SEG_NW - 1) {
+                        done[s] = 0;
+                        issue_item(q + nstages);
+                    }
+                }
+            } else {
+                __syncthreads();  // every read of this slot is done
+                if (tid == 0) issue_item(q + nstages);
+            }
         }
+        if (WARP_SYNC) __syncthreads();  // every warp is through the tile's phases and has published its first row (wedge)
         if (FUSED) seg_resolve_deferred<Pol>(c, A, &finc);
         if (FUSED && SEG_CFG_FUSED_COLD == 2) {
             c.head = fhead;
