@@ -95,6 +95,25 @@ __global__ void pyramid_level_kernel(const uint32_t *in, const int64_t nin, uint
     if ((threadIdx.x & 31) == 0 && i < nin) out[i >> 5] = ball;
 }
 
+// the first level reads the validity bitmap itself (n / 8 bytes): four words per thread (one 16-byte load), eight threads
+// share an output word.  The bitmap is padded with zero bytes to a multiple of 16 (DevCol).
+__global__ void pyramid_level4_kernel(const uint4 *in, const int64_t nin /* words */, uint32_t *out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    uint32_t nib = 0;
+    if (4 * i < nin) {
+        const uint4 w = in[i];
+        nib = (w.x != 0 ? 1u : 0u) | (w.y != 0 ? 2u : 0u) | (w.z != 0 ? 4u : 0u) | (w.w != 0 ? 8u : 0u);
+        const int64_t left = nin - 4 * i;  // (only the words of the bitmap count, whatever the padding holds)
+        if (left < 4) nib &= (1u << left) - 1u;
+    }
+    uint32_t v = nib << (4 * (lane & 7));
+    v |= __shfl_xor_sync(0xffffffffu, v, 1);
+    v |= __shfl_xor_sync(0xffffffffu, v, 2);
+    v |= __shfl_xor_sync(0xffffffffu, v, 4);
+    if ((lane & 7) == 0 && 4 * i < nin) out[i >> 3] = v;
+}
+
 // One thread per (window, column): blockIdx.y is the column.  The chain of dependent loads of a window (first row, its
 // time, validity words, summary levels, the two points of Linear) is the whole cost of this kernel; one thread walking it
 // for every column in turn took 551 us for 1.1e6 windows x 5 columns (ncu: 44 long-scoreboard stall cycles per issued
@@ -416,7 +435,12 @@ int launch_interp_windows(const InterpLaunch &L0, cudaStream_t stream) {
         int64_t nin = (L.g.n + 31) / 32;
         for (int l = 0; l < L.pyr.nlev; ++l) {
             uint32_t *out = c.summary + L.pyr.off[l];
-            pyramid_level_kernel<<<(unsigned)((nin + 255) / 256), 256, 0, stream>>>(in, nin, out);
+            if (l == 0 && ((uintptr_t)in & 15) == 0) {
+                const int64_t groups = (nin + 3) / 4;
+                pyramid_level4_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const uint4 *>(in), nin, out);
+            } else {
+                pyramid_level_kernel<<<(unsigned)((nin + 255) / 256), 256, 0, stream>>>(in, nin, out);
+            }
             in = out;
             nin = L.pyr.words[l];
         }
