@@ -1515,6 +1515,14 @@ static int side_width() {
     }();
     return k;
 }
+// one launch for both aggregation families of a column (seg_full.cu); BOWGPU_SEG_MERGE=0 keeps them apart
+static bool merge_families() {
+    static const bool on = [] {
+        const char *e = getenv("BOWGPU_SEG_MERGE");
+        return !e || atoi(e) != 0;
+    }();
+    return on;
+}
 static int32_t ensure_side(bowgpu_ctx *ctx, int k) {
     if (k <= 1) return BOWGPU_OK;
     if (!ctx->side_fork) CK(cudaEventCreateWithFlags(&ctx->side_fork, cudaEventDisableTiming));
@@ -1577,10 +1585,10 @@ static int32_t aggregate_core(bowgpu_rolling *r, const bowgpu_agg_spec *specs, i
     int32_t rc = ensure_side(ctx, K);
     if (rc) return rc;
     const size_t wv = align_up((size_t)W * 8, 256), wb = align_up((size_t)((W + 7) / 8) + 16, 256);
-    const size_t carry_bytes = align_up(std::max(seg_carry_bytes(g.n), integral_carry_bytes(g.n)), 256);
-    const size_t skip_bytes = align_up(std::max(seg_skip_bytes(g.n), integral_skip_bytes(g.n)) + 256, 256);
+    const size_t carry_bytes = align_up(std::max(std::max(seg_carry_bytes(g.n), integral_carry_bytes(g.n)), full_carry_bytes(g.n)), 256);
+    const size_t skip_bytes = align_up(std::max(std::max(seg_skip_bytes(g.n), integral_skip_bytes(g.n)), full_skip_bytes(g.n)) + 256, 256);
     size_t need = 8192 + 256 * (size_t)(n_basic_cols + n_int_cols + 2) + (size_t)K * (skip_bytes + carry_bytes + 512) + (size_t)n_basic_cols * 2 * (wv + 256) +
-                  (size_t)n_int_cols * 4 * (wv + 256);
+                  (size_t)n_int_cols * 6 * (wv + 256);
     if (mem == BOWGPU_MEM_HOST) need += (size_t)nspecs * (wv + wb);
     rc = arena_reserve(ctx, need);
     if (rc) return rc;
@@ -1624,6 +1632,9 @@ static int32_t aggregate_core(bowgpu_rolling *r, const bowgpu_agg_spec *specs, i
             for (int o = 0; o < BOWGPU_AGG__COUNT; ++o)
                 if (count[o]) any_basic |= agg_is_basic(o), any_int |= agg_is_integral(o);
             if (!(fam == 0 ? any_basic : any_int)) continue;
+            // a column with aggregations of BOTH families: one merged launch (seg_full.cu) in the first pass
+            const bool both = any_basic && any_int && merge_families();
+            if (fam == 1 && both) continue;
             // ---- the lane this launch runs on
             if (lane == width) {  // open a wave (the main stream has already been told to wait for the previous one)
                 width = std::min(K, left);
@@ -1661,7 +1672,71 @@ static int32_t aggregate_core(bowgpu_rolling *r, const bowgpu_agg_spec *specs, i
                 }
                 return BOWGPU_OK;
             };
-            if (fam == 0) {
+            if (fam == 0 && both) {
+                FullLaunch L;
+                memset(&L, 0, sizeof L);
+                L.time = (const int64_t *)f->cols[r->time_col].values;
+                L.values = dc.values;
+                L.validity = dc.validity;
+                L.is_int = dc.dtype == BOWGPU_INT64;
+                L.g = g;
+                L.carry_head = carry;
+                L.carry_tail = carry + full_carry_bytes(g.n) / 2;
+                L.skip = skip;
+                L.status = ctx->d_status;
+                if (syn_by_col) L.syn = syn_by_col[c];
+                L.gate = gate;
+                L.gate_lanes = width;
+                int64_t *cnt = nullptr;
+                if (primary[BOWGPU_AGG_COUNT] >= 0 && specs[primary[BOWGPU_AGG_COUNT]].nfactors == 0)
+                    cnt = (int64_t *)dvals[primary[BOWGPU_AGG_COUNT]];
+                else
+                    cnt = (int64_t *)arena_take(ctx, wv);
+                CK(cudaMemsetAsync(cnt, 0, (size_t)W * 8, st));
+                L.out_basic.cnt = cnt;
+                double *sum_dst = pick_dst(BOWGPU_AGG_SUM, BOWGPU_AGG_MEAN);
+                L.out_basic.sum = sum_dst;
+                L.out_basic.mn = (double *)prim(BOWGPU_AGG_MIN);
+                L.out_basic.mx = (double *)prim(BOWGPU_AGG_MAX);
+                L.out_basic.first = (uint64_t *)prim(BOWGPU_AGG_FIRST);
+                L.out_basic.last = (uint64_t *)prim(BOWGPU_AGG_LAST);
+                // the merged kernel always forms both integrals: the ones nobody asked for land in scratch
+                L.out_integral.n_step = (int64_t *)arena_take(ctx, wv);
+                L.out_integral.n_trap = (int64_t *)arena_take(ctx, wv);
+                CK(cudaMemsetAsync(L.out_integral.n_step, 0, (size_t)W * 8, st));
+                CK(cudaMemsetAsync(L.out_integral.n_trap, 0, (size_t)W * 8, st));
+                double *step_dst = pick_dst(BOWGPU_AGG_INTEGRAL_STEP, BOWGPU_AGG_WAVG_STEP);
+                double *trap_dst = pick_dst(BOWGPU_AGG_INTEGRAL_TRAPEZOID, BOWGPU_AGG_WAVG_LINEAR);
+                L.out_integral.step = step_dst ? step_dst : (double *)arena_take(ctx, wv);
+                L.out_integral.trap = trap_dst ? trap_dst : (double *)arena_take(ctx, wv);
+                if (!L.out_integral.n_step || !L.out_integral.n_trap || !L.out_integral.step || !L.out_integral.trap)
+                    return fail(ctx, BOWGPU_ENOMEM, "aggregate: scratch");
+                cudaEvent_t e0, e1;
+                timing_main_pair(ctx, &e0, &e1);
+                CK(launch_segreduce_full(L, sm_share, st, e0, e1));
+                count_launch(ctx, 1, true);
+                count_launch(ctx, 1);
+                if ((rc = copy_dups(BOWGPU_AGG_COUNT, cnt))) return rc;
+                if ((rc = copy_dups(BOWGPU_AGG_SUM, sum_dst))) return rc;
+                for (int op : {BOWGPU_AGG_MIN, BOWGPU_AGG_MAX, BOWGPU_AGG_FIRST, BOWGPU_AGG_LAST})
+                    if ((rc = copy_dups(op, prim(op)))) return rc;
+                if ((rc = copy_dups(BOWGPU_AGG_INTEGRAL_STEP, step_dst))) return rc;
+                if ((rc = copy_dups(BOWGPU_AGG_INTEGRAL_TRAPEZOID, trap_dst))) return rc;
+                for (int j = 0; j < nspecs; ++j) {
+                    if (specs[j].col != c) continue;
+                    if (agg_is_basic(specs[j].op)) {
+                        spec_cnt[j] = cnt;
+                        if (specs[j].op == BOWGPU_AGG_MEAN) spec_src[j] = sum_dst;
+                    }
+                    switch (specs[j].op) {
+                    case BOWGPU_AGG_INTEGRAL_STEP: spec_cnt[j] = L.out_integral.n_step; break;
+                    case BOWGPU_AGG_INTEGRAL_TRAPEZOID: spec_cnt[j] = L.out_integral.n_trap; break;
+                    case BOWGPU_AGG_WAVG_STEP: spec_cnt[j] = L.out_integral.n_step, spec_src[j] = L.out_integral.step; break;
+                    case BOWGPU_AGG_WAVG_LINEAR: spec_cnt[j] = L.out_integral.n_trap, spec_src[j] = L.out_integral.trap; break;
+                    default: break;
+                    }
+                }
+            } else if (fam == 0) {
                 SegLaunch L;
                 memset(&L, 0, sizeof L);
                 L.time = (const int64_t *)f->cols[r->time_col].values;

@@ -116,6 +116,27 @@ struct IntLaunch {
 };
 size_t integral_carry_bytes(int64_t n);
 size_t integral_skip_bytes(int64_t n);
+
+// ---- both families of one column in one launch (seg_full.cu) -------------------------------------------
+struct FullLaunch {
+    const int64_t *time;
+    const uint64_t *values;
+    const uint8_t *validity;
+    int32_t is_int;
+    WindowGeom g;
+    BasicOut out_basic;        // cnt is required (zeroed by the caller); the other pointers may be null
+    IntegralOut out_integral;  // all four arrays required (n_step / n_trap zeroed by the caller)
+    void *carry_head;          // [ntiles] of full_carry_bytes(n) / 2
+    void *carry_tail;
+    void *skip;                // full_skip_bytes(n) or null
+    int32_t *status;
+    FusedSyn syn;
+    int32_t *gate;
+    int32_t gate_lanes;
+};
+size_t full_carry_bytes(int64_t n);
+size_t full_skip_bytes(int64_t n);
+int launch_segreduce_full(const FullLaunch &L, int sm_count, cudaStream_t stream, cudaEvent_t ev_main0, cudaEvent_t ev_main1);
 int launch_segreduce_integral(const IntLaunch &L, int sm_count, cudaStream_t stream, cudaEvent_t ev_main0,
                               cudaEvent_t ev_main1);
 
