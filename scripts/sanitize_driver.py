@@ -11,19 +11,23 @@ import numpy as np  # noqa: E402
 
 from bow_b200 import native as N  # noqa: E402
 from oracle import refc as R  # noqa: E402
+from tests import helpers as H  # noqa: E402
 
 ALL = ["WindowStart", "Count", "Sum", "ArithmeticMean", "Min", "Max", "First", "Last", "IntegralStep", "IntegralTrapezoid",
        "WeightedAverageStep", "WeightedAverageLinear"]
 
 
-def close(a, b, name):
+TOL_OPS = {"Sum", "ArithmeticMean", "IntegralStep", "IntegralTrapezoid", "WeightedAverageStep", "WeightedAverageLinear"}
+
+
+def close(a, b, name, spec=None, scales=None):
+    """bit-exact, or - float reductions - within the stated class |gpu - ref| <= 1e-12 * max(|ref|, sum|terms|)"""
     (gv, gm), (wv, wm) = a, b
-    assert np.array_equal(gm, wm), name
-    if gv.dtype == np.float64:
-        ok = np.isclose(gv[gm], wv[wm], rtol=1e-9, atol=1e-9, equal_nan=True)
-        assert ok.all(), name
+    assert gv.dtype == wv.dtype and np.array_equal(gm, wm), name
+    if spec is not None and spec[0] in TOL_OPS and not (spec[0] == "Sum" and spec[1] == 2):  # (Sum of the int64 column: exact)
+        H.assert_in_tolerance_class(gv[gm], wv[wm], scales[spec[1]][spec[0]][gm], name)
     else:
-        assert np.array_equal(gv[gm], wv[wm]), name
+        assert np.array_equal(gv[gm].view(np.int64), wv[wm].view(np.int64)), name
 
 
 def main():
@@ -42,15 +46,17 @@ def main():
         got = r.aggregate(specs)
         ref = R.RefRolling(R.Frame(cols), 0, interval, offset=offset)
         want = ref.aggregate(specs)
+        # (the inclusive aggregations force inclusive windows for the whole call, aggregation.go:183-185)
+        scales = {c: H.term_scales(cols, c, interval, offset=offset, inclusive=True) for c in (1, 2)}
         for s, g, w in zip(specs, got, want):
-            close(g, w, f"aggregate {s} interval {interval}")
+            close(g, w, f"aggregate {s} interval {interval}", s, scales)
         ops = ["WindowStart", "Linear", "StepPrevious"]
         got = r.interpolate_aggregate(ops, specs)                 # fused
         fi = r.interpolate(ops)                                   # materialised
         ri = N.Rolling(fi, 0, interval, offset=offset)
         got2 = ri.aggregate(specs)
         for s, g, w in zip(specs, got, got2):
-            close(g, w, f"fused vs materialised {s}")
+            close(g, w, f"fused vs materialised {s}", s, scales)
         ri.close(); fi.close(); r.close()
     fr.aggregate_whole(0, specs)
     for meth in ("Previous", "Next", "Mean"):
@@ -67,8 +73,9 @@ def main():
     hs = [("WindowStart", 0), ("ArithmeticMean", 1), ("Min", 1), ("Max", 1), ("Count", 1), ("IntegralTrapezoid", 1)]
     got = N.aggregate_host(ctx, cols, 0, 50, hs, offset=3, chunk_rows=16384)
     want = R.RefRolling(R.Frame(cols), 0, 50, offset=3).aggregate(hs)
+    scales = {1: H.term_scales(cols, 1, 50, offset=3, inclusive=True)}
     for s, g, w in zip(hs, got, want):
-        close(g, w, f"aggregate_host {s}")
+        close(g, w, f"aggregate_host {s}", s, scales)
     N.interpolate_aggregate_host(ctx, cols, 0, 50, ["WindowStart", "Linear", "StepPrevious"], hs, offset=3, chunk_rows=16384)
     # parquet ingest: the reference-written fixtures (Snappy, optional columns)
     gold = os.path.join(ROOT, "tests", "golden", "parquet")
