@@ -74,3 +74,43 @@ def test_nested_schema_is_refused(tmp_path):
     with pytest.raises(N.BowGpuError) as e:
         N.ParquetFile(path)
     assert e.value.status == "EUNSUPPORTED"
+
+
+@pytest.mark.parametrize("opts", [dict(compression="SNAPPY", use_dictionary=False), dict(compression="NONE", use_dictionary=True),
+                                  dict(compression="SNAPPY", use_dictionary=True, data_page_version="2.0", data_page_size=4096,
+                                       row_group_size=7000)])
+def test_page_walk_sizes_follow_the_metadata(tmp_path, opts):
+    """the host-side page walk (bowgpu_parquet_plan: what sizes the device buffers) against pyarrow's column-chunk metadata"""
+    rng = np.random.default_rng(2)
+    n = 20_000
+    t = pa.table({"t": pa.array(np.arange(n, dtype=np.int64) * 1000),
+                  "v": pa.array(rng.normal(size=n), mask=rng.random(n) < 0.25),
+                  "k": pa.array(rng.integers(0, 9, n).astype(np.int64), mask=rng.random(n) < 0.5),
+                  "s": pa.array(["x"] * n)})
+    path = str(tmp_path / "p.parquet")
+    pq.write_table(t, path, **opts)
+    meta = pq.ParquetFile(path).metadata
+    comp = uncomp = 0
+    for g in range(meta.num_row_groups):
+        for c in range(3):   # t, v, k
+            col = meta.row_group(g).column(c)
+            comp += col.total_compressed_size
+            uncomp += col.total_uncompressed_size
+    with N.ParquetFile(path) as pf:
+        p = pf.plan([0, 1, 2])
+        chunks = 3 * meta.num_row_groups
+        assert comp <= p["image_bytes"] <= comp + 32 * chunks + 64           # every chunk as stored, 16-byte padded
+        if opts["compression"] == "SNAPPY":                                    # page bodies once uncompressed (headers excluded)
+            assert 0 < p["scratch_bytes"] <= uncomp + 32 * p["pages"] + 64
+        else:
+            assert p["scratch_bytes"] == 64
+        if opts["use_dictionary"]:
+            assert 0 < p["aux_entries"] <= 3 * n                              # one index per value of a dictionary-encoded page
+        else:
+            assert p["aux_entries"] == 0
+        assert p["pages"] >= chunks
+        one = pf.plan([1])
+        assert one["pages"] < p["pages"] and one["image_bytes"] < p["image_bytes"]
+        with pytest.raises(N.BowGpuError) as e:
+            pf.plan([3])
+        assert e.value.status == "ETYPE"
