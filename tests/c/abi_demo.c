@@ -19,7 +19,7 @@
         }                                                                                             \
     } while (0)
 
-int main(void) {
+int main(int argc, char **argv) {
     bowgpu_ctx *ctx = NULL;
     if (bowgpu_abi_version() != BOWGPU_ABI_VERSION) return 3;
     int32_t st = bowgpu_ctx_create(0, NULL, &ctx);
@@ -106,11 +106,61 @@ int main(void) {
     }
     printf("sort: %s\n", sbad ? "MISMATCH" : "ok");
 
+    /* NewBowFromParquet (bowparquet.go:44-155): a file written by the reference's own writer (benchmarks/bow1-10-rows.parquet,
+     * SNAPPY + PLAIN + 3-row pages), three of its numeric columns decoded on the device, then IntervalRolling(Int64_ref, 10)
+     * + Count over the decoded frame without a host round trip */
+    int pbad = 0;
+    if (argc > 1) {
+        bowgpu_parquet *pq = NULL;
+        char msg[256];
+        CHECK(bowgpu_parquet_open(argv[1], &pq, msg, (int32_t)sizeof msg));
+        int32_t idx[3] = {-1, -1, -1};
+        const char *want_names[3] = {"Int64_ref", "Int64_bow1", "Float64_bow1"};
+        for (int32_t j = 0; j < bowgpu_parquet_num_cols(pq); ++j)
+            for (int c = 0; c < 3; ++c)
+                if (strcmp(bowgpu_parquet_col_name(pq, j), want_names[c]) == 0) idx[c] = j;
+        pbad |= idx[0] < 0 || idx[1] < 0 || idx[2] < 0 || bowgpu_parquet_num_rows(pq) != 10;
+        pbad |= bowgpu_parquet_col_dtype(pq, idx[0]) != BOWGPU_INT64 || bowgpu_parquet_col_dtype(pq, idx[2]) != BOWGPU_FLOAT64;
+        bowgpu_frame *pf = NULL;
+        CHECK(bowgpu_parquet_read(ctx, pq, idx, 3, &pf));
+        int64_t pt[10], pi[10];
+        double pv[10];
+        uint8_t pb[3][2];
+        bowgpu_out_col pd[3] = {{pt, pb[0], 0, 0}, {pi, pb[1], 0, 0}, {pv, pb[2], 0, 0}};
+        CHECK(bowgpu_frame_download(pf, pd, 3));
+        const int64_t want_t[10] = {3, 18, 28, 32, 42, 55, 63, 73, 89, 92};
+        const int64_t want_i[10] = {8, 0, 0, 6, 5, 0, 0, 1, 0, 0};
+        const double want_v[10] = {5.5, 9.5, 0.5, 8.5, 0, 5.5, 9.5, 0, 6.5, 0};
+        for (int i = 0; i < 10; ++i) pbad |= pt[i] != want_t[i] || pi[i] != want_i[i] || pv[i] != want_v[i];
+        pbad |= pb[1][0] != 0x99 || (pb[1][1] & 3) != 0x00 || pb[2][0] != 0x6F || (pb[2][1] & 3) != 0x01;
+        pbad |= bowgpu_frame_col_null_count(pf, 0) != 0 || bowgpu_frame_col_null_count(pf, 1) != 6 || bowgpu_frame_col_null_count(pf, 2) != 3;
+        bowgpu_rolling *pr = NULL;
+        CHECK(bowgpu_rolling_create(pf, 0, 10, 0, 0, NULL, &pr));
+        const int64_t PW = bowgpu_rolling_num_windows(pr); /* windows [0,10) .. [90,100) */
+        pbad |= PW != 10;
+        if (!pbad) {
+            bowgpu_agg_spec ps[2];
+            memset(ps, 0, sizeof ps);
+            ps[0].op = BOWGPU_AGG_WINDOW_START, ps[0].col = 0;
+            ps[1].op = BOWGPU_AGG_COUNT, ps[1].col = 2;
+            int64_t pws[10], pc[10];
+            uint8_t pm[2][2];
+            bowgpu_out_col po[2] = {{pws, pm[0], 0, 0}, {pc, pm[1], 0, 0}};
+            CHECK(bowgpu_rolling_aggregate(pr, ps, 2, po, BOWGPU_MEM_HOST));
+            const int64_t want_c[10] = {1, 1, 1, 1, 0, 1, 1, 0, 1, 0};
+            for (int k = 0; k < 10; ++k) pbad |= pws[k] != 10 * k || pc[k] != want_c[k];
+        }
+        bowgpu_rolling_destroy(pr);
+        bowgpu_frame_destroy(pf);
+        bowgpu_parquet_close(pq);
+        printf("parquet: %s\n", pbad ? "MISMATCH" : "ok");
+    }
+
     bowgpu_frame_destroy(sorted);
     bowgpu_frame_destroy(unsorted);
     bowgpu_frame_destroy(fi);
     bowgpu_rolling_destroy(r);
     bowgpu_frame_destroy(frame);
     bowgpu_ctx_destroy(ctx);
-    return (bad || ibad || sbad) ? 1 : 0;
+    return (bad || ibad || sbad || pbad) ? 1 : 0;
 }

@@ -14,6 +14,8 @@ def test_c_consumer_runs(tmp_path):
     subprocess.check_call(["gcc", "-O2", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "abi_demo.c"),
                            "-o", str(exe), "-L", os.path.join(ROOT, "bow_b200"), "-lbowgpu",
                            "-Wl,-rpath," + os.path.join(ROOT, "bow_b200"), "-lm"])
-    p = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    fixture = os.path.join(ROOT, "tests", "golden", "parquet", "bow1-10-rows.parquet")
+    p = subprocess.run([str(exe), fixture], capture_output=True, text=True, timeout=120)
     assert p.returncode == 0, p.stdout + p.stderr
     assert "aggregate: ok" in p.stdout and "interpolate: ok" in p.stdout and "sort: ok" in p.stdout
+    assert "parquet: ok" in p.stdout
