@@ -14,7 +14,7 @@ def test_c_consumer_runs(tmp_path):
     subprocess.check_call(["gcc", "-O2", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "abi_demo.c"),
                            "-o", str(exe), "-L", os.path.join(ROOT, "bow_b200"), "-lbowgpu",
                            "-Wl,-rpath," + os.path.join(ROOT, "bow_b200"), "-lm"])
-    fixture = os.path.join(ROOT, "tests", "golden", "parquet", "bow1-10-rows.parquet")
+    fixture = os.path.join(ROOT, "tests", "golden", "parquet", "refwriter_bow1_10_rows.parquet")
     p = subprocess.run([str(exe), fixture], capture_output=True, text=True, timeout=120)
     assert p.returncode == 0, p.stdout + p.stderr
     assert "aggregate: ok" in p.stdout and "interpolate: ok" in p.stdout and "sort: ok" in p.stdout

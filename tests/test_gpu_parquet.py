@@ -70,7 +70,7 @@ def test_config0_fixture_matches_the_npz(ctx):
     """the same file as decoded when the round-1 fixture was made"""
     z = np.load(os.path.join(os.path.dirname(GOLD), "config1_bow1_100000.npz"))
     names = ["Int64_ref", "Int64_no_nils_bow1", "Int64_bow1", "Float64_bow1"]
-    got = check(ctx, os.path.join(GOLD, "bow1-100000-rows.parquet"), names)
+    got = check(ctx, os.path.join(GOLD, "refwriter_bow1_100000_rows.parquet"), names)
     for name, (gv, gm) in zip(names, got):
         assert np.array_equal(gv.view(np.int64), z[name].view(np.int64))
         assert np.array_equal(np.packbits(gm, bitorder="little"), z[name + "__valid"])
@@ -185,7 +185,7 @@ def test_mirror_NewBowFromParquet(ctx, tmp_path):
     from bow_b200 import runtime
     runtime.set_default_ctx(ctx)
     try:
-        path = os.path.join(GOLD, "bow1-1000-rows.parquet")
+        path = os.path.join(GOLD, "refwriter_bow1_1000_rows.parquet")
         names = ["Int64_ref", "Int64_bow1", "Float64_bow1"]
         b = B.NewBowFromParquet(path, colNames=names)
         want = pq.read_table(path, columns=names)
@@ -206,7 +206,7 @@ def test_config0_from_the_parquet_file_stays_on_the_device(ctx, interval):
     IntervalRolling(Int64_ref, 10) -> ArithmeticMean / Count / Min / Max), file -> device frame -> Aggregate without a
     host round trip, against the oracle on the independently decoded columns."""
     from oracle import refc as R
-    path = os.path.join(GOLD, "bow1-100000-rows.parquet")
+    path = os.path.join(GOLD, "refwriter_bow1_100000_rows.parquet")
     names = ["Int64_ref", "Int64_bow1", "Float64_bow1"]
     with N.ParquetFile(path) as pf:
         fr = pf.read(ctx, [pf.names.index(n) for n in names])

@@ -39,7 +39,7 @@ def test_reference_written_files(name):
 
 def test_config0_file_equals_the_round1_fixture():
     z = np.load(os.path.join(os.path.dirname(GOLD), "config1_bow1_100000.npz"))
-    got = P.read_parquet(os.path.join(GOLD, "bow1-100000-rows.parquet"))
+    got = P.read_parquet(os.path.join(GOLD, "refwriter_bow1_100000_rows.parquet"))
     for name in ("Int64_ref", "Int64_no_nils_bow1", "Int64_bow1", "Float64_bow1"):
         gv, gm = got[name]
         assert np.array_equal(gv.view(np.int64), z[name].view(np.int64))
