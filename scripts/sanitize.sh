@@ -1,5 +1,5 @@
 #!/bin/bash
-# compute-sanitizer over scripts/sanitize_driver.py (every kernel family, small inputs) -> gpurun_out/sanitizer_<tag>.txt
+# compute-sanitizer over tests/kernel_driver.py (every kernel family, small inputs) -> gpurun_out/sanitizer_<tag>.txt
 tag=${1:-r2}
 out=gpurun_out/sanitizer_$tag.txt
 mkdir -p gpurun_out
@@ -10,7 +10,7 @@ run() {  # <label> <env...> -- <tool args...>
   while [ "$1" != "--" ]; do envs+=("$1"); shift; done
   shift
   echo "== $label: env ${envs[*]} compute-sanitizer $*" >> $out
-  env "${envs[@]}" timeout 1500 compute-sanitizer "$@" python scripts/sanitize_driver.py 2>&1 | grep -E "sanitize driver|ERROR SUMMARY|RACECHECK SUMMARY|=========     at |========= Invalid|========= Uninit|========= Error|hazard|Traceback|Error|assert" | head -40 >> $out
+  env "${envs[@]}" timeout 1500 compute-sanitizer "$@" python tests/kernel_driver.py 2>&1 | grep -E "sanitize driver|ERROR SUMMARY|RACECHECK SUMMARY|=========     at |========= Invalid|========= Uninit|========= Error|hazard|Traceback|Error|assert" | head -40 >> $out
 }
 run "memcheck (default path)" SAN_ROWS=120000 -- --tool memcheck
 run "memcheck (side-by-side lanes)" SAN_ROWS=120000 BOWGPU_SEG_SIDE=3 -- --tool memcheck
