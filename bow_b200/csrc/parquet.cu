@@ -373,7 +373,10 @@ void walk_chunk(const PqFile *f, ChunkWalk &w) {
         TReader r(f->map + pos, f->map + end);
         PageHeader h;
         parse_page_header(r, h);
-        if (!r.ok || h.compressed < 0 || h.uncompressed < 0 || (r.p - f->map) + h.compressed > end) return bail(BOWGPU_EIO, "malformed page header");
+        // (a page is a few KB to a few MB; a header that claims more than 1 GiB uncompressed is damage, not data)
+        if (!r.ok || h.compressed < 0 || h.uncompressed < 0 || h.uncompressed > (1 << 30) || h.num_values < 0 ||
+            (r.p - f->map) + h.compressed > end)
+            return bail(BOWGPU_EIO, "malformed page header");
         const int64_t body = r.p - f->map;
         pos = body + h.compressed;
         if (h.type != 0 && h.type != 2 && h.type != 3) continue;  // index pages: skipped
